@@ -1,0 +1,227 @@
+#!/usr/bin/env python3
+"""Generate the golden fixtures under tests/golden/ from the UNMODIFIED reference.
+
+Run in the authoring container only (it needs /root/reference; the GPU box does not
+have it):   python tests/golden/make_golden.py
+
+The reference class is imported read-only from /root/reference/src/nets/qpnet.py and
+driven through its public entry points (``forward``, ``batch_fast_generate``,
+``_dilated_index``, ``_generate_dilated_index``, ``encode_mu_law``, ``decode_mu_law``).
+Parameters come from ``oracle.qpnet_oracle.init_params`` (deterministic, seeded) and
+are loaded with ``load_state_dict`` so that tests can rebuild the identical model
+without the reference.  ``Categorical.sample`` is replaced, for the sampling fixtures
+only, by an inverse-CDF draw on pre-drawn uniforms (the reference's global-RNG
+multinomial cannot be shared with another implementation).
+"""
+import os
+import sys
+import warnings
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, "/root/reference/src/nets")
+warnings.filterwarnings("ignore")
+
+import qpnet as ref  # noqa: E402  (the reference)
+from oracle import qpnet_oracle as orc  # noqa: E402
+from qpnet_b200 import synth  # noqa: E402
+
+torch.set_num_threads(8)
+torch.manual_seed(0)
+
+
+def ref_model(arch_kw, params):
+    m = ref.QPNet(**arch_kw)
+    m.load_state_dict(params)
+    m.eval()
+    return m
+
+
+def d_from_f0(f0, f32=False):
+    d = orc.extend_time(orc.dilated_factor(f0, synth.FS, synth.DENSE_FACTOR), synth.UPSAMPLING)
+    return d.astype(np.float32) if f32 else d
+
+
+# ---------------------------------------------------------------- G1: indices
+def golden_indices():
+    tiny = ref.QPNet(n_resch=4, n_skipch=4)
+    out = {}
+    for factor in (1.0, 0.5, 1.5):
+        for n in (1100, 20020, 30030):
+            frames = n // synth.UPSAMPLING
+            f0 = np.stack([synth.f0_contour(frames, u) * factor for u in (0, 1)])
+            d64 = np.stack([d_from_f0(f) for f in f0])
+            d32 = torch.from_numpy(d64).float()
+            for dil in (1, 2, 4, 8):
+                key = f"f{factor}_n{n}_d{dil}"
+                a = tiny._dilated_index(d32, dil, 1, True)[:, 0].numpy()
+                b = tiny._dilated_index(d64, dil, 1, False)[:, 0]
+                c = tiny._generate_dilated_index(d32, dil, 1, True)[:, 0].numpy()
+                e = tiny._generate_dilated_index(d64, dil, 1, False)[:, 0]
+                pos = np.arange(-n, 0)
+                out[key + "_tf32"] = (a - pos).astype(np.int16)   # store look-back, compresses well
+                out[key + "_tf64"] = (b - pos).astype(np.int16)
+                out[key + "_g32"] = c.astype(np.int16)
+                out[key + "_g64"] = e.astype(np.int16)
+    np.savez_compressed(os.path.join(HERE, "indices.npz"), **out)
+    print("indices:", len(out), "arrays")
+
+
+# ---------------------------------------------------------------- G2/G3: forward + grads
+def tf_case(arch_kw, seed, bias_std, frames, bl, f0_factor=1.0, grads=False):
+    a = orc.Arch(**arch_kw)
+    p = orc.init_params(a, seed, bias_std)
+    m = ref_model(arch_kw, p)
+    hs, f0, _ = synth.utterance(frames, seed, f0_factor, a.A)
+    T = frames * a.U
+    d = torch.from_numpy(d_from_f0(f0)).float()[None, :T]
+    rs = np.random.RandomState(seed)
+    x = torch.from_numpy(rs.randint(0, a.Q, size=(1, T))).long()
+    t = torch.from_numpy(rs.randint(0, a.Q, size=(1, bl))).long()
+    h = torch.from_numpy(hs.T.copy())[None]
+    logits = m(x, h, d, torch.tensor([bl]))
+    res = {"logits": logits.detach().numpy()[0]}
+    if grads:
+        loss = torch.nn.functional.cross_entropy(logits.reshape(-1, a.Q), t.reshape(-1))
+        loss.backward()
+        res["loss"] = np.float32(loss.item())
+        for name, prm in m.named_parameters():
+            res["grad/" + name] = (prm.grad.numpy() if prm.grad is not None
+                                   else np.zeros(0, np.float32))
+        res["target"] = t.numpy()[0]
+    res["x"] = x.numpy()[0].astype(np.int16)
+    return res
+
+
+SMALL = dict(n_resch=32, n_skipch=16)
+FULL = dict()
+
+
+def golden_forward():
+    out = {}
+    cases = [("small_s1_b0", SMALL, 1, 0.0, 12, 330, 1.0, True),
+             ("small_s2_b1", SMALL, 2, 0.1, 14, 330, 1.0, True),
+             ("small_s3_b1_f05", SMALL, 3, 0.1, 22, 220, 0.5, False),
+             ("full_s4_b1", FULL, 4, 0.05, 12, 330, 1.0, False)]
+    for name, kw, seed, bstd, frames, bl, fac, grads in cases:
+        r = tf_case(kw, seed, bstd, frames, bl, fac, grads)
+        for k, v in r.items():
+            out[f"{name}/{k}"] = v
+        out[f"{name}/meta"] = np.array([seed, frames, bl], np.int64)
+        out[f"{name}/meta_f"] = np.array([bstd, fac], np.float64)
+        print("forward", name, r["logits"].shape, float(np.abs(r["logits"]).max()))
+    np.savez_compressed(os.path.join(HERE, "forward.npz"), **out)
+
+
+# ---------------------------------------------------------------- G4: generation
+class _ShimCategorical:
+    """Inverse-CDF stand-in for torch.distributions.Categorical (sampling fixtures)."""
+    uniforms = None
+    step = 0
+    rows = None
+
+    def __init__(self, probs):
+        self.probs = probs
+
+    def sample(self):
+        cls = _ShimCategorical
+        u = cls.uniforms[cls.rows_alive(), cls.step]
+        cdf = torch.cumsum(self.probs, dim=-1)
+        k = torch.searchsorted(cdf, u.reshape(-1, 1).to(cdf.dtype), right=True).reshape(-1)
+        cls.step += 1
+        return torch.clamp(k, max=self.probs.shape[-1] - 1)
+
+    @classmethod
+    def rows_alive(cls):
+        return cls.rows
+
+
+def gen_case(arch_kw, seed, bias_std, frames_list, mode, extra_memory, f0_factor=1.0):
+    a = orc.Arch(**arch_kw)
+    p = orc.init_params(a, seed, bias_std)
+    m = ref_model(arch_kw, p)
+    B = len(frames_list)
+    Fmax = max(frames_list)
+    h = np.zeros((B, a.A, Fmax), np.float32)
+    d = np.zeros((B, Fmax * a.U), np.float64)
+    n_list = []
+    for b, fr in enumerate(frames_list):
+        hs, f0, n = synth.utterance(fr, 100 * seed + b, f0_factor, a.A)
+        h[b, :, :fr] = hs.T
+        d[b, : fr * a.U] = d_from_f0(f0)
+        n_list.append(n)
+    x = torch.full((B, 1), a.Q // 2, dtype=torch.long)
+    g = torch.Generator().manual_seed(100)
+    uniforms = torch.rand((B, max(n_list)), generator=g)
+    # rows alive bookkeeping: the reference drops finished utterances (shortest first)
+    order = np.argsort(np.array(n_list), kind="stable")
+    _ShimCategorical.uniforms = uniforms
+    _ShimCategorical.step = 0
+
+    def rows_alive():
+        step = _ShimCategorical.step
+        return torch.tensor([b for b in range(B) if n_list_orig[b] > step])
+    n_list_orig = list(n_list)
+    _ShimCategorical.rows_alive = classmethod(lambda cls: rows_alive())
+    saved = torch.distributions.Categorical
+    torch.distributions.Categorical = _ShimCategorical
+    try:
+        with torch.no_grad():
+            dd = torch.from_numpy(d).float() if extra_memory else d
+            res = m.batch_fast_generate(x, torch.from_numpy(h), list(n_list), dd,
+                                        None, mode, extra_memory)
+    finally:
+        torch.distributions.Categorical = saved
+    # reference returns ascending-length (finish) order
+    by_input = [None] * B
+    for r, b in zip(res, order):
+        assert len(r) == n_list_orig[b]
+        by_input[b] = r
+    return by_input, uniforms.numpy(), n_list_orig
+
+
+def golden_generate():
+    out = {}
+    cases = [("small_argmax", SMALL, 5, 0.1, [3, 5, 4], "argmax", False, 1.0),
+             ("small_sampling", SMALL, 6, 0.1, [4, 3, 5], "sampling", False, 1.0),
+             ("small_sampling_xm", SMALL, 6, 0.1, [4, 3, 5], "sampling", True, 1.0),
+             ("small_sampling_f05", SMALL, 7, 0.1, [6, 6], "sampling", False, 0.5),
+             ("small_sampling_f15", SMALL, 8, 0.1, [5, 4], "sampling", False, 1.5),
+             ("full_sampling", FULL, 9, 0.05, [2, 3], "sampling", False, 1.0)]
+    for name, kw, seed, bstd, frames, mode, xm, fac in cases:
+        res, uni, n_list = gen_case(kw, seed, bstd, frames, mode, xm, fac)
+        for b, r in enumerate(res):
+            out[f"{name}/sym{b}"] = r.astype(np.int16)
+        out[f"{name}/uniforms"] = uni.astype(np.float32)
+        out[f"{name}/meta"] = np.array([seed] + frames, np.int64)
+        out[f"{name}/meta_f"] = np.array([bstd, fac], np.float64)
+        print("generate", name, [len(r) for r in res], [int(r[:8].sum()) for r in res])
+    np.savez_compressed(os.path.join(HERE, "generate.npz"), **out)
+
+
+# ---------------------------------------------------------------- G5: mu-law
+def golden_mulaw():
+    xs = np.array([-1, -.5, -.01, 0, .01, .5, 1], np.float64)
+    rs = np.random.RandomState(0)
+    xr = np.clip(rs.randn(4096) * 0.3, -1, 1)
+    np.savez_compressed(os.path.join(HERE, "mulaw.npz"),
+                        x_known=xs, enc_known=ref.encode_mu_law(xs),
+                        x_rand=xr, enc_rand=ref.encode_mu_law(xr),
+                        dec_all=ref.decode_mu_law(np.arange(256)))
+    print("mulaw enc known:", ref.encode_mu_law(xs))
+
+
+if __name__ == "__main__":
+    which = sys.argv[1:] or ["indices", "forward", "generate", "mulaw"]
+    if "indices" in which:
+        golden_indices()
+    if "forward" in which:
+        golden_forward()
+    if "generate" in which:
+        golden_generate()
+    if "mulaw" in which:
+        golden_mulaw()
