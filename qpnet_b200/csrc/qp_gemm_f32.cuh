@@ -1,0 +1,301 @@
+// fp32 SIMT segmented GEMM with fused epilogues -- the exact-arithmetic path of the
+// teacher-forced stack (used for tight-tolerance parity and by backward).
+//
+//   acc[r, n] = sum_seg sum_k  A_seg[ src_row_seg(r), k ] * W(n, koff_seg + k)
+//
+// A is assembled on the fly from up to three K-segments of time-major activations
+// (past tap rows, current tap rows, aux rows): the 2-tap causal / pitch-adaptive conv is
+// a GEMM whose A rows are *gathered*, never materialised (qpnet.py:295-298,657-666).
+#pragma once
+#include "qp_common.cuh"
+
+namespace qp {
+
+struct Seg {
+  const float* base;   // [B][rows][ld]
+  int64_t bstride;     // elements between batch elements
+  int ld;              // row pitch
+  const int* rowmap;   // optional [B][n_rows]: explicit source row (adaptive past tap)
+  int row_off;         // else source row = r + row_off ; src < 0 or >= src_rows reads zero
+  int src_rows;        // rows available in base per batch element
+  int K;               // segment width
+  int relu;            // apply relu while loading
+};
+
+enum Epi { EPI_PLAIN = 0, EPI_GATE, EPI_RESSKIP, EPI_DGATE, EPI_DX };
+
+struct GemmArgs {
+  Seg seg[3];
+  int nseg;
+  const float* W;  // NT: W[n*ldw + k]   (w_kn = 0)   NN: W[k*ldw + n]  (w_kn = 1)
+  int ldw, w_kn;
+  const float* bias;  // [N] or null
+  int B, n_rows, N;
+  int n_begin;  // first output column computed (skip the dead res rows of the last block)
+  // ---- epilogue operands (meaning depends on Epi) ----
+  float* out;  int64_t out_bstride;  int ldo;     // PLAIN: out[r][n]; GATE: z; RESSKIP: x_next; DGATE: dgate
+  const float* mask; int64_t mask_bstride; int ldmask;  // PLAIN: multiply by (mask[r][n] > 0)
+  float* gsave; int64_t gsave_bstride;            // GATE: optional (n_rows, 2C) sigmoid/tanh outputs; DGATE: input
+  const float* resid; int64_t resid_bstride; int ldresid; int resid_off;  // RESSKIP: + x_cur[r + off][n]; DX: dXnext
+  float* skip; int64_t skip_bstride; int skip_row0; int skip_accum; int C;  // RESSKIP
+  // DX: scatter dgate * Wg into dX (past rows, atomics), dX (current rows) and dHup
+  float* dx; int64_t dx_bstride; const int* dx_rowmap; int dx_past_off; int dx_cur_off; int dx_rows;
+  float* dh; int64_t dh_bstride; int dh_off; int A;
+};
+
+constexpr int GM = 64, GN = 64, GK = 16;
+
+__device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + __expf(-x)); }
+
+template <int EPI>
+__global__ void __launch_bounds__(256) gemm_f32_kernel(GemmArgs a) {
+  __shared__ float As[GK][GM + 4];
+  __shared__ float Ws[GK][GN + 4];
+  const int b = blockIdx.z;
+  const int r0 = blockIdx.x * GM;
+  const int n0 = a.n_begin + blockIdx.y * GN;
+  const int tid = threadIdx.x, tx = tid % 16, ty = tid / 16;
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+  int koff = 0;
+  for (int s = 0; s < a.nseg; ++s) {
+    const Seg sg = a.seg[s];
+    const float* abase = sg.base + (int64_t)b * sg.bstride;
+    for (int k0 = 0; k0 < sg.K; k0 += GK) {
+      // A tile: 64 rows x 16 k
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        int e = tid + i * 256;
+        int rr = e / GK, kk = e % GK;
+        int r = r0 + rr, k = k0 + kk;
+        float v = 0.f;
+        if (r < a.n_rows && k < sg.K) {
+          int src = sg.rowmap ? sg.rowmap[(int64_t)b * a.n_rows + r] : r + sg.row_off;
+          if (src >= 0 && src < sg.src_rows) {
+            v = abase[(int64_t)src * sg.ld + k];
+            if (sg.relu) v = fmaxf(v, 0.f);
+          }
+        }
+        As[kk][rr] = v;
+      }
+      // W tile: 64 n x 16 k
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        int e = tid + i * 256;
+        int nn, kk;
+        if (a.w_kn) { kk = e / GN; nn = e % GN; } else { nn = e / GK; kk = e % GK; }
+        int n = n0 + nn, k = k0 + kk;
+        float v = 0.f;
+        if (n < a.N && k < sg.K)
+          v = a.w_kn ? a.W[(int64_t)(koff + k) * a.ldw + n] : a.W[(int64_t)n * a.ldw + koff + k];
+        Ws[kk][nn] = v;
+      }
+      __syncthreads();
+#pragma unroll
+      for (int kk = 0; kk < GK; ++kk) {
+        float av[4], wv[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) av[i] = As[kk][ty * 4 + i];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) wv[j] = Ws[kk][tx * 4 + j];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], wv[j], acc[i][j]);
+      }
+      __syncthreads();
+    }
+    koff += sg.K;
+  }
+
+  // ------------------------------------------------------------------ epilogue
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int r = r0 + ty * 4 + i;
+    if (r >= a.n_rows) continue;
+    const int nb = n0 + tx * 4;
+    if (EPI == EPI_PLAIN) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        int n = nb + j;
+        if (n >= a.N) continue;
+        float v = acc[i][j] + (a.bias ? a.bias[n] : 0.f);
+        if (a.mask && !(a.mask[(int64_t)b * a.mask_bstride + (int64_t)r * a.ldmask + n] > 0.f)) v = 0.f;
+        a.out[(int64_t)b * a.out_bstride + (int64_t)r * a.ldo + n] = v;
+      }
+    } else if (EPI == EPI_GATE) {
+      // columns are (sigmoid, tanh) pairs: n = 2c + g   (qpnet.py:665-666 / 634-635)
+#pragma unroll
+      for (int j = 0; j < 4; j += 2) {
+        int n = nb + j;
+        if (n >= a.N) continue;
+        float sg_ = sigmoidf_(acc[i][j] + a.bias[n]);
+        float th_ = tanhf(acc[i][j + 1] + a.bias[n + 1]);
+        a.out[(int64_t)b * a.out_bstride + (int64_t)r * a.ldo + (n >> 1)] = sg_ * th_;
+        if (a.gsave) {
+          float* g = a.gsave + (int64_t)b * a.gsave_bstride + (int64_t)r * a.N + n;
+          g[0] = sg_;
+          g[1] = th_;
+        }
+      }
+    } else if (EPI == EPI_RESSKIP) {
+      // rows [0,C): residual projection + x_cur (qpnet.py:668-669); rows [C,C+S): skip (667)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        int n = nb + j;
+        if (n >= a.N) continue;
+        float v = acc[i][j] + a.bias[n];
+        if (n < a.C) {
+          v += a.resid[(int64_t)b * a.resid_bstride + (int64_t)(r + a.resid_off) * a.ldresid + n];
+          a.out[(int64_t)b * a.out_bstride + (int64_t)r * a.ldo + n] = v;
+        } else if (r >= a.skip_row0) {
+          float* p = a.skip + (int64_t)b * a.skip_bstride + (int64_t)(r - a.skip_row0) * (a.N - a.C) + (n - a.C);
+          *p = a.skip_accum ? *p + v : v;
+        }
+      }
+    } else if (EPI == EPI_DGATE) {
+      // acc = dz[r][c] (N = C).  dgate[2c] = dz*th*sg*(1-sg);  dgate[2c+1] = dz*sg*(1-th^2)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        int c = nb + j;
+        if (c >= a.N) continue;
+        const float* g = a.gsave + (int64_t)b * a.gsave_bstride + (int64_t)r * (2 * a.N) + 2 * c;
+        float sg_ = g[0], th_ = g[1], dz = acc[i][j];
+        float* o = a.out + (int64_t)b * a.out_bstride + (int64_t)r * a.ldo + 2 * c;
+        o[0] = dz * th_ * sg_ * (1.f - sg_);
+        o[1] = dz * sg_ * (1.f - th_ * th_);
+      }
+    } else if (EPI == EPI_DX) {
+      // acc = (dgate * Wg)[r][k], k over [past C | current C | aux Ap]
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        int k = nb + j;
+        if (k >= a.N) continue;
+        float v = acc[i][j];
+        if (k < a.C) {
+          int src = a.dx_rowmap ? a.dx_rowmap[(int64_t)b * a.n_rows + r] : r + a.dx_past_off;
+          if (src >= 0 && src < a.dx_rows) atomicAdd(a.dx + (int64_t)b * a.dx_bstride + (int64_t)src * a.C + k, v);
+        } else if (k < 2 * a.C) {
+          int c = k - a.C;
+          if (a.resid) v += a.resid[(int64_t)b * a.resid_bstride + (int64_t)r * a.ldresid + c];
+          atomicAdd(a.dx + (int64_t)b * a.dx_bstride + (int64_t)(r + a.dx_cur_off) * a.C + c, v);
+        } else if (k - 2 * a.C < a.A) {
+          float* p = a.dh + (int64_t)b * a.dh_bstride + (int64_t)(r + a.dh_off) * a.A + (k - 2 * a.C);
+          *p += v;
+        }
+      }
+    }
+  }
+}
+
+template <int EPI>
+inline int launch_gemm(const GemmArgs& a, cudaStream_t stream) {
+  if (a.n_rows <= 0 || a.B <= 0 || a.N - a.n_begin <= 0) return QP_OK;
+  dim3 grid((a.n_rows + GM - 1) / GM, (a.N - a.n_begin + GN - 1) / GN, a.B);
+  gemm_f32_kernel<EPI><<<grid, 256, 0, stream>>>(a);
+  QP_LAUNCH_CHECK();
+  return QP_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+// weight-gradient GEMM:  out[i][j] (+)= sum_b sum_r  P[b][r][i] * Q_seg[b][src(r)][j - joff]
+// P: plain rows with up to two column segments (dXnext | dSkip);  Q: gathered segments.
+// ---------------------------------------------------------------------------------------
+struct WgradArgs {
+  Seg p[2]; int np;     // column segments of P (rows of the output)
+  Seg q[3]; int nq;     // column segments of Q (columns of the output)
+  int B, n_rows;
+  int I, J;             // output dims
+  float* out; int ldo;  // out[i*ldo + j], overwritten
+  float* colsum;        // optional [I]: sum_r P[r][i]  (bias gradient), overwritten
+};
+
+__device__ __forceinline__ float seg_load(const Seg& sg, int b, int r, int k, int n_rows) {
+  int src = sg.rowmap ? sg.rowmap[(int64_t)b * n_rows + r] : r + sg.row_off;
+  if (src < 0 || src >= sg.src_rows) return 0.f;
+  float v = sg.base[(int64_t)b * sg.bstride + (int64_t)src * sg.ld + k];
+  return sg.relu ? fmaxf(v, 0.f) : v;
+}
+
+static __global__ void __launch_bounds__(256) wgrad_f32_kernel(WgradArgs a) {
+  __shared__ float Ps[GK][GM + 4];
+  __shared__ float Qs[GK][GN + 4];
+  const int i0 = blockIdx.x * GM, j0 = blockIdx.y * GN;
+  const int tid = threadIdx.x, tx = tid % 16, ty = tid / 16;
+  float acc[4][4];
+  float csum = 0.f;  // threads with tx == 0 (first 64 rows mapping below) accumulate colsum
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  // resolve which P / Q segment each of this thread's load slots belongs to (fixed per thread)
+  for (int b = 0; b < a.B; ++b) {
+    for (int r0 = 0; r0 < a.n_rows; r0 += GK) {
+#pragma unroll
+      for (int e4 = 0; e4 < 4; ++e4) {
+        int e = tid + e4 * 256;
+        int ii = e % GM, rr = e / GM;  // coalesced along i
+        int i = i0 + ii, r = r0 + rr;
+        float v = 0.f;
+        if (i < a.I && r < a.n_rows) {
+          int off = 0;
+          for (int s = 0; s < a.np; ++s) {
+            if (i - off < a.p[s].K) { v = seg_load(a.p[s], b, r, i - off, a.n_rows); break; }
+            off += a.p[s].K;
+          }
+        }
+        Ps[rr][ii] = v;
+        int jj = e % GN;
+        int j = j0 + jj;
+        float w = 0.f;
+        if (j < a.J && r < a.n_rows) {
+          int off = 0;
+          for (int s = 0; s < a.nq; ++s) {
+            if (j - off < a.q[s].K) { w = seg_load(a.q[s], b, r, j - off, a.n_rows); break; }
+            off += a.q[s].K;
+          }
+        }
+        Qs[rr][jj] = w;
+      }
+      __syncthreads();
+#pragma unroll
+      for (int kk = 0; kk < GK; ++kk) {
+        float pv[4], qv[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) pv[i] = Ps[kk][ty * 4 + i];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) qv[j] = Qs[kk][tx * 4 + j];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(pv[i], qv[j], acc[i][j]);
+      }
+      if (a.colsum && blockIdx.y == 0 && tid < GM) {
+#pragma unroll
+        for (int kk = 0; kk < GK; ++kk) csum += Ps[kk][tid];
+      }
+      __syncthreads();
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      int ii = i0 + ty * 4 + i, jj = j0 + tx * 4 + j;
+      if (ii < a.I && jj < a.J) a.out[(int64_t)ii * a.ldo + jj] = acc[i][j];
+    }
+  if (a.colsum && blockIdx.y == 0 && tid < GM && i0 + tid < a.I) a.colsum[i0 + tid] = csum;
+}
+
+inline int launch_wgrad(const WgradArgs& a, cudaStream_t stream) {
+  dim3 grid((a.I + GM - 1) / GM, (a.J + GN - 1) / GN);
+  wgrad_f32_kernel<<<grid, 256, 0, stream>>>(a);
+  QP_LAUNCH_CHECK();
+  return QP_OK;
+}
+
+}  // namespace qp

@@ -1,0 +1,212 @@
+// Error plumbing, device checks and the small integer / fp64 kernels of the path:
+// mu-law codec, F0 -> dilated factor, max-ceil reduction, dilation-index builders.
+#include <stdarg.h>
+#include <string.h>
+
+#include "qp_common.cuh"
+
+namespace qp {
+
+static thread_local char g_err[512] = "";
+static thread_local int g_launches = 0;
+
+int set_error(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+void count_launch(int n) { g_launches += n; }
+void reset_launch_count() { g_launches = 0; }
+
+int check_device() {
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return set_error(QP_EARCH, "no CUDA device: %s", cudaGetErrorString(e));
+  int major = 0;
+  e = cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
+  if (e != cudaSuccess) return set_error(QP_EARCH, "cudaDeviceGetAttribute: %s", cudaGetErrorString(e));
+  if (major != 10)
+    return set_error(QP_EARCH, "libqpnet_b200 is built for sm_100a only (device is cc %d.x); no fallback", major);
+  return QP_OK;
+}
+
+int check_arch(const QpArch* a) {
+  if (!a) return set_error(QP_EINVAL, "arch is NULL");
+  if (a->n_quantize < 2 || a->n_quantize > 1024) return set_error(QP_EINVAL, "n_quantize out of range");
+  if (a->n_aux < 1 || a->n_aux > 64) return set_error(QP_EINVAL, "n_aux must be in [1,64]");
+  if (a->n_resch < 4 || a->n_resch % 4) return set_error(QP_EINVAL, "n_resch must be a multiple of 4");
+  if (a->n_skipch < 1) return set_error(QP_EINVAL, "n_skipch must be positive");
+  if (a->upsampling < 1) return set_error(QP_EINVAL, "upsampling must be positive");
+  if (a->n_fixed < 1 || a->n_fixed > QP_MAX_LAYERS || a->n_adaptive < 1 || a->n_adaptive > QP_MAX_LAYERS)
+    return set_error(QP_EINVAL, "layer counts out of range");
+  for (int i = 0; i < a->n_fixed; ++i)
+    if (a->dil_fixed[i] < 1) return set_error(QP_EINVAL, "bad fixed dilation");
+  for (int i = 0; i < a->n_adaptive; ++i)
+    if (a->dil_adaptive[i] < 1) return set_error(QP_EINVAL, "bad adaptive dilation");
+  return QP_OK;
+}
+
+// ------------------------------------------------------------------ mu-law (qpnet.py:22-45)
+__global__ void mulaw_encode_kernel(const double* __restrict__ x, int64_t n, double mu, int64_t* __restrict__ y) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double v = x[i];
+  double sgn = (v > 0.0) - (v < 0.0);
+  double fx = sgn * log(1.0 + mu * fabs(v)) / log(1.0 + mu);
+  y[i] = (int64_t)floor((fx + 1.0) / 2.0 * mu + 0.5);
+}
+
+__global__ void mulaw_decode_kernel(const int64_t* __restrict__ y, int64_t n, double mu, double* __restrict__ x) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double fx = ((double)y[i] - 0.5) / mu * 2.0 - 1.0;
+  double sgn = (fx > 0.0) - (fx < 0.0);
+  x[i] = sgn / mu * (pow(1.0 + mu, fabs(fx)) - 1.0);
+}
+
+// ------------------------------------------------------------------ F0 -> d
+// qpnet_train.py:147-165,178 ; qpnet_decode.py:90-108 ; utils.py:216-235
+__global__ void f0_to_dilated_kernel(const double* __restrict__ f0, int B, int F, double fs, double dense,
+                                     int U, double f0_floor, double* __restrict__ d64, float* __restrict__ d32) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int64_t total = (int64_t)B * F * U;
+  if (i >= total) return;
+  int64_t frame = i / U;  // (b*F + f)
+  double f = f0[frame];
+  if (f0_floor >= 0.0 && f < f0_floor) f = f0_floor;
+  if (f == 0.0) f = fs / dense;
+  double d = __ddiv_rn(__ddiv_rn(1.0 * fs, f), dense);
+  if (d64) d64[i] = d;
+  if (d32) d32[i] = (float)d;
+}
+
+template <typename T>
+__global__ void max_ceil_kernel(const T* __restrict__ d, int64_t n, int32_t* __restrict__ out) {
+  int best = INT32_MIN;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    T v = d[i];
+    if (v == v) {  // nanmax semantics (qpnet.py:350)
+      int c = (int)ceil((double)v);
+      best = max(best, c);
+    }
+  }
+  for (int o = 16; o; o >>= 1) best = max(best, __shfl_xor_sync(0xffffffffu, best, o));
+  if ((threadIdx.x & 31) == 0 && best != INT32_MIN) atomicMax(out, best);
+}
+
+__global__ void set_int_kernel(int32_t* p, int32_t v) { *p = v; }
+
+// ------------------------------------------------------------------ index builders
+template <int FLAVOUR, typename TIn, typename TOut>
+__global__ void index_kernel(const TIn* __restrict__ d, int B, int n, int64_t ld, int dil, TOut* __restrict__ idx) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (int64_t)B * n) return;
+  int b = (int)(i / n), t = (int)(i % n);
+  TIn v = d[(int64_t)b * ld + t];
+  int r;
+  if (FLAVOUR == 0) r = tf_index_f32((float)v, dil, t - n);
+  else if (FLAVOUR == 1) r = tf_index_f64((double)v, dil, t - n);
+  else if (FLAVOUR == 2) r = gen_index_f32((float)v, dil);
+  else r = gen_index_f64((double)v, dil);
+  idx[i] = (TOut)r;
+}
+
+}  // namespace qp
+
+using namespace qp;
+
+extern "C" {
+
+int qp_abi_version(void) { return QP_ABI_VERSION; }
+const char* qp_last_error(void) { return g_err; }
+int qp_last_launch_count(void) { return g_launches; }
+int qp_device_ok(void) { return check_device(); }
+
+int qp_num_tensors(const QpArch* arch) {
+  if (check_arch(arch) != QP_OK) return QP_EINVAL;
+  return tensor_map(arch).count();
+}
+
+int qp_mulaw_encode(const double* x, int64_t n, int32_t mu, int64_t* y, void* stream) {
+  if (int e = check_device()) return e;
+  QP_REQUIRE(x && y && n >= 0 && mu > 1, "qp_mulaw_encode: bad arguments");
+  reset_launch_count();
+  if (n == 0) return QP_OK;
+  mulaw_encode_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(x, n, (double)(mu - 1), y);
+  QP_LAUNCH_CHECK();
+  return QP_OK;
+}
+
+int qp_mulaw_decode(const int64_t* y, int64_t n, int32_t mu, double* x, void* stream) {
+  if (int e = check_device()) return e;
+  QP_REQUIRE(x && y && n >= 0 && mu > 1, "qp_mulaw_decode: bad arguments");
+  reset_launch_count();
+  if (n == 0) return QP_OK;
+  mulaw_decode_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(y, n, (double)(mu - 1), x);
+  QP_LAUNCH_CHECK();
+  return QP_OK;
+}
+
+int qp_f0_to_dilated(const double* f0, int32_t B, int32_t F, double fs, double dense, int32_t U,
+                     double f0_floor, double* d64, float* d32, void* stream) {
+  if (int e = check_device()) return e;
+  QP_REQUIRE(f0 && B >= 0 && F >= 0 && U > 0 && fs > 0 && dense > 0, "qp_f0_to_dilated: bad arguments");
+  QP_REQUIRE(d64 || d32, "qp_f0_to_dilated: no output requested");
+  reset_launch_count();
+  int64_t total = (int64_t)B * F * U;
+  if (total == 0) return QP_OK;
+  f0_to_dilated_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(f0, B, F, fs, dense, U,
+                                                                                         f0_floor, d64, d32);
+  QP_LAUNCH_CHECK();
+  return QP_OK;
+}
+
+}  // extern "C"
+template <typename T>
+static int max_ceil_impl(const T* d, int64_t n, int32_t* out, void* stream) {
+  if (int e = check_device()) return e;
+  QP_REQUIRE(d && out && n > 0, "qp_max_ceil: bad arguments");
+  reset_launch_count();
+  set_int_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(out, INT32_MIN);
+  QP_LAUNCH_CHECK();
+  int blocks = (int)((n + 1023) / 1024);
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  max_ceil_kernel<T><<<blocks, 256, 0, (cudaStream_t)stream>>>(d, n, out);
+  QP_LAUNCH_CHECK();
+  return QP_OK;
+}
+extern "C" {
+int qp_max_ceil_f32(const float* d, int64_t n, int32_t* out, void* stream) { return max_ceil_impl(d, n, out, stream); }
+int qp_max_ceil_f64(const double* d, int64_t n, int32_t* out, void* stream) { return max_ceil_impl(d, n, out, stream); }
+
+}  // extern "C"
+template <int FL, typename TIn, typename TOut>
+static int index_impl(const TIn* d, int32_t B, int32_t n, int64_t ld, int32_t dil, TOut* idx, void* stream) {
+  if (int e = check_device()) return e;
+  QP_REQUIRE(B >= 0 && n >= 0 && dil >= 1 && ld >= n, "qp_index: bad shape (B=%d n=%d ld=%lld dil=%d)", B, n,
+             (long long)ld, dil);
+  reset_launch_count();
+  int64_t total = (int64_t)B * n;
+  if (total == 0) return QP_OK;  // empty input: nothing to do (ragged/empty edge case)
+  QP_REQUIRE(d && idx, "qp_index: NULL pointer");
+  index_kernel<FL, TIn, TOut><<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(d, B, n, ld, dil, idx);
+  QP_LAUNCH_CHECK();
+  return QP_OK;
+}
+extern "C" {
+int qp_index_tf_f32(const float* d, int32_t B, int32_t n, int64_t ld, int32_t dil, int64_t* idx, void* s) {
+  return index_impl<0>(d, B, n, ld, dil, idx, s);
+}
+int qp_index_tf_f64(const double* d, int32_t B, int32_t n, int64_t ld, int32_t dil, int32_t* idx, void* s) {
+  return index_impl<1>(d, B, n, ld, dil, idx, s);
+}
+int qp_index_gen_f32(const float* d, int32_t B, int32_t n, int64_t ld, int32_t dil, int64_t* idx, void* s) {
+  return index_impl<2>(d, B, n, ld, dil, idx, s);
+}
+int qp_index_gen_f64(const double* d, int32_t B, int32_t n, int64_t ld, int32_t dil, int32_t* idx, void* s) {
+  return index_impl<3>(d, B, n, ld, dil, idx, s);
+}
+
+}  // extern "C"

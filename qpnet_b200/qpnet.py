@@ -1,0 +1,275 @@
+"""Drop-in mirror of the reference model class (``/root/reference/src/nets/qpnet.py``).
+
+``from qpnet_b200.qpnet import QPNet, initialize, encode_mu_law, decode_mu_law`` replaces
+``from qpnet import ...`` (qpnet_train.py:35-37, qpnet_decode.py:32-34).  The class keeps
+
+* the constructor signature and every public attribute callers read
+  (qpnet.py:174-237; ``receptiveCausal_field`` ... are read at qpnet_train.py:463-465),
+* parameter names and shapes, so ``state_dict()`` / ``load_state_dict()`` / Adam /
+  ``model.apply(initialize)`` work on the reference's checkpoints unchanged,
+* ``forward(x, h, dilated_factors, blength)`` (qpnet.py:239-312) -> (B, bl, Q) logits
+  attached to autograd,
+* ``batch_fast_generate(x, h, n_samples_list, dilated_factors, intervals, mode,
+  extra_memory)`` (qpnet.py:314-559) -> list of int64 ndarrays in finish order.
+
+All arithmetic happens in libqpnet_b200.so (hand-written sm_100a kernels) through the C
+ABI of include/qpnet_b200.h.  The submodules below only hold parameters; they are never
+called.  There is no CPU path: tensors must live on a CUDA device.
+
+Deliberate differences from the reference (SURVEY.md caveats):
+* C1: every batch element gathers its past taps from ITSELF (the reference reads batch
+  element 0 for all of them, qpnet.py:250; its shipped configuration is batch_size 1).
+* C6: ``batch_fast_generate`` accepts a one-sample seed only (every reference caller
+  passes one, qpnet_decode.py:170).
+* sampling uses an inverse-CDF draw on counter-based (Philox) or caller-supplied uniforms
+  instead of torch's global-RNG multinomial (qpnet.py:508-510).
+"""
+from __future__ import annotations
+
+import logging
+import sys
+
+import numpy as np
+import torch
+from torch import nn
+
+from . import _lib, ops
+from ._lib import check, lib
+from .ops import decode_mu_law, encode_mu_law  # noqa: F401  (re-exported like the reference module)
+
+
+def initialize(m):
+    """qpnet.py:47-58 -- Xavier-uniform Conv1d weights / zero biases; unit upsampler."""
+    if isinstance(m, nn.Conv1d):
+        nn.init.xavier_uniform_(m.weight)
+        nn.init.constant_(m.bias, 0.0)
+    if isinstance(m, nn.ConvTranspose2d):
+        nn.init.constant_(m.weight, 1.0)
+        nn.init.constant_(m.bias, 0.0)
+
+
+class _Tap2(nn.Module):
+    """Parameter holder named like CausalConv1d (qpnet.py:110-132): ``.conv`` (out, in, 2)."""
+
+    def __init__(self, cin, cout, k):
+        super().__init__()
+        self.conv = nn.Conv1d(cin, cout, k)
+
+
+class _CurPrev(nn.Module):
+    """Parameter holder named like DilatedConv1d (qpnet.py:89-108): ``.convC`` / ``.convP``."""
+
+    def __init__(self, cin, cout):
+        super().__init__()
+        self.convC = nn.Conv1d(cin, cout, 1)
+        self.convP = nn.Conv1d(cin, cout, 1)
+
+
+class _Up(nn.Module):
+    """Parameter holder named like UpSampling (qpnet.py:134-158)."""
+
+    def __init__(self, factor):
+        super().__init__()
+        self.conv = nn.ConvTranspose2d(1, 1, kernel_size=(1, factor), stride=(1, factor))
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+class _TeacherForced(torch.autograd.Function):
+    """logits = stack(x, h, d; params) with the hand-written backward (qp_forward / qp_backward)."""
+
+    @staticmethod
+    def forward(ctx, model, x, h, d, bl, M, check_range, *params):
+        B, T = x.shape
+        F = h.shape[2]
+        need_grad = torch.is_grad_enabled() and any(p.requires_grad for p in params)
+        flags = _lib.QP_F_SAVE if need_grad else 0
+        arch = model._arch
+        nbytes = lib.qp_forward_workspace_bytes(arch, B, T, bl, M, flags)
+        if nbytes == 0:
+            raise ValueError("qp_forward_workspace_bytes rejected the shapes")
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=x.device)
+        logits = torch.empty((B, bl, model.n_quantize), dtype=torch.float32, device=x.device)
+        tensors = [p.detach() for p in params]
+        check(lib.qp_forward(arch, _lib.ptr_array(tensors), x.data_ptr(), h.data_ptr(), d.data_ptr(), B, T, F, bl, M,
+                             logits.data_ptr(), ws.data_ptr(), nbytes, flags, _stream()))
+        model.last_launches = lib.qp_last_launch_count()
+        if check_range:
+            check(lib.qp_workspace_status(ws.data_ptr(), _stream()))   # qpnet.py:294 assert
+        ctx.model, ctx.ws, ctx.nbytes, ctx.flags = model, ws, nbytes, flags
+        ctx.shape = (B, T, F, bl, M)
+        ctx.save_for_backward(x, h, d, *tensors)
+        return logits
+
+    @staticmethod
+    def backward(ctx, dlogits):
+        x, h, d, *tensors = ctx.saved_tensors
+        B, T, F, bl, M = ctx.shape
+        if not (ctx.flags & _lib.QP_F_SAVE):
+            raise RuntimeError("forward ran without gradient tracking")
+        dlogits = dlogits.contiguous().float()
+        grads = [torch.empty_like(t) for t in tensors]
+        check(lib.qp_backward(ctx.model._arch, _lib.ptr_array(tensors), x.data_ptr(), h.data_ptr(), d.data_ptr(),
+                              B, T, F, bl, M, dlogits.data_ptr(), _lib.ptr_array(grads), ctx.ws.data_ptr(), ctx.nbytes,
+                              ctx.flags, _stream()))
+        ctx.model.last_launches += lib.qp_last_launch_count()
+        ctx.ws = None
+        return (None, None, None, None, None, None, None, *grads)
+
+
+class QPNet(nn.Module):
+    """QUASI-PERIODIC WAVENET -- same constructor as qpnet.py:174-178."""
+
+    def __init__(self, n_quantize=256, n_aux=39, n_resch=512, n_skipch=256,
+                 dilationF_depth=4, dilationF_repeat=3, dilationA_depth=4, dilationA_repeat=1,
+                 kernel_size=2, upsampling_factor=110):
+        super().__init__()
+        if kernel_size != 2:
+            raise ValueError("only kernel_size=2 is supported (the reference's generation FIFOs assume 2 taps)")
+        if upsampling_factor <= 0:
+            raise ValueError("upsampling_factor must be positive")
+        self.n_quantize, self.n_aux, self.n_resch, self.n_skipch = n_quantize, n_aux, n_resch, n_skipch
+        self.kernel_size, self.upsampling_factor = kernel_size, upsampling_factor
+        self.receptiveCausal_field = kernel_size - 1
+        self.dilationF_depth, self.dilationF_repeat = dilationF_depth, dilationF_repeat
+        self.dilationsF = [2 ** i for i in range(dilationF_depth)] * dilationF_repeat
+        self.receptiveF_field = (kernel_size - 1) * sum(self.dilationsF)
+        self.dilationA_depth, self.dilationA_repeat = dilationA_depth, dilationA_repeat
+        self.dilationsA = [2 ** i for i in range(dilationA_depth)] * dilationA_repeat
+        self.receptiveA_field = (kernel_size - 1) * sum(self.dilationsA)
+        C_, S_, A_, Q_ = n_resch, n_skipch, n_aux, n_quantize
+        # registration order == the reference's state_dict order (qpnet.py:201-235)
+        self.causal = _Tap2(Q_, C_, kernel_size)
+        self.upsampling = _Up(upsampling_factor)
+        nF, nA = len(self.dilationsF), len(self.dilationsA)
+        self.dilF_sigmoid = nn.ModuleList([_Tap2(C_, C_, kernel_size) for _ in range(nF)])
+        self.dilF_tanh = nn.ModuleList([_Tap2(C_, C_, kernel_size) for _ in range(nF)])
+        self.auxF_1x1_sigmoid = nn.ModuleList([nn.Conv1d(A_, C_, 1) for _ in range(nF)])
+        self.auxF_1x1_tanh = nn.ModuleList([nn.Conv1d(A_, C_, 1) for _ in range(nF)])
+        self.skipF_1x1 = nn.ModuleList([nn.Conv1d(C_, S_, 1) for _ in range(nF)])
+        self.resF_1x1 = nn.ModuleList([nn.Conv1d(C_, C_, 1) for _ in range(nF)])
+        self.dilA_sigmoid = nn.ModuleList([_CurPrev(C_, C_) for _ in range(nA)])
+        self.dilA_tanh = nn.ModuleList([_CurPrev(C_, C_) for _ in range(nA)])
+        self.auxA_1x1_sigmoid = nn.ModuleList([nn.Conv1d(A_, C_, 1) for _ in range(nA)])
+        self.auxA_1x1_tanh = nn.ModuleList([nn.Conv1d(A_, C_, 1) for _ in range(nA)])
+        self.skipA_1x1 = nn.ModuleList([nn.Conv1d(C_, S_, 1) for _ in range(nA)])
+        self.resA_1x1 = nn.ModuleList([nn.Conv1d(C_, C_, 1) for _ in range(nA)])
+        self.conv_post_1 = nn.Conv1d(S_, S_, 1)
+        self.conv_post_2 = nn.Conv1d(S_, Q_, 1)
+        self.n_ch = n_resch
+        self._arch = _lib.make_arch(Q_, A_, C_, S_, upsampling_factor, self.dilationsF, self.dilationsA)
+        n_expected = lib.qp_num_tensors(self._arch)
+        if n_expected != len(list(self.parameters())):
+            raise RuntimeError("parameter table does not match the library's layout")
+        self.check_range = True     # mirror the reference's gather assert (costs one sync)
+        self.last_launches = 0      # kernels launched by the most recent call (bench accounting)
+        self.philox_seed = 100      # qpnet_decode.py:58 default --seed
+
+    # ------------------------------------------------------------------ helpers
+    def _tensors(self):
+        ts = list(self.parameters())
+        for t in ts:
+            if not t.is_cuda:
+                raise RuntimeError("QPNet parameters must be on a CUDA (sm_100a) device: call .cuda(); "
+                                   "there is no CPU path")
+            if t.dtype != torch.float32 or not t.is_contiguous():
+                raise RuntimeError("QPNet parameters must be contiguous float32")
+        return ts
+
+    # ------------------------------------------------------------------ qpnet.py:239-312
+    def forward(self, x, h, dilated_factors, blength):
+        """x (B,T) long, h (B,n_aux,T/U) float, dilated_factors (B,T) float, blength (B,) int
+        -> (B, batch_length, n_quantize) logits."""
+        assert torch.all(blength == blength[0])                      # qpnet.py:253
+        bl = int(blength[0])
+        params = self._tensors()
+        ops._need_cuda(x, h, dilated_factors)
+        x = x.contiguous().to(torch.int64)
+        h = h.contiguous().float()
+        d = dilated_factors.contiguous().float()
+        M = ops.max_ceil(d)                                           # qpnet.py:255
+        return _TeacherForced.apply(self, x, h, d, bl, M, self.check_range, *params)
+
+    # ------------------------------------------------------------------ qpnet.py:314-559
+    @torch.no_grad()
+    def batch_fast_generate(self, x, h, n_samples_list, dilated_factors, intervals=None, mode="sampling",
+                            extra_memory=False, uniforms=None, force=None, return_logits=False):
+        """Batch fast generation.  Returns the list of generated int64 arrays in FINISH
+        (ascending length) order and mutates ``n_samples_list`` like the reference does
+        (qpnet.py:527-559): all but one entry are deleted.
+
+        Extra keyword arguments (not in the reference): ``uniforms`` (B, >=max_n) pre-drawn
+        U[0,1) numbers for the inverse-CDF sampler (default: in-kernel Philox keyed by
+        ``self.philox_seed``), ``force`` (B, >=max_n) symbols fed back instead of the drawn
+        ones, ``return_logits`` -> also return per-step logits (B, max_n, Q).
+        """
+        if mode == "sampling":
+            qmode = _lib.QP_MODE_SAMPLING
+        elif mode == "argmax":
+            qmode = _lib.QP_MODE_ARGMAX
+        else:
+            logging.error("mode should be sampling or argmax")       # qpnet.py:513-515
+            sys.exit(1)
+        params = self._tensors()
+        dev = params[0].device
+        B = len(n_samples_list)
+        if x.dim() != 2 or x.shape[0] != B or x.shape[1] != 1:
+            raise NotImplementedError("batch_fast_generate takes a (B, 1) seed (SURVEY.md caveat C6)")
+        max_n = max(n_samples_list)
+        h = h.to(dev).contiguous().float()
+        F = h.shape[2]
+        if extra_memory:
+            d = dilated_factors.to(dev).contiguous().float()          # torch fp32 flavour (qpnet.py:615-617)
+            d_is_f64 = 0
+        else:
+            d = torch.from_numpy(np.ascontiguousarray(dilated_factors, dtype=np.float64)).to(dev)
+            d_is_f64 = 1                                              # numpy fp64 flavour (qpnet.py:621-622)
+        if d.shape[0] != B or d.shape[1] != F * self.upsampling_factor:
+            raise ValueError("dilated_factors must be (B, upsampling_factor * frames)")
+        M = ops.max_ceil(d)                                           # qpnet.py:347-350
+        seed = x[:, -1].to(dev).contiguous().to(torch.int64)
+        n_dev = torch.tensor(list(n_samples_list), dtype=torch.int32, device=dev)
+        out = torch.zeros((B, max(max_n, 1)), dtype=torch.int32, device=dev)
+        a = _lib.QpGenerateArgs()
+        a.B, a.F, a.M, a.mode, a.max_steps, a.d_is_f64 = B, F, M, qmode, max_n, d_is_f64
+        a.seed, a.h, a.d, a.n_samples = seed.data_ptr(), h.data_ptr(), d.data_ptr(), n_dev.data_ptr()
+        keep = [seed, h, d, n_dev, out]
+        if uniforms is not None:
+            uniforms = uniforms.to(dev).contiguous().float()
+            assert uniforms.shape[0] == B and uniforms.shape[1] >= max_n
+            a.uniforms, a.ld_uniforms = uniforms.data_ptr(), uniforms.stride(0)
+        a.philox_seed = int(self.philox_seed)
+        if force is not None:
+            force = force.to(dev).contiguous().to(torch.int32)
+            assert force.shape[0] == B and force.shape[1] >= max_n
+            a.force, a.ld_force = force.data_ptr(), force.stride(0)
+        a.out, a.ld_out = out.data_ptr(), out.stride(0)
+        logits = None
+        if return_logits:
+            logits = torch.zeros((B, max_n, self.n_quantize), dtype=torch.float32, device=dev)
+            a.logits_out = logits.data_ptr()
+        nbytes = lib.qp_generate_workspace_bytes(self._arch, B, M)
+        if nbytes == 0:
+            raise ValueError("qp_generate_workspace_bytes rejected the shapes")
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        check(lib.qp_generate(self._arch, _lib.ptr_array(params), a, ws.data_ptr(), nbytes, _stream()))
+        self.last_launches = lib.qp_last_launch_count()
+        check(lib.qp_workspace_status(ws.data_ptr(), _stream()))      # sync + watchdog status
+        host = out.cpu().numpy().astype(np.int64)
+        del keep
+        # ---- retirement order and caller-list mutation, exactly qpnet.py:527-557 --------
+        alive = list(range(B))
+        end_samples = []
+        while True:
+            mi = int(np.argmin(n_samples_list))
+            b = alive[mi]
+            end_samples.append(host[b, : n_samples_list[mi]].copy())
+            if len(alive) == 1:
+                break
+            del alive[mi]
+            del n_samples_list[mi]
+        if return_logits:
+            return end_samples, logits
+        return end_samples
