@@ -1,0 +1,337 @@
+#!/usr/bin/env python3
+"""bench.py -- headline benchmark of the QPNet hot path on B200 (BASELINE.json).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+Workload (config.workload): BASELINE.json configs[1] -- batch fast generation of 32 synthetic
+5 s utterances (1000 frames -> 109 999 samples each) with the SI default model, random-init
+weights, synthetic WORLD-style aux features and F0 contours, sampling mode.  A "step" is one
+full pass of the hot path over that batch.  With N > 1 ranks (torchrun) every rank generates
+its own 32 utterances (utterance sharding, no collective: weak scaling; N = 8 is configs[3]).
+
+Metric: generated samples per second, whole job.
+  value : inputs resident in HBM, device-timed with CUDA events (max over ranks).
+  e2e   : the same through QPNet.batch_fast_generate with HOST buffers (pinned h / d in,
+          int64 symbol arrays out), host<->device copies inside the timed region.
+  roofline     : the persistent generator kernel against the measured HBM bandwidth.
+  cpu_baseline : the CPU oracle port of the reference algorithm on the host cores (rank 0,
+                 N = 1 only), on a bounded sample of the same workload.
+
+--impl reference times the reference's CPU implementation of the path.  The reference is pure
+Python and cannot travel to the GPU box (and must not be copied), so the arm runs the oracle
+port (oracle/qpnet_oracle.py, pinned to the reference by tests/golden/) with every host thread.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+UTTS_PER_GPU = 32
+FRAMES = 1000            # 5 s at 5 ms shift
+FS = 22050
+ALG_WEIGHT_BYTES = 47.25e6   # live weights in bf16, streamed once per step
+ALG_STATE_BYTES = 31.7e3     # per utterance per step (FIFO taps, aux, offsets, symbol)
+
+
+def build_inputs(n_utts, first_utt, frames):
+    from qpnet_b200 import synth
+    h = np.zeros((n_utts, synth.N_AUX, frames), np.float32)
+    f0 = np.zeros((n_utts, frames), np.float64)
+    n_list = []
+    for b in range(n_utts):
+        hs, f, n = synth.utterance(frames, first_utt + b)
+        h[b] = hs.T
+        f0[b] = f
+        n_list.append(n)
+    return h, f0, n_list
+
+
+def host_dilated(f0):
+    """caller-side d exactly as qpnet_decode.py:174-175 builds it (numpy fp64)."""
+    d = np.ones(f0.shape) * FS
+    d /= f0
+    d /= 8
+    return np.repeat(d, 110, axis=1)
+
+
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.path = tempfile.mktemp(prefix="qp_clocks_", suffix=".csv")
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(gpu_index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except OSError:
+            pass
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in open(self.path):
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for nme, val in zip(names, f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(nme)
+        os.unlink(self.path)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def oracle_sample(n_utts, steps, frames, threads):
+    """Time `steps` sample steps of the CPU oracle port on `n_utts` utterances of the workload.
+    Returns samples/s.  (test infrastructure used as a *baseline*, never as the product)"""
+    import torch
+    from oracle import qpnet_oracle as orc
+    torch.set_num_threads(threads)
+    a = orc.Arch()
+    p = orc.init_params(a, 0)
+    h, f0, n_list = build_inputs(n_utts, 0, frames)
+    d = host_dilated(f0)
+    g = torch.Generator().manual_seed(100)
+    uni = torch.rand((n_utts, steps), generator=g)
+    x = torch.full((n_utts, 1), a.Q // 2, dtype=torch.long)
+    with torch.no_grad():
+        orc.generate(a, p, x, torch.from_numpy(h), list(n_list), d, mode="sampling", uniforms=uni, max_steps=2)
+        t0 = time.perf_counter()
+        orc.generate(a, p, x, torch.from_numpy(h), list(n_list), d, mode="sampling", uniforms=uni, max_steps=steps)
+        dt = time.perf_counter() - t0
+    return n_utts * steps / dt, dt
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        return float(json.load(open(path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def ncu_traffic_per_step():
+    """dram bytes per generator step from the committed ncu --set full capture (or None)."""
+    path = os.path.join(ROOT, "profiles", "gen_kernel_traffic.json")
+    if os.path.exists(path):
+        try:
+            return float(json.load(open(path))["dram_bytes_per_step"])
+        except Exception:
+            return None
+    return None
+
+
+def run_reference_arm(args, rank, world):
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    sample_steps = args.ref_sample_steps
+    vals = []
+    for i in range(args.warmup + args.steps):
+        v, dt = oracle_sample(UTTS_PER_GPU, sample_steps, FRAMES, threads)
+        if i >= args.warmup:
+            vals.append((v, dt))
+    value = float(np.mean([v for v, _ in vals]))
+    ms = float(np.mean([dt for _, dt in vals]) * 1e3)
+    sample = (f"{sample_steps} sample steps of the {UTTS_PER_GPU}-utterance batch per bench step "
+              f"(workload has 109999); oracle port of qpnet.py:314-559, torch CPU fp32")
+    line = {"impl": "reference", "metric": "generated samples/sec (whole box)", "value": value, "unit": "samples/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "real_time_factor": value / FS,
+            "config": workload_config(args.gpus),
+            "cpu_baseline": {"value": value, "unit": "samples/s", "cores": threads, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(n_gpus):
+    return {"workload": "BASELINE configs[1]: QPNet SI default, batch_fast_generate of 32 synthetic 5 s utterances "
+                        "per GPU (1000 frames, 109999 samples each), mode=sampling, extra_memory=False",
+            "utterances_per_gpu": UTTS_PER_GPU, "utterances_total": UTTS_PER_GPU * n_gpus,
+            "samples_per_utterance": FRAMES * 110 - 1, "parallelism": f"utterance-sharded x{n_gpus}, no collective",
+            "l2": "inputs are re-read per step and the generator's working set is re-packed per call; "
+                  "a 512 MiB buffer is written between timed iterations to flush L2"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--frames", type=int, default=FRAMES, help="(debug) frames per utterance")
+    ap.add_argument("--utts", type=int, default=UTTS_PER_GPU, help="(debug) utterances per GPU")
+    ap.add_argument("--ref-sample-steps", type=int, default=120)
+    ap.add_argument("--cpu-sample-steps", type=int, default=200)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference_arm(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    assert torch.cuda.is_available(), "bench.py needs a B200; there is no CPU fallback"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    assert world == args.gpus or world == 1, "launch with torchrun --nproc-per-node N for --gpus N"
+
+    import __graft_entry__
+    if rank == 0:
+        __graft_entry__.build()
+    if world > 1:
+        dist.barrier()
+    from qpnet_b200 import _lib, ops
+    from qpnet_b200.qpnet import QPNet, initialize
+
+    torch.manual_seed(0)                      # identical random-init weights on every rank
+    model = QPNet()
+    model.apply(initialize)
+    model = model.to(dev)
+    model.philox_seed = 100 + rank
+    n_utts, frames = args.utts, args.frames
+    h_np, f0_np, n_list = build_inputs(n_utts, rank * n_utts, frames)
+    max_n = max(n_list)
+    total_samples_rank = int(sum(n_list))
+
+    # ---------------- device-resident arm (value) ----------------
+    h_dev = torch.from_numpy(h_np).to(dev)
+    d64_dev, _ = ops.f0_to_dilated(torch.from_numpy(f0_np).to(dev), FS, 8, 110, want_f32=False)
+    seed_dev = torch.full((n_utts,), 128, dtype=torch.int64, device=dev)
+    n_dev = torch.tensor(n_list, dtype=torch.int32, device=dev)
+    flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step_resident():
+        out, _ = model.generate_device(seed_dev, h_dev, d64_dev, n_dev, max_n, _lib.QP_MODE_SAMPLING,
+                                       check_status=False)
+        return out
+
+    for _ in range(args.warmup):
+        step_resident()
+        flush.fill_(1)
+    barrier()
+    sampler = ClockSampler(local) if rank == 0 else None
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    launches = 0
+    t_wall0 = time.perf_counter()
+    for i in range(args.steps):
+        ev[i][0].record()
+        out = step_resident()
+        ev[i][1].record()
+        launches += model.last_launches
+        flush.fill_(i)                      # L2 flush between timed iterations (outside the events)
+    barrier()
+    t_wall = time.perf_counter() - t_wall0
+    clocks = sampler.stop() if sampler else None
+    status = _lib.lib.qp_workspace_status(model._last_ws.data_ptr(), torch.cuda.current_stream().cuda_stream)
+    assert status == 0, _lib.lib.qp_last_error()
+    dev_ms = [a.elapsed_time(b) for a, b in ev]
+    t_dev = torch.tensor([sum(dev_ms) / 1e3], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t_dev, op=dist.ReduceOp.MAX)
+    t_dev = float(t_dev.item())
+    value = total_samples_rank * world * args.steps / t_dev
+    sym = out[:, :max_n].cpu().numpy()
+    assert sym.min() >= 0 and sym.max() < 256 and len(np.unique(sym[:, :2000])) > 16, "degenerate output"
+
+    # ---------------- end-to-end arm (public API, host buffers) ----------------
+    h_pin = torch.from_numpy(h_np).pin_memory()
+    d_pin = torch.from_numpy(host_dilated(f0_np)).pin_memory()
+    x_seed = torch.full((n_utts, 1), 128, dtype=torch.long)
+    h2d = h_pin.numel() * 4 + d_pin.numel() * 8 + n_utts * 8 + n_utts * 4
+    d2h = n_utts * max_n * 4 + 4
+    model.batch_fast_generate(x_seed, h_pin, list(n_list), d_pin)          # warm-up
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        res = model.batch_fast_generate(x_seed, h_pin, list(n_list), d_pin)
+    torch.cuda.synchronize()
+    t_e2e = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
+    e2e_value = total_samples_rank * world * args.steps / float(t_e2e.item())
+    assert len(res) == n_utts and all(len(r) == n for r, n in zip(res, sorted(n_list)))
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---------------- roofline of the dominant kernel (persistent generator) ----------------
+    peak, peak_src = peaks()
+    steps_per_launch = max_n + 1                       # + the priming step
+    bytes_per_launch = steps_per_launch * (ALG_WEIGHT_BYTES + n_utts * ALG_STATE_BYTES)
+    kernel_s = (sum(dev_ms) / len(dev_ms)) / 1e3       # events bracket pack + generator; generator is > 99.9 %
+    achieved = bytes_per_launch / kernel_s / 1e9
+    tps = ncu_traffic_per_step()
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": (tps * steps_per_launch if tps is not None else None), "peak_source": peak_src,
+                "kernel": "qp::gen_kernel", "us_per_sample_step": kernel_s / steps_per_launch * 1e6,
+                "algorithmic_bytes_per_step": ALG_WEIGHT_BYTES + n_utts * ALG_STATE_BYTES}
+
+    cpu = None
+    if args.gpus == 1 and not args.no_cpu_baseline:
+        threads = os.cpu_count() or 1
+        v, dt = oracle_sample(n_utts, args.cpu_sample_steps, frames, threads)
+        cpu = {"value": v, "unit": "samples/s", "cores": threads, "kind": "port",
+               "sample": f"first {args.cpu_sample_steps} sample steps of the same {n_utts}-utterance batch "
+                         f"({dt:.1f} s of CPU work), oracle port of qpnet.py:314-559, torch CPU fp32"}
+
+    line = {"metric": "generated samples/sec (whole box)", "value": value, "unit": "samples/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": t_dev / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "real_time_factor": value / FS, "real_time_factor_per_gpu": value / FS / world,
+            "config": workload_config(args.gpus),
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "real_time_factor": e2e_value / FS},
+            "gpu_launches": launches,
+            "roofline": roofline, "cpu_baseline": cpu, "wall_s_timed_region": t_wall}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -81,10 +81,9 @@ class _TeacherForced(torch.autograd.Function):
     """logits = stack(x, h, d; params) with the hand-written backward (qp_forward / qp_backward)."""
 
     @staticmethod
-    def forward(ctx, model, x, h, d, bl, M, check_range, *params):
+    def forward(ctx, model, x, h, d, bl, M, check_range, need_grad, *params):
         B, T = x.shape
         F = h.shape[2]
-        need_grad = torch.is_grad_enabled() and any(p.requires_grad for p in params)
         flags = _lib.QP_F_SAVE if need_grad else 0
         arch = model._arch
         nbytes = lib.qp_forward_workspace_bytes(arch, B, T, bl, M, flags)
@@ -116,7 +115,7 @@ class _TeacherForced(torch.autograd.Function):
                               ctx.flags, _stream()))
         ctx.model.last_launches += lib.qp_last_launch_count()
         ctx.ws = None
-        return (None, None, None, None, None, None, None, *grads)
+        return (None, None, None, None, None, None, None, None, *grads)
 
 
 class QPNet(nn.Module):
@@ -190,7 +189,56 @@ class QPNet(nn.Module):
         h = h.contiguous().float()
         d = dilated_factors.contiguous().float()
         M = ops.max_ceil(d)                                           # qpnet.py:255
-        return _TeacherForced.apply(self, x, h, d, bl, M, self.check_range, *params)
+        need_grad = torch.is_grad_enabled() and any(p.requires_grad for p in params)
+        return _TeacherForced.apply(self, x, h, d, bl, M, self.check_range, need_grad, *params)
+
+    # ------------------------------------------------------------------ device-resident core
+    @torch.no_grad()
+    def generate_device(self, seed, h, d, n_dev, max_n, qmode=_lib.QP_MODE_SAMPLING, uniforms=None, force=None,
+                        return_logits=False, check_status=True):
+        """Generation with every input already resident in HBM: seed (B,) int64, h (B,A,F) fp32,
+        d (B,F*U) fp64 (numpy flavour of the reference) or fp32 (extra_memory flavour), n_dev (B,)
+        int32.  Returns (symbols (B, max_n) int32 on the device, logits or None)."""
+        params = self._tensors()
+        dev = params[0].device
+        ops._need_cuda(seed, h, d, n_dev)
+        B, F = h.shape[0], h.shape[2]
+        if d.shape[0] != B or d.shape[1] != F * self.upsampling_factor:
+            raise ValueError("dilated_factors must be (B, upsampling_factor * frames)")
+        if d.dtype not in (torch.float32, torch.float64):
+            raise TypeError("dilated_factors must be float32 or float64")
+        M = ops.max_ceil(d)                                           # qpnet.py:347-350
+        launches = ops.last_launch_count()
+        out = torch.zeros((B, max(max_n, 1)), dtype=torch.int32, device=dev)
+        a = _lib.QpGenerateArgs()
+        a.B, a.F, a.M, a.mode, a.max_steps = B, F, M, qmode, max_n
+        a.d_is_f64 = 1 if d.dtype == torch.float64 else 0
+        a.seed, a.h, a.d, a.n_samples = seed.data_ptr(), h.data_ptr(), d.data_ptr(), n_dev.data_ptr()
+        if uniforms is not None:
+            uniforms = uniforms.to(dev).contiguous().float()
+            assert uniforms.shape[0] == B and uniforms.shape[1] >= max_n
+            a.uniforms, a.ld_uniforms = uniforms.data_ptr(), uniforms.stride(0)
+        a.philox_seed = int(self.philox_seed)
+        if force is not None:
+            force = force.to(dev).contiguous().to(torch.int32)
+            assert force.shape[0] == B and force.shape[1] >= max_n
+            a.force, a.ld_force = force.data_ptr(), force.stride(0)
+        a.out, a.ld_out = out.data_ptr(), out.stride(0)
+        logits = None
+        if return_logits:
+            logits = torch.zeros((B, max_n, self.n_quantize), dtype=torch.float32, device=dev)
+            a.logits_out = logits.data_ptr()
+        nbytes = lib.qp_generate_workspace_bytes(self._arch, B, M)
+        if nbytes == 0:
+            raise ValueError("qp_generate_workspace_bytes rejected the shapes")
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        check(lib.qp_generate(self._arch, _lib.ptr_array(params), a, ws.data_ptr(), nbytes, _stream()))
+        self.last_launches = launches + lib.qp_last_launch_count()
+        if check_status:
+            check(lib.qp_workspace_status(ws.data_ptr(), _stream()))  # sync + watchdog status
+        else:
+            self._last_ws = ws                                        # keep alive until the caller syncs
+        return out, logits
 
     # ------------------------------------------------------------------ qpnet.py:314-559
     @torch.no_grad()
@@ -218,47 +266,18 @@ class QPNet(nn.Module):
         if x.dim() != 2 or x.shape[0] != B or x.shape[1] != 1:
             raise NotImplementedError("batch_fast_generate takes a (B, 1) seed (SURVEY.md caveat C6)")
         max_n = max(n_samples_list)
-        h = h.to(dev).contiguous().float()
-        F = h.shape[2]
+        h = h.to(dev, non_blocking=True).contiguous().float()
         if extra_memory:
-            d = dilated_factors.to(dev).contiguous().float()          # torch fp32 flavour (qpnet.py:615-617)
-            d_is_f64 = 0
-        else:
-            d = torch.from_numpy(np.ascontiguousarray(dilated_factors, dtype=np.float64)).to(dev)
-            d_is_f64 = 1                                              # numpy fp64 flavour (qpnet.py:621-622)
-        if d.shape[0] != B or d.shape[1] != F * self.upsampling_factor:
-            raise ValueError("dilated_factors must be (B, upsampling_factor * frames)")
-        M = ops.max_ceil(d)                                           # qpnet.py:347-350
+            d = dilated_factors.to(dev, non_blocking=True).contiguous().float()   # torch fp32 flavour (qpnet.py:615-617)
+        else:                                                         # numpy fp64 flavour (qpnet.py:621-622)
+            if isinstance(dilated_factors, torch.Tensor):             # (a pinned fp64 CPU tensor is accepted too)
+                d = dilated_factors.to(torch.float64).to(dev, non_blocking=True).contiguous()
+            else:
+                d = torch.from_numpy(np.ascontiguousarray(dilated_factors, dtype=np.float64)).to(dev)
         seed = x[:, -1].to(dev).contiguous().to(torch.int64)
         n_dev = torch.tensor(list(n_samples_list), dtype=torch.int32, device=dev)
-        out = torch.zeros((B, max(max_n, 1)), dtype=torch.int32, device=dev)
-        a = _lib.QpGenerateArgs()
-        a.B, a.F, a.M, a.mode, a.max_steps, a.d_is_f64 = B, F, M, qmode, max_n, d_is_f64
-        a.seed, a.h, a.d, a.n_samples = seed.data_ptr(), h.data_ptr(), d.data_ptr(), n_dev.data_ptr()
-        keep = [seed, h, d, n_dev, out]
-        if uniforms is not None:
-            uniforms = uniforms.to(dev).contiguous().float()
-            assert uniforms.shape[0] == B and uniforms.shape[1] >= max_n
-            a.uniforms, a.ld_uniforms = uniforms.data_ptr(), uniforms.stride(0)
-        a.philox_seed = int(self.philox_seed)
-        if force is not None:
-            force = force.to(dev).contiguous().to(torch.int32)
-            assert force.shape[0] == B and force.shape[1] >= max_n
-            a.force, a.ld_force = force.data_ptr(), force.stride(0)
-        a.out, a.ld_out = out.data_ptr(), out.stride(0)
-        logits = None
-        if return_logits:
-            logits = torch.zeros((B, max_n, self.n_quantize), dtype=torch.float32, device=dev)
-            a.logits_out = logits.data_ptr()
-        nbytes = lib.qp_generate_workspace_bytes(self._arch, B, M)
-        if nbytes == 0:
-            raise ValueError("qp_generate_workspace_bytes rejected the shapes")
-        ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
-        check(lib.qp_generate(self._arch, _lib.ptr_array(params), a, ws.data_ptr(), nbytes, _stream()))
-        self.last_launches = lib.qp_last_launch_count()
-        check(lib.qp_workspace_status(ws.data_ptr(), _stream()))      # sync + watchdog status
+        out, logits = self.generate_device(seed, h, d, n_dev, max_n, qmode, uniforms, force, return_logits)
         host = out.cpu().numpy().astype(np.int64)
-        del keep
         # ---- retirement order and caller-list mutation, exactly qpnet.py:527-557 --------
         alive = list(range(B))
         end_samples = []

@@ -111,8 +111,10 @@ def test_mulaw_vs_reference_goldens(dev):
     assert ops.encode_mu_law(g["x_known"]).tolist() == [0, 16, 98, 128, 157, 239, 255]
     assert np.array_equal(ops.encode_mu_law(g["x_rand"]), g["enc_rand"])
     np.testing.assert_allclose(ops.decode_mu_law(np.arange(256)), g["dec_all"], rtol=0, atol=1e-14)
-    # round trip property on every symbol
-    assert np.array_equal(ops.encode_mu_law(ops.decode_mu_law(np.arange(1, 256))), np.arange(1, 256))
+    # (decode is NOT the inverse of encode in the reference -- asymmetric -0.5, qpnet.py:43 -- and
+    # decode(y) sits exactly on an encode rounding boundary, so no round-trip property exists.)
+    xr = np.random.RandomState(5).uniform(-1, 1, 100000)
+    assert np.array_equal(ops.encode_mu_law(xr), orc.encode_mu_law(xr))
 
 
 # ------------------------------------------------------------------ teacher-forced stack
