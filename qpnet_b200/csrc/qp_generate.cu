@@ -1,24 +1,30 @@
 // Persistent autoregressive generator: QPNet.batch_fast_generate (qpnet.py:314-559).
 //
-// ONE cooperative kernel runs priming and every sample step of the whole batch.
-//   * grid = C/4 CTAs (128 for the SI default model); CTA s owns residual channels
-//     [4s, 4s+4) of every block: its 8 gate rows (4 sigmoid + 4 tanh), 4 residual rows and
-//     ceil(S/grid) skip rows, plus a slice of the two head projections.
-//   * per block two phases separated by a grid-wide barrier (monotonic counter in L2):
-//       gate  : pre = Wg . [x(t-k) ; x(t) ; h_up(t)]  -> z = sigmoid * tanh   (bf16 to L2)
-//       res   : x'  = R z + r + x(t) (fp32 carry kept in the owning CTA), skip += K z + k
-//     then head-1, head-2 and the sampling phase (one warp per utterance: softmax,
-//     inverse-CDF / argmax, next causal-layer lookup).
-//   * the batch is the M dimension of mma.sync.m16n8k16 (bf16 in, fp32 accumulate), the
-//     CTA's 8 output rows are N; K is split over the 8 warps and reduced through smem.
-//   * every block input lives in a power-of-two ring of bf16 rows in global memory (L2
-//     resident): the ring is both the FIFO of qpnet.py:388-393,431-437 and the exchange
-//     buffer between CTAs.  Fixed blocks read slot t-dil, adaptive blocks read slot
-//     t-k, k = -round(-d[t]*dil) computed in-kernel with the reference's rounding
-//     (qpnet.py:616-617 / 621-622); k == 0 selects the oldest entry (caveat C4).
+// ONE persistent kernel runs priming and every sample step of the whole batch as a
+// barrier-free DATAFLOW over the SMs.
+//   * grid = C/4 CTAs (128 for the SI default model), one per SM, co-resident (cooperative
+//     launch).  CTA s owns residual channels [4s, 4s+4) of every block: 8 "current tap" gate
+//     rows (4 sigmoid + 4 tanh), the matching 8 "past tap" gate rows, 4 residual rows,
+//     S/grid skip rows, and a slice of both head projections.
+//   * per block two phases:
+//       gate : [cur | P'] = [Wc ; Wp] . [x(t) ; h_up(t)]   (two n-tiles of mma.sync.m16n8k16,
+//              batch = M dimension, bf16 operands, fp32 accumulate, K split over 8 warps)
+//              pre = cur + P(t-k) + bias ;  z = sigmoid * tanh ;  P'(t) is stored for step t+k
+//       res  : x' = R z + r + x(t)  (fp32 carry stays in the owning CTA),  skip += K z + k
+//     then head-1, head-2, and the sampling phase (one warp per utterance).
+//   * The past tap W0.x(t-k) of qpnet.py:81-87,657-666 is never re-read as an activation:
+//     each CTA keeps ITS 8 partial sums P(t) = Wp.x(t) per utterance in a private ring
+//     (depth = the reference's FIFO depth, qpnet.py:388-393,431-437) and reads back the
+//     entry k steps old; k = dil for fixed blocks, k = -round(-d[t]*dil) for adaptive blocks,
+//     computed in-kernel with the reference's rounding (qpnet.py:616-617 / 621-622);
+//     k == 0 selects the oldest entry (caveat C4).
+//   * Exchange between CTAs goes through small L2-resident buffers whose every 32-bit word
+//     carries a 1-bit epoch tag (LSB of the low bf16 / of the fp32 logit): consumers poll the
+//     data itself, so one store->load round trip replaces "fence + atomic + poll + load".
+//     Write-after-read safety follows from data dependence.
 //   * priming (qpnet.py:355-440) is evaluated on a length-1 time axis: the pad region is
-//     constant, so step "-1" runs the stack with past == current and fills every ring slot.
-#include <cooperative_groups.h>
+//     constant, so step "-1" runs the stack with P(t-k) := P'(t) and fills every ring slot.
+#include <algorithm>
 
 #include "qp_common.cuh"
 #include "qp_pack.cuh"
@@ -28,18 +34,20 @@ namespace qp {
 constexpr int GEN_THREADS = 256;
 constexpr int GEN_WARPS = 8;
 constexpr int CHUNK = 32;  // utterances per MMA pass (two m16 tiles)
-constexpr long long GEN_TIMEOUT_CYCLES = 6000000000LL;  // ~3 s per barrier: watchdog, not a schedule
+constexpr long long GEN_TIMEOUT_CYCLES = 6000000000LL;  // ~3 s: watchdog, not a schedule
+constexpr int TRACE_EVENTS = 4;
 
 struct GenPlan {
-  int C, S, Q, A, Ap, Kg, L, nF, nA, U;
+  int C, S, Q, A, Ap, L, nF, nA, U;
   int nCTA, spc, rp1, nt1, rp2, nt2;
+  int Kc;  // C + Ap : K of the current-tap gate tile
   int B, Bpad, nchunk, F, M;
   int dil[2 * QP_MAX_LAYERS];
-  int depth[2 * QP_MAX_LAYERS];     // look-back bound of block l's input FIFO
+  int depth[2 * QP_MAX_LAYERS];     // look-back bound of block l (FIFO depth of the reference)
   int ring_size[2 * QP_MAX_LAYERS]; // power of two > depth
   // device buffers
   const float** tab;
-  __nv_bfloat16* WgG;   // [L][nCTA][8][Kg]
+  __nv_bfloat16* WgG;   // [L][nCTA] { Wc[8][Kc], Wp[8][C] }
   __nv_bfloat16* WrsG;  // [L][nCTA][8][C]
   float* bgG;           // [L][nCTA][8]
   float* brsG;          // [L][nCTA][8]
@@ -48,13 +56,17 @@ struct GenPlan {
   __nv_bfloat16* W2G;   // [nCTA][nt2*8][S]
   float* b2G;           // [nCTA][nt2*8]
   float* E0; float* E1; // [Q][C] fp32
-  __nv_bfloat16* ring[2 * QP_MAX_LAYERS];  // [ring_size][Bpad][C]
+  float* Pring[2 * QP_MAX_LAYERS];  // [ring_size][nCTA][Bpad][8] fp32, private per CTA
+  // tagged exchange buffers (memset to 0xFF before launch)
+  __nv_bfloat16* xbuf;      // [L][Bpad][C]   block inputs of the current step
   __nv_bfloat16* zbuf;      // [Bpad][C]
-  __nv_bfloat16* skipbuf;   // [Bpad][S]  relu(sum of skips)
-  __nv_bfloat16* h1buf;     // [Bpad][S]  relu(head-1)
+  __nv_bfloat16* skipbuf;   // [Bpad][S]      relu(sum of skips)
+  __nv_bfloat16* h1buf;     // [Bpad][S]      relu(head-1)
   float* logitbuf;          // [Bpad][Q]
   int2* symbuf;             // [Bpad] (previous, current) symbol fed to the causal layer
-  unsigned long long* barrier;
+  void* tagged_begin; size_t tagged_bytes;
+  long long* trace;         // [steps][2L+3][TRACE_EVENTS] clock64 of CTA 0 (debug)
+  int trace_step0, trace_nsteps;
   int32_t* status;
 };
 
@@ -62,66 +74,76 @@ static int pow2_above(int v) { int p = 1; while (p <= v) p <<= 1; return p; }
 
 static size_t make_gen_plan(const QpArch* a, int B, int F, int M, void* base, size_t cap, GenPlan* p) {
   PackedDims pd = packed_dims(a);
-  p->C = pd.C; p->S = pd.S; p->Q = pd.Q; p->A = pd.A; p->Ap = pd.Ap; p->Kg = pd.Kg; p->L = pd.L;
-  p->nF = pd.nF; p->nA = pd.nA; p->U = pd.U;
+  p->C = pd.C; p->S = pd.S; p->Q = pd.Q; p->A = pd.A; p->Ap = pd.Ap; p->L = pd.L;
+  p->nF = pd.nF; p->nA = pd.nA; p->U = pd.U; p->Kc = pd.C + pd.Ap;
   p->nCTA = pd.C / 4;
-  p->spc = (pd.S + p->nCTA - 1) / p->nCTA;
-  p->rp1 = (pd.S + p->nCTA - 1) / p->nCTA; p->nt1 = (p->rp1 + 7) / 8;
-  p->rp2 = (pd.Q + p->nCTA - 1) / p->nCTA; p->nt2 = (p->rp2 + 7) / 8;
+  const int n = p->nCTA;
+  p->spc = 2 * ((pd.S / 2 + n - 1) / n);               // skip rows per CTA (even: rows travel in pairs)
+  p->rp1 = 2 * ((pd.S / 2 + n - 1) / n); p->nt1 = (p->rp1 + 7) / 8;
+  p->rp2 = 2 * ((pd.Q / 2 + n - 1) / n); p->nt2 = (p->rp2 + 7) / 8;
   p->B = B; p->nchunk = (B + CHUNK - 1) / CHUNK; p->Bpad = p->nchunk * CHUNK; p->F = F; p->M = M;
   Arena ar(base, cap);
   p->status = ar.take<int32_t>(64);
-  p->barrier = ar.take<unsigned long long>(32);
   p->tab = ar.take<const float*>(tensor_map(a).count());
-  const size_t n = p->nCTA;
-  p->WgG = ar.take<__nv_bfloat16>((size_t)pd.L * n * 8 * pd.Kg);
+  p->WgG = ar.take<__nv_bfloat16>((size_t)pd.L * n * 8 * (p->Kc + pd.C));
   p->WrsG = ar.take<__nv_bfloat16>((size_t)pd.L * n * 8 * pd.C);
   p->bgG = ar.take<float>((size_t)pd.L * n * 8);
   p->brsG = ar.take<float>((size_t)pd.L * n * 8);
-  p->W1G = ar.take<__nv_bfloat16>(n * p->nt1 * 8 * pd.S);
-  p->b1G = ar.take<float>(n * p->nt1 * 8);
-  p->W2G = ar.take<__nv_bfloat16>(n * p->nt2 * 8 * pd.S);
-  p->b2G = ar.take<float>(n * p->nt2 * 8);
+  p->W1G = ar.take<__nv_bfloat16>((size_t)n * p->nt1 * 8 * pd.S);
+  p->b1G = ar.take<float>((size_t)n * p->nt1 * 8);
+  p->W2G = ar.take<__nv_bfloat16>((size_t)n * p->nt2 * 8 * pd.S);
+  p->b2G = ar.take<float>((size_t)n * p->nt2 * 8);
   p->E0 = ar.take<float>((size_t)pd.Q * pd.C);
   p->E1 = ar.take<float>((size_t)pd.Q * pd.C);
   for (int l = 0; l < pd.L; ++l) {
     p->dil[l] = l < pd.nF ? a->dil_fixed[l] : a->dil_adaptive[l - pd.nF];
     p->depth[l] = l < pd.nF ? p->dil[l] : p->dil[l] * M;
     p->ring_size[l] = pow2_above(p->depth[l]);
-    p->ring[l] = ar.take<__nv_bfloat16>((size_t)p->ring_size[l] * p->Bpad * pd.C);
+    p->Pring[l] = ar.take<float>((size_t)p->ring_size[l] * n * p->Bpad * 8);
   }
+  ar.off = align_up(ar.off, 256);
+  size_t t0 = ar.off;
+  p->xbuf = ar.take<__nv_bfloat16>((size_t)pd.L * p->Bpad * pd.C);
   p->zbuf = ar.take<__nv_bfloat16>((size_t)p->Bpad * pd.C);
   p->skipbuf = ar.take<__nv_bfloat16>((size_t)p->Bpad * pd.S);
   p->h1buf = ar.take<__nv_bfloat16>((size_t)p->Bpad * pd.S);
   p->logitbuf = ar.take<float>((size_t)p->Bpad * pd.Q);
   p->symbuf = ar.take<int2>(p->Bpad);
+  ar.off = align_up(ar.off, 256);
+  p->tagged_begin = base ? (char*)base + t0 : nullptr;
+  p->tagged_bytes = ar.off - t0;
+  p->trace = ar.take<long long>((size_t)8 * (2 * pd.L + 3) * TRACE_EVENTS);
+  p->trace_step0 = -100; p->trace_nsteps = 8;
   return align_up(ar.off, 256);
 }
 
 // ------------------------------------------------------------------ weight packing (bf16)
 __global__ void gen_pack_kernel(TensorMap tm, GenPlan p, const float* const* __restrict__ tab) {
-  const int C = p.C, S = p.S, Q = p.Q, A = p.A, Kg = p.Kg, L = p.L, n = p.nCTA;
-  const size_t n_wg = (size_t)L * n * 8 * Kg, n_wrs = (size_t)L * n * 8 * C, n_b = (size_t)L * n * 8;
+  const int C = p.C, S = p.S, Q = p.Q, A = p.A, Kc = p.Kc, L = p.L, n = p.nCTA;
+  const int per_cta = 8 * (Kc + C);
+  const size_t n_wg = (size_t)L * n * per_cta, n_wrs = (size_t)L * n * 8 * C, n_b = (size_t)L * n * 8;
   const size_t n_w1 = (size_t)n * p.nt1 * 8 * S, n_b1 = (size_t)n * p.nt1 * 8;
   const size_t n_w2 = (size_t)n * p.nt2 * 8 * S, n_b2 = (size_t)n * p.nt2 * 8, n_e = (size_t)Q * C;
   const size_t total = n_wg + n_wrs + 2 * n_b + n_w1 + n_b1 + n_w2 + n_b2 + 2 * n_e;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
     size_t k = i;
     if (k < n_wg) {
-      int col = (int)(k % Kg); size_t r = k / Kg;
-      int r8 = (int)(r % 8); r /= 8;
+      int e = (int)(k % per_cta); size_t r = k / per_cta;
       int s = (int)(r % n), l = (int)(r / n);
+      bool past = e >= 8 * Kc;
+      int r8, col;
+      if (!past) { r8 = e / Kc; col = e % Kc; } else { r8 = (e - 8 * Kc) / C; col = (e - 8 * Kc) % C; }
       int g = r8 >= 4, c = 4 * s + (r8 & 3);
       float v = 0.f;
       if (l < p.nF) {
-        if (col < C) v = tab[tm.dilF_w(g, l)][((size_t)c * C + col) * 2 + 0];
-        else if (col < 2 * C) v = tab[tm.dilF_w(g, l)][((size_t)c * C + (col - C)) * 2 + 1];
-        else if (col < 2 * C + A) v = tab[tm.auxF_w(g, l)][(size_t)c * A + (col - 2 * C)];
+        if (past) v = tab[tm.dilF_w(g, l)][((size_t)c * C + col) * 2 + 0];
+        else if (col < C) v = tab[tm.dilF_w(g, l)][((size_t)c * C + col) * 2 + 1];
+        else if (col < C + A) v = tab[tm.auxF_w(g, l)][(size_t)c * A + (col - C)];
       } else {
         int j = l - p.nF;
-        if (col < C) v = tab[tm.dilA_wP(g, j)][(size_t)c * C + col];
-        else if (col < 2 * C) v = tab[tm.dilA_wC(g, j)][(size_t)c * C + (col - C)];
-        else if (col < 2 * C + A) v = tab[tm.auxA_w(g, j)][(size_t)c * A + (col - 2 * C)];
+        if (past) v = tab[tm.dilA_wP(g, j)][(size_t)c * C + col];
+        else if (col < C) v = tab[tm.dilA_wC(g, j)][(size_t)c * C + col];
+        else if (col < C + A) v = tab[tm.auxA_w(g, j)][(size_t)c * A + (col - C)];
       }
       p.WgG[k] = __float2bfloat16(v);
       continue;
@@ -212,15 +234,30 @@ __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sa), "l"(gmem) : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
 
-__device__ __forceinline__ unsigned long long ld_acquire_u64(const unsigned long long* p) {
-  unsigned long long v;
-  asm volatile("ld.acquire.gpu.global.u64 %0, [%1];\n" : "=l"(v) : "l"(p) : "memory");
+__device__ __forceinline__ uint4 ld_strong_v4(const void* p) {
+  uint4 v;
+  asm volatile("ld.relaxed.gpu.global.v4.u32 {%0,%1,%2,%3}, [%4];\n"
+               : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
   return v;
 }
-__device__ __forceinline__ void red_release_add_u64(unsigned long long* p, unsigned long long v) {
-  asm volatile("red.release.gpu.global.add.u64 [%0], %1;\n" ::"l"(p), "l"(v) : "memory");
+__device__ __forceinline__ uint2 ld_strong_v2(const void* p) {
+  uint2 v;
+  asm volatile("ld.relaxed.gpu.global.v2.u32 {%0,%1}, [%2];\n" : "=r"(v.x), "=r"(v.y) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ unsigned ld_strong_u32(const void* p) {
+  unsigned v;
+  asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];\n" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_strong_u32(void* p, unsigned v) {
+  asm volatile("st.relaxed.gpu.global.u32 [%0], %1;\n" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ void st_strong_v2(void* p, unsigned a, unsigned b) {
+  asm volatile("st.relaxed.gpu.global.v2.u32 [%0], {%1,%2};\n" ::"l"(p), "r"(a), "r"(b) : "memory");
 }
 
 __device__ __forceinline__ void ldmatrix_x4(unsigned& a0, unsigned& a1, unsigned& a2, unsigned& a3, const void* p) {
@@ -245,6 +282,21 @@ __device__ __forceinline__ float fast_tanh(float x) {
   float e = __expf(-2.f * fabsf(x));
   float t = (1.f - e) / (1.f + e);
   return copysignf(t, x);
+}
+
+// bf16 bits of x, round-to-nearest-even
+__device__ __forceinline__ unsigned bf16_rne(float x) { return (unsigned)__bfloat16_as_ushort(__float2bfloat16_rn(x)); }
+// bf16 bits of x rounded to the nearest value whose mantissa LSB equals `par` (error <= 1 ulp)
+__device__ __forceinline__ unsigned bf16_tagged(float x, unsigned par) {
+  unsigned u = __float_as_uint(x);
+  unsigned hi = u >> 16, rem = u & 0xFFFFu;
+  unsigned r = hi + ((rem > 0x8000u) || (rem == 0x8000u && (hi & 1u)));
+  if ((r & 1u) != par) r = (r > hi) ? r - 1u : r + 1u;
+  return r & 0xFFFFu;
+}
+// one exchange word: two channels, epoch tag in bit 0
+__device__ __forceinline__ unsigned pack_tagged(float lo, float hi, unsigned par) {
+  return bf16_tagged(lo, par) | (bf16_rne(hi) << 16);
 }
 
 // Philox4x32-10, one draw per (utterance, step)
@@ -272,372 +324,530 @@ struct GenArgsDev {
 };
 
 struct Smem {
-  __nv_bfloat16* A;   // [CHUNK][pitchA]   past | current   (or z / skip / head-1 rows)
-  __nv_bfloat16* H;   // [Bpad][pitchH]    aux rows of the current step (all chunks)
-  __nv_bfloat16* W;   // weight tile(s) of the current phase
-  float* P;           // [8 warps][CHUNK][8] partial sums
-  float* xcarry;      // [Bpad][4] fp32 residual stream of the owned channels
-  float* skipacc;     // [Bpad][4]
-  int* look;          // [Bpad] ring slot of the past tap for the current adaptive block
-  int* flag;          // [1] watchdog
+  __nv_bfloat16* A;    // [CHUNK][pitchA]  polled operand rows (x(t) / z / skip / head-1)
+  __nv_bfloat16* H;    // [Bpad][pitchH]   aux rows of the current step
+  __nv_bfloat16* W0;   // double-buffered weight tiles (current phase / prefetch of the next): W0 + sel*wstride
+  int wstride;
+  float* P;            // [8 warps][CHUNK][16] partial sums
+  float* Pp0;          // [2][Bpad][8] prefetched past-tap partial sums P(t-k), double-buffered
+  int ppstride;
+  float* Hraw;         // [Bpad][A] fp32 aux frame currently in use
+  __device__ __forceinline__ __nv_bfloat16* W(int sel) const { return W0 + sel * wstride; }
+  __device__ __forceinline__ float* Pp(int sel) const { return Pp0 + sel * ppstride; }
+  float* xcarry;       // [Bpad][4] fp32 residual stream of the owned channels
+  float* skipacc;      // [Bpad][4]
+  int* abort;          // [1]
 };
 
-// K-split MMA over one chunk: acc (per warp) = A[chunk rows][K] * W[8 rows][K]^T
-__device__ __forceinline__ void mma_chunk(const Smem& sm, int pitchA, int pitchW, int pitchH, const __nv_bfloat16* Wt,
-                                          int ks_main, int ks_aux, int chunk, int mtiles, float (&acc)[2][4]) {
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-#pragma unroll
-  for (int i = 0; i < 2; ++i)
-#pragma unroll
-    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
-  const int arow = lane & 15, acol = (lane >> 4) * 8;
-  const int brow = lane & 7, bcol = ((lane >> 3) & 1) * 8;
-  for (int ks = warp; ks < ks_main + ks_aux; ks += GEN_WARPS) {
-    unsigned b0, b1;
-    ldmatrix_x2(b0, b1, Wt + brow * pitchW + ks * 16 + bcol);
-    for (int mt = 0; mt < mtiles; ++mt) {
-      const __nv_bfloat16* ap = ks < ks_main
-                                    ? sm.A + (mt * 16 + arow) * pitchA + ks * 16 + acol
-                                    : sm.H + (chunk * CHUNK + mt * 16 + arow) * pitchH + (ks - ks_main) * 16 + acol;
-      unsigned a0, a1, a2, a3;
-      ldmatrix_x4(a0, a1, a2, a3, ap);
-      mma_bf16(acc[mt], a0, a1, a2, a3, b0, b1);
-    }
-  }
-  // scatter the warp's partial C fragments: P[warp][m][n]
-  float* pw = sm.P + warp * CHUNK * 8;
-  const int r = lane >> 2, c = (lane & 3) * 2;
-#pragma unroll
-  for (int mt = 0; mt < 2; ++mt) {
-    pw[(mt * 16 + r) * 8 + c] = acc[mt][0];
-    pw[(mt * 16 + r) * 8 + c + 1] = acc[mt][1];
-    pw[(mt * 16 + r + 8) * 8 + c] = acc[mt][2];
-    pw[(mt * 16 + r + 8) * 8 + c + 1] = acc[mt][3];
-  }
+struct Watch {
+  long long t0;
+  __device__ __forceinline__ Watch() : t0(0) {}
+};
+
+// spin bookkeeping: returns true when the watchdog fired or another CTA already failed
+__device__ __forceinline__ bool spin_failed(const GenPlan& p, unsigned& spins, long long& t0) {
+  if ((++spins & 1023u) != 0) return false;
+  if (t0 == 0) t0 = clock64();
+  if (*((volatile int32_t*)p.status) != 0) return true;
+  if (clock64() - t0 > GEN_TIMEOUT_CYCLES) { atomicExch(p.status, QP_ETIMEOUT); return true; }
+  return false;
 }
 
-__device__ __forceinline__ float reduce_partials(const Smem& sm) {
-  // thread t owns output (m = t / 8, n = t % 8)
-  float s = 0.f;
+// Poll CHUNK rows of K tagged bf16 from an exchange buffer into sm.A (row pitch pitchA).
+// Every 32-bit word must carry tag `par`.  First an optimistic round over all of this
+// thread's chunks; while something is still stale only ONE chunk is probed per round (failed
+// probes are pure L2 traffic shared by 128 CTAs), and a hit triggers another full round.
+// Returns nonzero when the watchdog fired.
+__device__ __forceinline__ int poll_rows(const Smem& sm, const GenPlan& p, const __nv_bfloat16* src, int K, int chunk,
+                                         unsigned par, int pitchA) {
+  const int row = threadIdx.x >> 3, c0 = threadIdx.x & 7;
+  const int nchunks = K >> 3;
+  const uint4* g = (const uint4*)(src + (size_t)(chunk * CHUNK + row) * K);
+  uint4* d = (uint4*)(sm.A + row * pitchA);
+  int fail = 0;
+  for (int cb = c0; cb < nchunks && !fail; cb += 64) {
+    uint4 v[8];
+    unsigned pend = 0;
 #pragma unroll
-  for (int w = 0; w < GEN_WARPS; ++w) s += sm.P[w * CHUNK * 8 + threadIdx.x];
-  return s;
+    for (int i = 0; i < 8; ++i)
+      if (cb + 8 * i < nchunks) pend |= 1u << i;
+    unsigned spins = 0;
+    long long t0 = 0;
+    bool burst = true;
+    while (pend) {
+      if (burst) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+          if (pend & (1u << i)) v[i] = ld_strong_v4(g + cb + 8 * i);
+        unsigned before = pend;
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+          if (pend & (1u << i)) {
+            unsigned bad = ((v[i].x ^ par) | (v[i].y ^ par) | (v[i].z ^ par) | (v[i].w ^ par)) & 1u;
+            if (!bad) { d[cb + 8 * i] = v[i]; pend &= ~(1u << i); }
+          }
+        burst = pend != before && pend != 0;   // progress: try the rest again right away
+      } else {
+        const int i = __ffs(pend) - 1;
+        uint4 w = ld_strong_v4(g + cb + 8 * i);
+        unsigned bad = ((w.x ^ par) | (w.y ^ par) | (w.z ^ par) | (w.w ^ par)) & 1u;
+        if (!bad) { d[cb + 8 * i] = w; pend &= ~(1u << i); burst = true; }
+        else if (spin_failed(p, spins, t0)) { fail = 1; break; }
+      }
+    }
+  }
+  return fail;
 }
 
 // copy `rows` weight rows of K bf16 from global (pitch K) to smem (pitch pitchW), async
 __device__ __forceinline__ void load_weights_async(__nv_bfloat16* dst, int pitchW, const __nv_bfloat16* src, int rows, int K) {
-  const int cpr = K / 8;
-  for (int e = threadIdx.x; e < rows * cpr; e += GEN_THREADS) {
-    int r = e / cpr, c = e % cpr;
-    cp_async16(dst + r * pitchW + c * 8, src + (size_t)r * K + c * 8);
-  }
+  const int cpr = K >> 3;
+  for (int r = threadIdx.x >> 5; r < rows; r += GEN_WARPS)
+    for (int c = threadIdx.x & 31; c < cpr; c += 32) cp_async16(dst + r * pitchW + c * 8, src + (size_t)r * K + c * 8);
 }
-// copy one row of K bf16 per utterance of the chunk into sm.A at column col0, async
-__device__ __forceinline__ void load_rows_async(const Smem& sm, int pitchA, int col0, const __nv_bfloat16* base,
-                                                size_t slot_stride, const int* slots, int fixed_slot, int chunk,
-                                                int K, int ldsrc) {
-  const int cpr = K / 8;
-  for (int e = threadIdx.x; e < CHUNK * cpr; e += GEN_THREADS) {
-    int m = e / cpr, c = e % cpr;
-    int u = chunk * CHUNK + m;
-    int slot = slots ? slots[u] : fixed_slot;
-    cp_async16(sm.A + m * pitchA + col0 + c * 8, base + slot * slot_stride + (size_t)u * ldsrc + c * 8);
+
+__device__ __forceinline__ void store_partials(float* pw, const float (&acc)[2][4], int lane, int ncols, int col0) {
+  const int r = lane >> 2, c = col0 + (lane & 3) * 2;
+#pragma unroll
+  for (int mt = 0; mt < 2; ++mt) {
+    pw[(mt * 16 + r) * ncols + c] = acc[mt][0];
+    pw[(mt * 16 + r) * ncols + c + 1] = acc[mt][1];
+    pw[(mt * 16 + r + 8) * ncols + c] = acc[mt][2];
+    pw[(mt * 16 + r + 8) * ncols + c + 1] = acc[mt][3];
   }
 }
 
-__device__ __forceinline__ void barrier_arrive(const GenPlan& p) {
-  __syncthreads();
-  if (threadIdx.x == 0) red_release_add_u64(p.barrier, 1ULL);
-}
-// returns false when the watchdog fired (every thread of the CTA gets the same answer)
-__device__ __forceinline__ bool barrier_wait(const GenPlan& p, const Smem& sm, unsigned long long target) {
-  if (threadIdx.x == 0) {
-    long long t0 = clock64();
-    int ok = 1;
-    while (ld_acquire_u64(p.barrier) < target) {
-      if (clock64() - t0 > GEN_TIMEOUT_CYCLES || *((volatile int32_t*)p.status) != 0) {
-        atomicExch(p.status, QP_ETIMEOUT);
-        ok = 0;
-        break;
-      }
-    }
-    *sm.flag = ok;
+// one n-tile: acc = A[chunk rows][K] * Wt[8 rows][K]^T, K split over the warps, partials to sm.P (16 cols).
+// Both m16 tiles are always computed (rows of padded utterances are finite garbage).
+__device__ __forceinline__ void mma_tile(const Smem& sm, int pitchA, const __nv_bfloat16* Wt, int pitchW, int ksteps,
+                                         int col0) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float acc[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+  const __nv_bfloat16* ap = sm.A + (lane & 15) * pitchA + (lane >> 4) * 8;
+  const __nv_bfloat16* bp = Wt + (lane & 7) * pitchW + ((lane >> 3) & 1) * 8;
+  for (int ks = warp; ks < ksteps; ks += GEN_WARPS) {
+    unsigned b0, b1, a0, a1, a2, a3;
+    ldmatrix_x2(b0, b1, bp + ks * 16);
+    ldmatrix_x4(a0, a1, a2, a3, ap + ks * 16);
+    mma_bf16(acc[0], a0, a1, a2, a3, b0, b1);
+    ldmatrix_x4(a0, a1, a2, a3, ap + 16 * pitchA + ks * 16);
+    mma_bf16(acc[1], a0, a1, a2, a3, b0, b1);
   }
-  __syncthreads();
-  return *sm.flag != 0;
+  store_partials(sm.P + warp * CHUNK * 16, acc, lane, 16, col0);
+}
+
+// Sampling of one utterance by one warp (qpnet.py:505-512): poll the tagged logits, softmax,
+// inverse CDF on a uniform (or argmax).  PER = logits per lane (contiguous span, so the prefix
+// sum runs in symbol order).  Returns the symbol, or -1 when the watchdog fired.
+template <int PER>
+__device__ __forceinline__ int sample_symbol(const GenPlan& p, const GenArgsDev& g, const Smem& sm, int u, int t, int lane) {
+  const int Q = p.Q;
+  const float* lg = p.logitbuf + (size_t)u * Q;
+  const unsigned par_t = (unsigned)t & 1u;
+  const int per = (Q + 31) / 32;
+  float v[PER];
+  unsigned pend = 0;
+#pragma unroll
+  for (int i = 0; i < PER; ++i) {
+    v[i] = -INFINITY;
+    if (i < per && lane * per + i < Q) pend |= 1u << i;
+  }
+  unsigned spins = 0;
+  long long t0 = 0;
+  int bad = 0;
+  while (pend) {
+    unsigned w[PER];
+#pragma unroll
+    for (int i = 0; i < PER; ++i)
+      if (pend & (1u << i)) w[i] = ld_strong_u32(lg + lane * per + i);
+#pragma unroll
+    for (int i = 0; i < PER; ++i)
+      if ((pend & (1u << i)) && ((w[i] ^ par_t) & 1u) == 0) { v[i] = __uint_as_float(w[i]); pend &= ~(1u << i); }
+    if (pend && spin_failed(p, spins, t0)) { bad = 1; break; }
+  }
+  if (__any_sync(0xffffffffu, bad)) {
+    if (lane == 0) *sm.abort = 1;
+    return -1;
+  }
+  float mx = -INFINITY;
+  int amax = 0;
+#pragma unroll
+  for (int i = 0; i < PER; ++i)
+    if (v[i] > mx) { mx = v[i]; amax = lane * per + i; }
+  if (g.logits_out && t < g.n_samples[u]) {
+    float* lo = g.logits_out + ((size_t)u * g.max_steps + t) * Q;
+#pragma unroll
+    for (int i = 0; i < PER; ++i)
+      if (i < per && lane * per + i < Q) lo[lane * per + i] = v[i];
+  }
+  // warp arg-max (first maximum wins)
+  float wmx = mx;
+  int wam = amax;
+  for (int o = 16; o; o >>= 1) {
+    float om = __shfl_xor_sync(0xffffffffu, wmx, o);
+    int oa = __shfl_xor_sync(0xffffffffu, wam, o);
+    if (om > wmx || (om == wmx && oa < wam)) { wmx = om; wam = oa; }
+  }
+  int sym;
+  if (g.mode == QP_MODE_ARGMAX) {
+    sym = wam;
+  } else {
+    float local = 0.f;
+#pragma unroll
+    for (int i = 0; i < PER; ++i) { v[i] = __expf(v[i] - wmx); local += v[i]; }   // exp(-inf) = 0 for padding
+    float incl = local;
+    for (int o = 1; o < 32; o <<= 1) {
+      float nb = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += nb;
+    }
+    float total = __shfl_sync(0xffffffffu, incl, 31);
+    float uu = g.uniforms ? g.uniforms[(long long)u * g.ld_uniforms + t] : philox_uniform(g.philox_seed, u, t);
+    float target = uu * total;
+    float run = incl - local;
+    int cnt = 0;
+#pragma unroll
+    for (int i = 0; i < PER; ++i) { run += v[i]; if (i < per && lane * per + i < Q && run <= target) ++cnt; }
+    for (int o = 16; o; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+    sym = min(cnt, Q - 1);
+  }
+  if (lane == 0 && t < g.n_samples[u]) g.out[(long long)u * g.ld_out + t] = sym;
+  return sym;
 }
 
 __global__ void __launch_bounds__(GEN_THREADS, 1) gen_kernel(GenPlan p, GenArgsDev g) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  const int C = p.C, S = p.S, Q = p.Q, A = p.A, Ap = p.Ap, L = p.L;
-  const int pitchA = 2 * C + 8, pitchH = Ap + 8, pitchWg = p.Kg + 8, pitchWc = C + 8, pitchWs = S + 8;
+  const int C = p.C, S = p.S, Q = p.Q, A = p.A, Ap = p.Ap, L = p.L, Kc = p.Kc;
+  const int pitchA = max(C, S) + 8, pitchH = Ap + 8, pitchWc = Kc + 8, pitchWp = C + 8, pitchWs = S + 8;
+  const int wtile_elems = max(8 * pitchWc + 8 * pitchWp, 8 * max(p.nt1, p.nt2) * pitchWs);
   Smem sm;
   {
     unsigned char* q = smem_raw;
     sm.A = (__nv_bfloat16*)q; q += (size_t)CHUNK * pitchA * 2;
     sm.H = (__nv_bfloat16*)q; q += (size_t)p.Bpad * pitchH * 2;
-    int wrows = 8 * max(1, max(p.nt1, p.nt2));
-    int wpitch = max(pitchWg, pitchWs);
-    sm.W = (__nv_bfloat16*)q; q += (size_t)wrows * wpitch * 2;
-    sm.P = (float*)q; q += GEN_WARPS * CHUNK * 8 * 4;
+    sm.W0 = (__nv_bfloat16*)q; q += (size_t)wtile_elems * 2 * 2; sm.wstride = wtile_elems;
+    sm.P = (float*)q; q += GEN_WARPS * CHUNK * 16 * 4;
+    sm.Pp0 = (float*)q; q += (size_t)p.Bpad * 8 * 4 * 2; sm.ppstride = p.Bpad * 8;
+    sm.Hraw = (float*)q; q += (size_t)p.Bpad * p.A * 4;
     sm.xcarry = (float*)q; q += (size_t)p.Bpad * 4 * 4;
     sm.skipacc = (float*)q; q += (size_t)p.Bpad * 4 * 4;
-    sm.look = (int*)q; q += (size_t)p.Bpad * 4;
-    sm.flag = (int*)q;
+    sm.abort = (int*)q;
   }
   const int s = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int nCTA = p.nCTA, B = p.B;
-  const size_t rowC = (size_t)p.Bpad * C;  // elements per ring slot
-  unsigned long long epoch = 0;
-  const int m_own = tid >> 3, n_own = tid & 7;  // (utterance-in-chunk, output row) reduced by this thread
+  const int nCTA = p.nCTA, B = p.B, Bpad = p.Bpad;
+  const int m_own = tid >> 3, n_own = tid & 7;  // (utterance-in-chunk, output row) finished by this thread
   const long long ldd = (long long)p.F * p.U;
+  const int half = Q / 2;
+  const int nphase = 2 * L + 3;
+  int wsel = 0;  // weight buffer holding the CURRENT phase's tiles
 
-  // zero the operand tiles once so that padded utterance rows stay finite
   for (int e = tid; e < CHUNK * pitchA; e += GEN_THREADS) sm.A[e] = __float2bfloat16(0.f);
-  for (int e = tid; e < p.Bpad * pitchH; e += GEN_THREADS) sm.H[e] = __float2bfloat16(0.f);
+  for (int e = tid; e < Bpad * pitchH; e += GEN_THREADS) sm.H[e] = __float2bfloat16(0.f);
+  if (tid == 0) *sm.abort = 0;
   __syncthreads();
 
-  // ---- symbol state + x0 for step -1 (priming constant) ---------------------------------
-  // sampling-phase style work item: global warp gw handles utterance gw
+  auto trace = [&](int t, int phase, int ev) {
+    if (s == 0 && tid == 0 && t >= p.trace_step0 && t < p.trace_step0 + p.trace_nsteps)
+      p.trace[((size_t)(t - p.trace_step0) * nphase + phase) * TRACE_EVENTS + ev] = clock64();
+  };
+
+  // ring slot / P prefetch for gate(t, l): P(t-k) rows of every utterance -> sm.Pp(l & 1)
+  auto prefetch_past = [&](int t, int l) {
+    const int rmask = p.ring_size[l] - 1;
+    const float* ring = p.Pring[l];
+    float* dst = sm.Pp(l & 1);
+    for (int e = tid; e < Bpad * 2; e += GEN_THREADS) {
+      const int u = e >> 1, hf = e & 1;
+      int k = p.dil[l];
+      if (l >= p.nF) {  // pitch-dependent look-back of this step (qpnet.py:476-483, 613-624)
+        k = 0;
+        if (u < B && t >= 0)
+          k = g.d_is_f64 ? -gen_index_f64(((const double*)g.d)[(long long)u * ldd + t], p.dil[l])
+                         : -gen_index_f32(((const float*)g.d)[(long long)u * ldd + t], p.dil[l]);
+        if (k <= 0 || k > p.depth[l]) k = p.depth[l];  // k == 0: python index 0 = oldest entry (C4)
+      }
+      const int slot = (t - k) & rmask;
+      cp_async16(dst + u * 8 + hf * 4, ring + (((size_t)slot * nCTA + s) * Bpad + u) * 8 + hf * 4);
+    }
+  };
+  auto prefetch_gate = [&](int t, int l, int wdst) {
+    const __nv_bfloat16* Wg = p.WgG + ((size_t)l * nCTA + s) * 8 * (Kc + C);
+    load_weights_async(sm.W(wdst), pitchWc, Wg, 8, Kc);
+    load_weights_async(sm.W(wdst) + 8 * pitchWc, pitchWp, Wg + 8 * Kc, 8, C);
+    if (t >= 0) prefetch_past(t, l);
+    cp_async_commit();
+  };
+
+  // next causal-layer output x0(t_next) = E0[prev] + E1[cur] + b  (qpnet.py:447-448, 561-564)
   auto write_x0 = [&](int u, int prev, int cur, int t_next) {
-    // ring[0] slot(t_next) <- bf16(E0[prev] + E1[cur] + b)   (qpnet.py:447-448, 561-564)
-    int slot = t_next & (p.ring_size[0] - 1);
-    __nv_bfloat16* dst = p.ring[0] + (size_t)slot * rowC + (size_t)u * C;
+    const unsigned par = (unsigned)(t_next + 1) & 1u;
+    __nv_bfloat16* dst = p.xbuf + (size_t)u * C;
     const float* e0 = p.E0 + (size_t)prev * C;
     const float* e1 = p.E1 + (size_t)cur * C;
     for (int c = lane * 4; c < C; c += 128) {
       float4 a = *(const float4*)(e0 + c), b = *(const float4*)(e1 + c), bb = *(const float4*)(g.causal_b + c);
-      __nv_bfloat162 lo = __floats2bfloat162_rn(a.x + b.x + bb.x, a.y + b.y + bb.y);
-      __nv_bfloat162 hi = __floats2bfloat162_rn(a.z + b.z + bb.z, a.w + b.w + bb.w);
-      uint2 v; v.x = *(unsigned*)&lo; v.y = *(unsigned*)&hi;
-      *(uint2*)(dst + c) = v;
+      st_strong_v2(dst + c, pack_tagged(a.x + b.x + bb.x, a.y + b.y + bb.y, par),
+                   pack_tagged(a.z + b.z + bb.z, a.w + b.w + bb.w, par));
     }
   };
-  const int half = Q / 2;
-  for (int u = s * GEN_WARPS + warp; u < p.Bpad; u += nCTA * GEN_WARPS) {
+
+  // aux rows of step tt: h_up[:, ta] = h[:, ta / U] * w[ta % U] + b, ta = max(tt, 0) (replicate pad, qpnet.py:359;
+  // 143-158, 451).  The frame is cached in smem (fp32) and refreshed when ta crosses a frame boundary.
+  auto make_aux = [&](int tt) {
+    if (tt >= g.max_steps) return;
+    const int ta = tt < 0 ? 0 : tt;
+    const int f = ta / p.U, j = ta - f * p.U;
+    if (j == 0 || tt <= 0) {
+      for (int e = tid; e < B * A; e += GEN_THREADS) {
+        int u = e / A, a = e - u * A;
+        sm.Hraw[e] = g.h[((size_t)u * A + a) * p.F + f];
+      }
+      __syncthreads();
+    }
+    const float w = g.up_w[j], bb = g.up_b[0];
+    for (int e = tid; e < B * A; e += GEN_THREADS) {
+      int u = e / A, a = e - u * A;
+      sm.H[u * pitchH + a] = __float2bfloat16(sm.Hraw[e] * w + bb);
+    }
+  };
+  make_aux(-1);
+
+  // ---- symbol state + x0 for step -1 (the constant of the priming region) ---------------
+  for (int u = s * GEN_WARPS + warp; u < Bpad; u += nCTA * GEN_WARPS) {
     write_x0(u, half, half, -1);
-    if (lane == 0) p.symbuf[u] = make_int2(half, half);
+    if (lane == 0) st_strong_v2(p.symbuf + u, (unsigned)half, (unsigned)half);  // version 0: tag bit 30 = 0
   }
-  barrier_arrive(p); ++epoch;
+  prefetch_gate(-1, 0, wsel);
 
   // =========================================================================== time loop
   for (int t = -1; t < g.max_steps; ++t) {
     const bool prime = t < 0;
-    const int ta = prime ? 0 : t;  // aux / d position (replicate pad: qpnet.py:359)
-    // ---- aux rows of this step: h_up[:, ta] = h[:, ta / U] * w[ta % U] + b  (qpnet.py:143-158, 451)
-    {
-      const int f = ta / p.U, j = ta % p.U;
-      const float w = g.up_w[j], bb = g.up_b[0];
-      for (int e = tid; e < B * A; e += GEN_THREADS) {
-        int u = e / A, a = e % A;
-        sm.H[u * pitchH + a] = __float2bfloat16(g.h[((size_t)u * A + a) * p.F + f] * w + bb);
-      }
-    }
+    const unsigned par_x = (unsigned)(t + 1) & 1u;
     for (int l = 0; l < L; ++l) {
       // ================================================================ gate phase
-      const __nv_bfloat16* Wg = p.WgG + ((size_t)l * nCTA + s) * 8 * p.Kg;
-      load_weights_async(sm.W, pitchWg, Wg, 8, p.Kg);
-      const int rmask = p.ring_size[l] - 1;
-      const int cur_slot = t & rmask;
-      if (l >= p.nF && !prime) {
-        // pitch-dependent look-back of this step (qpnet.py:476-483, 613-624)
-        const int dil = p.dil[l];
-        for (int u = tid; u < p.Bpad; u += GEN_THREADS) {
-          int k = 0;
-          if (u < B) {
-            k = g.d_is_f64 ? -gen_index_f64(((const double*)g.d)[(long long)u * ldd + t], dil)
-                           : -gen_index_f32(((const float*)g.d)[(long long)u * ldd + t], dil);
-            if (k <= 0 || k > p.depth[l]) k = p.depth[l];  // k == 0: python index 0 = oldest entry (C4)
-          }
-          sm.look[u] = (t - k) & rmask;
-        }
+      trace(t, 2 * l, 0);
+      {  // prefetch the res/skip tile of this block into the other weight buffer
+        load_weights_async(sm.W(wsel ^ 1), pitchWp, p.WrsG + ((size_t)l * nCTA + s) * 8 * C, 8, C);
+        cp_async_commit();
       }
-      cp_async_commit();
-      if (!barrier_wait(p, sm, epoch * nCTA)) return;  // (its __syncthreads also publishes sm.look)
-      if (l == 0) {  // after the barrier: symbuf was written by the sampling phase of other CTAs
+      int fail = 0;
+      if (l == 0) {
         // fp32 residual stream of the owned channels restarts from the causal layer
-        for (int u = tid; u < p.Bpad; u += GEN_THREADS) {
-          int2 sy = __ldcg(p.symbuf + u);
-          float4 a = *(const float4*)(p.E0 + (size_t)sy.x * C + 4 * s);
-          float4 b = *(const float4*)(p.E1 + (size_t)sy.y * C + 4 * s);
+        const unsigned vtag = ((unsigned)(t + 1) & 1u) << 30;
+        for (int u = tid; u < Bpad; u += GEN_THREADS) {
+          uint2 sy;
+          unsigned spins = 0; long long t0 = 0;
+          while (true) {
+            sy = ld_strong_v2(p.symbuf + u);
+            if (((sy.x ^ vtag) & 0x40000000u) == 0 && ((sy.y ^ vtag) & 0x40000000u) == 0) break;
+            if (spin_failed(p, spins, t0)) { fail = 1; break; }
+          }
+          int prev = (int)(sy.x & 0xFFFFu) % Q, cur = (int)(sy.y & 0xFFFFu) % Q;
+          float4 a = *(const float4*)(p.E0 + (size_t)prev * C + 4 * s);
+          float4 b = *(const float4*)(p.E1 + (size_t)cur * C + 4 * s);
           float4 bb = *(const float4*)(g.causal_b + 4 * s);
-          float4 v = make_float4(a.x + b.x + bb.x, a.y + b.y + bb.y, a.z + b.z + bb.z, a.w + b.w + bb.w);
-          *(float4*)(sm.xcarry + u * 4) = v;
+          *(float4*)(sm.xcarry + u * 4) = make_float4(a.x + b.x + bb.x, a.y + b.y + bb.y, a.z + b.z + bb.z, a.w + b.w + bb.w);
           *(float4*)(sm.skipacc + u * 4) = make_float4(0.f, 0.f, 0.f, 0.f);
         }
       }
+      const int gphase = (t + 1) * L + l;
+      const unsigned par_z = (unsigned)gphase & 1u;
       for (int ch = 0; ch < p.nchunk; ++ch) {
-        const int mtiles = (B - ch * CHUNK) > 16 ? 2 : 1;
-        if (prime || l < p.nF) {
-          int past_slot = prime ? cur_slot : ((t - p.dil[l]) & rmask);
-          load_rows_async(sm, pitchA, 0, p.ring[l], rowC, nullptr, past_slot, ch, C, C);
-        } else {
-          load_rows_async(sm, pitchA, 0, p.ring[l], rowC, sm.look, 0, ch, C, C);
+        fail |= poll_rows(sm, p, p.xbuf + (size_t)l * Bpad * C, C, ch, par_x, pitchA);
+        cp_async_wait<1>();  // this phase's weights + past partial sums have landed (prefetch stays in flight)
+        if (__syncthreads_or(fail | *sm.abort)) return;
+        trace(t, 2 * l, 1);
+        // current-tap tile (K = C + aux) and past-tap tile (K = C), K split over the warps
+        {
+          const __nv_bfloat16* Wc = sm.W(wsel);
+          const __nv_bfloat16* Wp = Wc + 8 * pitchWc;
+          float accc[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}}, accp[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+          const int arow = lane & 15, acol = (lane >> 4) * 8;
+          const int boff = ((lane >> 3) & 1) * 8;
+          const __nv_bfloat16* ap = sm.A + arow * pitchA + acol;
+          const __nv_bfloat16* bc = Wc + (lane & 7) * pitchWc + boff;
+          const __nv_bfloat16* bq = Wp + (lane & 7) * pitchWp + boff;
+          const int ksm = C / 16, ksa = Ap / 16;
+          for (int ks = warp; ks < ksm; ks += GEN_WARPS) {
+            unsigned b0, b1, q0, q1, a0, a1, a2, a3;
+            ldmatrix_x2(b0, b1, bc + ks * 16);
+            ldmatrix_x2(q0, q1, bq + ks * 16);
+            ldmatrix_x4(a0, a1, a2, a3, ap + ks * 16);
+            mma_bf16(accc[0], a0, a1, a2, a3, b0, b1);
+            mma_bf16(accp[0], a0, a1, a2, a3, q0, q1);
+            ldmatrix_x4(a0, a1, a2, a3, ap + 16 * pitchA + ks * 16);
+            mma_bf16(accc[1], a0, a1, a2, a3, b0, b1);
+            mma_bf16(accp[1], a0, a1, a2, a3, q0, q1);
+          }
+          if (warp < ksa) {  // aux columns of the current-tap tile (qpnet.py:663-664 / 632-633)
+            const __nv_bfloat16* hp = sm.H + (ch * CHUNK + arow) * pitchH + warp * 16 + acol;
+            unsigned b0, b1, a0, a1, a2, a3;
+            ldmatrix_x2(b0, b1, bc + (ksm + warp) * 16);
+            ldmatrix_x4(a0, a1, a2, a3, hp);
+            mma_bf16(accc[0], a0, a1, a2, a3, b0, b1);
+            ldmatrix_x4(a0, a1, a2, a3, hp + 16 * pitchH);
+            mma_bf16(accc[1], a0, a1, a2, a3, b0, b1);
+          }
+          float* pw = sm.P + warp * CHUNK * 16;
+          store_partials(pw, accc, lane, 16, 0);
+          store_partials(pw, accp, lane, 16, 8);
         }
-        load_rows_async(sm, pitchA, C, p.ring[l], rowC, nullptr, cur_slot, ch, C, C);
-        cp_async_commit();
-        cp_async_wait_all();
         __syncthreads();
-        float acc[2][4];
-        mma_chunk(sm, pitchA, pitchWg, pitchH, sm.W, 2 * C / 16, Ap / 16, ch, mtiles, acc);
-        __syncthreads();
-        float pre = reduce_partials(sm) + p.bgG[((size_t)l * nCTA + s) * 8 + n_own];
-        // rows 0-3 sigmoid, 4-7 tanh of channels 4s..4s+3: pair lanes n and n+4
-        float other = __shfl_down_sync(0xffffffffu, pre, 4);
-        if (n_own < 4) {
+        trace(t, 2 * l, 2);
+        {
+          float cur = 0.f, pnew = 0.f;
+#pragma unroll
+          for (int w = 0; w < GEN_WARPS; ++w) {
+            cur += sm.P[w * CHUNK * 16 + m_own * 16 + n_own];
+            pnew += sm.P[w * CHUNK * 16 + m_own * 16 + 8 + n_own];
+          }
+          const int u = ch * CHUNK + m_own;
+          // store P'(t) for step t+k; during priming fill the whole ring with the constant
+          float* ring = p.Pring[l] + ((size_t)s * Bpad + u) * 8 + n_own;
+          const size_t slot_stride = (size_t)nCTA * Bpad * 8;
+          const int rs = p.ring_size[l];
+          if (prime) {
+            for (int sl = 0; sl < rs; ++sl) ring[(size_t)sl * slot_stride] = pnew;
+          } else {
+            ring[(size_t)(t & (rs - 1)) * slot_stride] = pnew;
+          }
+          const float past = prime ? pnew : sm.Pp(l & 1)[u * 8 + n_own];
+          float pre = cur + past + p.bgG[((size_t)l * nCTA + s) * 8 + n_own];
+          // rows 0-3 sigmoid, 4-7 tanh of channels 4s..4s+3: pair lanes n and n+4
+          float other = __shfl_down_sync(0xffffffffu, pre, 4);
           float z = fast_sigmoid(pre) * fast_tanh(other);
-          p.zbuf[(size_t)(ch * CHUNK + m_own) * C + 4 * s + n_own] = __float2bfloat16(z);
+          float znext = __shfl_down_sync(0xffffffffu, z, 1);
+          if (n_own < 4 && !(n_own & 1))
+            st_strong_u32(p.zbuf + (size_t)u * C + 4 * s + n_own, pack_tagged(z, znext, par_z));
         }
-        __syncthreads();  // sm.A / sm.P reusable
+        if (p.nchunk > 1) __syncthreads();
       }
-      barrier_arrive(p); ++epoch;
+      wsel ^= 1;
+      trace(t, 2 * l, 3);
 
       // ================================================================ res / skip phase
-      const __nv_bfloat16* Wr = p.WrsG + ((size_t)l * nCTA + s) * 8 * C;
-      load_weights_async(sm.W, pitchWc, Wr, 8, C);
-      cp_async_commit();
-      if (!barrier_wait(p, sm, epoch * nCTA)) return;
+      trace(t, 2 * l + 1, 0);
       const bool last = (l == L - 1);
-      for (int ch = 0; ch < p.nchunk; ++ch) {
-        const int mtiles = (B - ch * CHUNK) > 16 ? 2 : 1;
-        load_rows_async(sm, pitchA, 0, p.zbuf, 0, nullptr, 0, ch, C, C);
+      if (last) make_aux(t + 1);   // sm.H is free now: build the next step's aux rows off the critical path
+      if (!last) prefetch_gate(t, l + 1, wsel ^ 1);
+      else if (!prime) {
+        load_weights_async(sm.W(wsel ^ 1), pitchWs, p.W1G + (size_t)s * p.nt1 * 8 * S, p.nt1 * 8, S);
         cp_async_commit();
-        cp_async_wait_all();
-        __syncthreads();
-        float acc[2][4];
-        mma_chunk(sm, pitchA, pitchWc, pitchH, sm.W, C / 16, 0, ch, mtiles, acc);
-        __syncthreads();
-        float v = reduce_partials(sm) + p.brsG[((size_t)l * nCTA + s) * 8 + n_own];
-        const int u = ch * CHUNK + m_own;
-        if (n_own < 4) {
-          if (!last) {  // the last block's residual projection is dead (qpnet.py:491, caveat C7)
-            float xn = v + sm.xcarry[u * 4 + n_own];
-            sm.xcarry[u * 4 + n_own] = xn;
-            __nv_bfloat16 xb = __float2bfloat16(xn);
-            __nv_bfloat16* ring = p.ring[l + 1];
-            const int rs = p.ring_size[l + 1];
-            if (prime) {
-              for (int sl = 0; sl < rs; ++sl) ring[(size_t)sl * rowC + (size_t)u * C + 4 * s + n_own] = xb;
-            } else {
-              ring[(size_t)(t & (rs - 1)) * rowC + (size_t)u * C + 4 * s + n_own] = xb;
-            }
-          }
-        } else if (n_own - 4 < p.spc) {
-          float sk = sm.skipacc[u * 4 + n_own - 4] + v;
-          sm.skipacc[u * 4 + n_own - 4] = sk;
-          int sr = s * p.spc + n_own - 4;
-          if (last && sr < S) p.skipbuf[(size_t)u * S + sr] = __float2bfloat16(fmaxf(sk, 0.f));
-        }
-        __syncthreads();
+      } else {
+        prefetch_gate(0, 0, wsel ^ 1);
       }
-      barrier_arrive(p); ++epoch;
+      for (int ch = 0; ch < p.nchunk; ++ch) {
+        fail = poll_rows(sm, p, p.zbuf, C, ch, par_z, pitchA);
+        cp_async_wait<1>();
+        if (__syncthreads_or(fail | *sm.abort)) return;
+        trace(t, 2 * l + 1, 1);
+        mma_tile(sm, pitchA, sm.W(wsel), pitchWp, C / 16, 0);
+        __syncthreads();
+        trace(t, 2 * l + 1, 2);
+        float v = 0.f;
+#pragma unroll
+        for (int w = 0; w < GEN_WARPS; ++w) v += sm.P[w * CHUNK * 16 + m_own * 16 + n_own];
+        v += p.brsG[((size_t)l * nCTA + s) * 8 + n_own];
+        const int u = ch * CHUNK + m_own;
+        float outv;
+        if (n_own < 4) {
+          outv = v + sm.xcarry[u * 4 + n_own];
+          sm.xcarry[u * 4 + n_own] = outv;
+        } else {
+          outv = sm.skipacc[u * 4 + n_own - 4] + v;
+          sm.skipacc[u * 4 + n_own - 4] = outv;
+          outv = fmaxf(outv, 0.f);
+        }
+        float nxt = __shfl_down_sync(0xffffffffu, outv, 1);
+        if (!(n_own & 1)) {
+          if (n_own < 4) {
+            // the last block's residual projection is dead (qpnet.py:491, caveat C7)
+            if (!last)
+              st_strong_u32(p.xbuf + ((size_t)(l + 1) * Bpad + u) * C + 4 * s + n_own, pack_tagged(outv, nxt, par_x));
+          } else if (last && !prime && n_own - 4 < p.spc) {
+            int sr = s * p.spc + n_own - 4;
+            if (sr < S) st_strong_u32(p.skipbuf + (size_t)u * S + sr, pack_tagged(outv, nxt, (unsigned)t & 1u));
+          }
+        }
+        if (p.nchunk > 1) __syncthreads();
+      }
+      wsel ^= 1;
+      trace(t, 2 * l + 1, 3);
     }
 
     if (!prime) {
+      const unsigned par_t = (unsigned)t & 1u;
       // ================================================================ head 1: relu -> 1x1 -> relu
-      load_weights_async(sm.W, pitchWs, p.W1G + (size_t)s * p.nt1 * 8 * S, p.nt1 * 8, S);
+      trace(t, 2 * L, 0);
+      load_weights_async(sm.W(wsel ^ 1), pitchWs, p.W2G + (size_t)s * p.nt2 * 8 * S, p.nt2 * 8, S);
       cp_async_commit();
-      if (!barrier_wait(p, sm, epoch * nCTA)) return;
       for (int ch = 0; ch < p.nchunk; ++ch) {
-        const int mtiles = (B - ch * CHUNK) > 16 ? 2 : 1;
-        load_rows_async(sm, pitchA, 0, p.skipbuf, 0, nullptr, 0, ch, S, S);
-        cp_async_commit();
-        cp_async_wait_all();
-        __syncthreads();
+        int fail = poll_rows(sm, p, p.skipbuf, S, ch, par_t, pitchA);
+        cp_async_wait<1>();
+        if (__syncthreads_or(fail | *sm.abort)) return;
+        trace(t, 2 * L, 1);
         for (int tl = 0; tl < p.nt1; ++tl) {
-          float acc[2][4];
-          mma_chunk(sm, pitchA, pitchWs, pitchH, sm.W + tl * 8 * pitchWs, S / 16, 0, ch, mtiles, acc);
+          mma_tile(sm, pitchA, sm.W(wsel) + tl * 8 * pitchWs, pitchWs, S / 16, 0);
           __syncthreads();
-          int rr = tl * 8 + n_own, rg = s * p.rp1 + rr;
-          float v = reduce_partials(sm) + p.b1G[(size_t)s * p.nt1 * 8 + rr];
-          if (rr < p.rp1 && rg < S) p.h1buf[(size_t)(ch * CHUNK + m_own) * S + rg] = __float2bfloat16(fmaxf(v, 0.f));
+          float v = 0.f;
+#pragma unroll
+          for (int w = 0; w < GEN_WARPS; ++w) v += sm.P[w * CHUNK * 16 + m_own * 16 + n_own];
+          const int rr = tl * 8 + n_own, rg = s * p.rp1 + rr;
+          v = fmaxf(v + p.b1G[(size_t)s * p.nt1 * 8 + rr], 0.f);
+          float nxt = __shfl_down_sync(0xffffffffu, v, 1);
+          if (!(n_own & 1) && rr < p.rp1 && rg < S)
+            st_strong_u32(p.h1buf + (size_t)(ch * CHUNK + m_own) * S + rg, pack_tagged(v, nxt, par_t));
           __syncthreads();
         }
       }
-      barrier_arrive(p); ++epoch;
+      wsel ^= 1;
+      trace(t, 2 * L, 3);
       // ================================================================ head 2: 1x1 -> logits
-      load_weights_async(sm.W, pitchWs, p.W2G + (size_t)s * p.nt2 * 8 * S, p.nt2 * 8, S);
-      cp_async_commit();
-      if (!barrier_wait(p, sm, epoch * nCTA)) return;
+      trace(t, 2 * L + 1, 0);
+      prefetch_gate(t + 1, 0, wsel ^ 1);
       for (int ch = 0; ch < p.nchunk; ++ch) {
-        const int mtiles = (B - ch * CHUNK) > 16 ? 2 : 1;
-        load_rows_async(sm, pitchA, 0, p.h1buf, 0, nullptr, 0, ch, S, S);
-        cp_async_commit();
-        cp_async_wait_all();
-        __syncthreads();
+        int fail = poll_rows(sm, p, p.h1buf, S, ch, par_t, pitchA);
+        cp_async_wait<1>();
+        if (__syncthreads_or(fail | *sm.abort)) return;
+        trace(t, 2 * L + 1, 1);
         for (int tl = 0; tl < p.nt2; ++tl) {
-          float acc[2][4];
-          mma_chunk(sm, pitchA, pitchWs, pitchH, sm.W + tl * 8 * pitchWs, S / 16, 0, ch, mtiles, acc);
+          mma_tile(sm, pitchA, sm.W(wsel) + tl * 8 * pitchWs, pitchWs, S / 16, 0);
           __syncthreads();
-          int rr = tl * 8 + n_own, rg = s * p.rp2 + rr;
-          float v = reduce_partials(sm) + p.b2G[(size_t)s * p.nt2 * 8 + rr];
-          if (rr < p.rp2 && rg < Q) p.logitbuf[(size_t)(ch * CHUNK + m_own) * Q + rg] = v;
+          float v = 0.f;
+#pragma unroll
+          for (int w = 0; w < GEN_WARPS; ++w) v += sm.P[w * CHUNK * 16 + m_own * 16 + n_own];
+          const int rr = tl * 8 + n_own, rg = s * p.rp2 + rr;
+          v += p.b2G[(size_t)s * p.nt2 * 8 + rr];
+          if (rr < p.rp2 && rg < Q)
+            st_strong_u32(p.logitbuf + (size_t)(ch * CHUNK + m_own) * Q + rg, (__float_as_uint(v) & ~1u) | par_t);
           __syncthreads();
         }
       }
-      barrier_arrive(p); ++epoch;
+      wsel ^= 1;
+      trace(t, 2 * L + 1, 3);
     }
 
     // ================================================================ sampling phase
     // one warp per utterance: softmax -> inverse CDF on u (or argmax) -> next causal lookup
-    if (!barrier_wait(p, sm, epoch * nCTA)) return;
-    for (int u = s * GEN_WARPS + warp; u < p.Bpad; u += nCTA * GEN_WARPS) {
-      int2 sy = __ldcg(p.symbuf + u);
+    trace(t, 2 * L + 2, 0);
+    for (int u = s * GEN_WARPS + warp; u < Bpad; u += nCTA * GEN_WARPS) {
+      // this warp wrote symbuf[u] itself one step ago: plain reload of its own last store
+      uint2 sy = ld_strong_v2(p.symbuf + u);
+      const int prev_cur = (int)(sy.y & 0xFFFFu);
       int fed;
       if (prime) {
         fed = u < B ? (int)(((g.seed[u] % Q) + Q) % Q) : half;  // qpnet.py:356-358: pad with Q/2, keep the seed last
       } else if (u < B) {
-        const float* lg = p.logitbuf + (size_t)u * Q;
-        const int per = (Q + 31) / 32;  // contiguous span per lane keeps the prefix sum in symbol order
-        float v[32];
-        float mx = -INFINITY;
-        int amax = 0;
-#pragma unroll 8
-        for (int i = 0; i < per; ++i) {
-          int q = lane * per + i;
-          v[i] = q < Q ? __ldcg(lg + q) : -INFINITY;
-          if (v[i] > mx) { mx = v[i]; amax = q; }
-        }
-        if (g.logits_out && t < g.n_samples[u]) {
-          float* lo = g.logits_out + ((size_t)u * g.max_steps + t) * Q;
-          for (int i = 0; i < per; ++i) { int q = lane * per + i; if (q < Q) lo[q] = v[i]; }
-        }
-        // warp arg-max (first maximum wins)
-        float wmx = mx; int wam = amax;
-        for (int o = 16; o; o >>= 1) {
-          float om = __shfl_xor_sync(0xffffffffu, wmx, o);
-          int oa = __shfl_xor_sync(0xffffffffu, wam, o);
-          if (om > wmx || (om == wmx && oa < wam)) { wmx = om; wam = oa; }
-        }
-        int sym;
-        if (g.mode == QP_MODE_ARGMAX) {
-          sym = wam;
-        } else {
-          float local = 0.f;
-          for (int i = 0; i < per; ++i) { v[i] = (lane * per + i) < Q ? __expf(v[i] - wmx) : 0.f; local += v[i]; }
-          float incl = local;
-          for (int o = 1; o < 32; o <<= 1) {
-            float nb = __shfl_up_sync(0xffffffffu, incl, o);
-            if (lane >= o) incl += nb;
-          }
-          float total = __shfl_sync(0xffffffffu, incl, 31);
-          float uu = g.uniforms ? g.uniforms[(long long)u * g.ld_uniforms + t] : philox_uniform(g.philox_seed, u, t);
-          float target = uu * total;
-          float run = incl - local;
-          int cnt = 0;
-          for (int i = 0; i < per; ++i) { run += v[i]; if ((lane * per + i) < Q && run <= target) ++cnt; }
-          for (int o = 16; o; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
-          sym = min(cnt, Q - 1);
-        }
-        if (lane == 0 && t < g.n_samples[u]) g.out[(long long)u * g.ld_out + t] = sym;
+        int sym = Q <= 256 ? sample_symbol<8>(p, g, sm, u, t, lane) : sample_symbol<32>(p, g, sm, u, t, lane);
+        if (sym < 0) break;   // watchdog
         fed = g.force ? g.force[(long long)u * g.ld_force + t] : sym;
       } else {
         fed = half;
       }
-      write_x0(u, sy.y, fed, t + 1);
-      if (lane == 0) p.symbuf[u] = make_int2(sy.y, fed);
+      write_x0(u, prev_cur, fed, t + 1);
+      const unsigned vtag = ((unsigned)(t + 2) & 1u) << 30;
+      if (lane == 0) st_strong_v2(p.symbuf + u, (unsigned)prev_cur | vtag, (unsigned)fed | vtag);
     }
-    barrier_arrive(p); ++epoch;
+    trace(t, 2 * L + 2, 3);
   }
 }
 
@@ -646,11 +856,11 @@ __global__ void __launch_bounds__(GEN_THREADS, 1) gen_kernel(GenPlan p, GenArgsD
 using namespace qp;
 
 static size_t gen_smem_bytes(const GenPlan& p) {
-  int pitchA = 2 * p.C + 8, pitchH = p.Ap + 8, pitchWg = p.Kg + 8, pitchWs = p.S + 8;
-  int wrows = 8 * std::max(1, std::max(p.nt1, p.nt2));
-  int wpitch = std::max(pitchWg, pitchWs);
-  size_t b = (size_t)CHUNK * pitchA * 2 + (size_t)p.Bpad * pitchH * 2 + (size_t)wrows * wpitch * 2 +
-             GEN_WARPS * CHUNK * 8 * 4 + (size_t)p.Bpad * 4 * 4 * 2 + (size_t)p.Bpad * 4 + 64;
+  int pitchA = std::max(p.C, p.S) + 8, pitchH = p.Ap + 8, pitchWc = p.Kc + 8, pitchWp = p.C + 8, pitchWs = p.S + 8;
+  int wtile = std::max(8 * pitchWc + 8 * pitchWp, 8 * std::max(p.nt1, p.nt2) * pitchWs);
+  size_t b = (size_t)CHUNK * pitchA * 2 + (size_t)p.Bpad * pitchH * 2 + (size_t)wtile * 2 * 2 +
+             GEN_WARPS * CHUNK * 16 * 4 + (size_t)p.Bpad * 8 * 4 * 2 + (size_t)p.Bpad * p.A * 4 +
+             (size_t)p.Bpad * 4 * 4 * 2 + 64;
   return align_up(b, 16);
 }
 
@@ -661,7 +871,7 @@ static int validate_gen(const QpArch* arch, const QpGenerateArgs* a) {
   QP_REQUIRE(a->B >= 1 && a->F >= 1 && a->M >= 1 && a->max_steps >= 0, "generate: bad shape");
   QP_REQUIRE(arch->n_resch % 16 == 0 && arch->n_skipch % 16 == 0, "generate: n_resch and n_skipch must be multiples of 16");
   QP_REQUIRE(arch->n_skipch <= arch->n_resch, "generate: n_skipch > n_resch is not supported");
-  QP_REQUIRE(arch->n_quantize <= 1024, "generate: n_quantize > 1024 is not supported");
+  QP_REQUIRE(arch->n_quantize <= 1024 && arch->n_quantize % 2 == 0, "generate: n_quantize must be even and <= 1024");
   QP_REQUIRE((long long)a->max_steps <= (long long)a->F * arch->upsampling, "generate: max_steps exceeds the aux length");
   QP_REQUIRE(a->seed && a->h && a->d && a->n_samples && a->out, "generate: NULL pointer");
   return QP_OK;
@@ -685,14 +895,17 @@ int qp_generate(const QpArch* arch, const float* const* tensors_host, const QpGe
   GenPlan p;
   size_t need = make_gen_plan(arch, a->B, a->F, a->M, ws, ws_bytes, &p);
   if (need > ws_bytes) return set_error(QP_EWORKSPACE, "generate: workspace %zu < %zu bytes", ws_bytes, need);
+  QP_REQUIRE(p.spc <= 4, "generate: n_skipch / (n_resch / 4) > 4 skip rows per CTA is not supported");
   int dev = 0, nsm = 0;
   QP_CUDA(cudaGetDevice(&dev));
   QP_CUDA(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev));
   QP_REQUIRE(p.nCTA <= nsm, "generate: n_resch/4 = %d CTAs exceed the %d SMs (one resident CTA per SM)", p.nCTA, nsm);
   size_t smem = gen_smem_bytes(p);
   QP_REQUIRE(smem <= 227 * 1024, "generate: %zu bytes of shared memory needed (batch too large for one launch)", smem);
+  if (const char* ts = getenv("QPNET_GEN_TRACE_STEP")) p.trace_step0 = atoi(ts);
   QP_CUDA(cudaMemsetAsync(p.status, 0, 256, st));
-  QP_CUDA(cudaMemsetAsync(p.barrier, 0, 256, st));
+  QP_CUDA(cudaMemsetAsync(p.tagged_begin, 0xFF, p.tagged_bytes, st));  // every word starts with a stale tag
+  QP_CUDA(cudaMemsetAsync(p.trace, 0, sizeof(long long) * 8 * (2 * p.L + 3) * TRACE_EVENTS, st));
   if (int e = upload_tensor_table(arch, tensors_host, p.tab, st)) return e;
   TensorMap tm = tensor_map(arch);
   gen_pack_kernel<<<148 * 8, 256, 0, st>>>(tm, p, p.tab);
@@ -710,6 +923,7 @@ int qp_generate(const QpArch* arch, const float* const* tensors_host, const QpGe
   QP_REQUIRE(occ >= 1 && occ * nsm >= p.nCTA, "generate: cooperative grid of %d CTAs does not fit (occ %d x %d SMs)",
              p.nCTA, occ, nsm);
   void* kargs[] = {(void*)&p, (void*)&g};
+  // cooperative launch = guaranteed co-residency of the dataflow graph's CTAs
   QP_CUDA(cudaLaunchCooperativeKernel((const void*)gen_kernel, dim3(p.nCTA), dim3(GEN_THREADS), kargs, smem, st));
   count_launch();
   return QP_OK;
@@ -722,8 +936,20 @@ int qp_workspace_status(const void* ws, void* stream) {
   QP_CUDA(cudaMemcpyAsync(&v, ws, sizeof(v), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
   QP_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
   if (v == QP_ERANGE) return set_error(QP_ERANGE, "past-tap index out of range (qpnet.py:294 assert)");
-  if (v == QP_ETIMEOUT) return set_error(QP_ETIMEOUT, "generator watchdog fired: a grid barrier never completed");
+  if (v == QP_ETIMEOUT) return set_error(QP_ETIMEOUT, "generator watchdog fired: an exchange word never arrived");
   return v;
+}
+
+// debug only (not part of the public header): copy the per-phase clock64 trace of CTA 0
+int qp_debug_gen_trace(const QpArch* arch, int32_t B, int32_t M, void* ws, size_t ws_bytes, long long* out_host,
+                       int32_t n, void* stream) {
+  GenPlan p;
+  make_gen_plan(arch, B, 1, M, ws, ws_bytes, &p);
+  int total = 8 * (2 * p.L + 3) * TRACE_EVENTS;
+  if (n > total) n = total;
+  QP_CUDA(cudaMemcpyAsync(out_host, p.trace, sizeof(long long) * n, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+  QP_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+  return n;
 }
 
 }  // extern "C"

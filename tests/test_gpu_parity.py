@@ -240,7 +240,8 @@ def test_generator_free_running_vs_reference_goldens(dev, name):
         first = int(neq[0]) if len(neq) else len(ref)
         firsts.append(first)
         print(name, "utt", b, "match rate %.4f first divergence %d / %d" % (float((r == ref).mean()), first, len(ref)))
-    assert max(firsts) >= 20, firsts                      # structural errors diverge immediately
+    # a structural error diverges at step 0 or 1; arithmetic noise (bf16 + 1-bit epoch tags) later
+    assert min(firsts) >= 3, firsts
 
 
 def test_generator_is_deterministic_and_batch_independent(dev):

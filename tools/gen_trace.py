@@ -1,0 +1,78 @@
+#!/usr/bin/env python3
+"""Debug aid: per-phase clock64 trace of CTA 0 of the persistent generator (QPNET_GEN_TRACE_STEP).
+
+    python tools/gen_trace.py [--utts 32] [--frames 20] [--step 1000]
+Prints, for 8 consecutive sample steps, the cycles spent per phase split into
+wait (poll for inputs), mma, epilogue.
+"""
+import argparse
+import ctypes as C
+import os
+import sys
+
+import numpy as np
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--utts", type=int, default=32)
+    ap.add_argument("--frames", type=int, default=20)
+    ap.add_argument("--step", type=int, default=1000)
+    args = ap.parse_args()
+    os.environ["QPNET_GEN_TRACE_STEP"] = str(args.step)
+    import bench
+    from qpnet_b200 import _lib, ops
+    from qpnet_b200.qpnet import QPNet, initialize
+    dev = torch.device("cuda:0")
+    torch.manual_seed(0)
+    m = QPNet()
+    m.apply(initialize)
+    m = m.to(dev)
+    h, f0, n_list = bench.build_inputs(args.utts, 0, args.frames)
+    d64, _ = ops.f0_to_dilated(torch.from_numpy(f0).to(dev), 22050, 8, 110, want_f32=False)
+    seed = torch.full((args.utts,), 128, dtype=torch.int64, device=dev)
+    n_dev = torch.tensor(n_list, dtype=torch.int32, device=dev)
+    for _ in range(2):
+        t0 = torch.cuda.Event(enable_timing=True); t1 = torch.cuda.Event(enable_timing=True)
+        t0.record()
+        out, _ = m.generate_device(seed, torch.from_numpy(h).to(dev), d64, n_dev, max(n_list), check_status=False)
+        t1.record()
+        torch.cuda.synchronize()
+        print("kernel ms", t0.elapsed_time(t1), "us/step", t0.elapsed_time(t1) * 1e3 / (max(n_list) + 1))
+    L = 16
+    nphase = 2 * L + 3
+    n = 8 * nphase * 4
+    buf = (C.c_longlong * n)()
+    fn = _lib.lib.qp_debug_gen_trace
+    fn.restype = C.c_int
+    fn.argtypes = [C.POINTER(_lib.QpArch), C.c_int32, C.c_int32, C.c_void_p, C.c_size_t, C.POINTER(C.c_longlong),
+                   C.c_int32, C.c_void_p]
+    ws = m._last_ws
+    M = ops.max_ceil(d64)
+    fn(m._arch, args.utts, M, ws.data_ptr(), ws.numel(), buf, n, None)
+    tr = np.array(buf, dtype=np.int64).reshape(8, nphase, 4)
+    names = [f"{'gate' if i % 2 == 0 else 'res '}{i // 2:02d}" for i in range(2 * L)] + ["head1 ", "head2 ", "sample"]
+    for st in range(1, 4):
+        print(f"--- step {args.step + st}: total {tr[st + 1, 0, 0] - tr[st, 0, 0]} cycles")
+        for ph in range(nphase):
+            a, b, c, d = tr[st, ph]
+            nxt = tr[st, ph + 1, 0] if ph + 1 < nphase else tr[st + 1, 0, 0]
+            if ph < nphase - 1:
+                print(f"{names[ph]} wait {b - a:6d}  mma {c - b:6d}  epi {d - c:6d}  gap {nxt - d:5d}")
+            else:
+                print(f"{names[ph]} total {d - a:6d} gap {nxt - d:5d}")
+    avg = np.zeros((nphase, 3))
+    for st in range(1, 7):
+        for ph in range(nphase - 1):
+            a, b, c, d = tr[st, ph]
+            avg[ph] += [b - a, c - b, d - c]
+    avg /= 6
+    print("mean over 6 steps (cycles): wait %.0f mma %.0f epi %.0f per phase; gate wait %.0f res wait %.0f" % (
+        avg[:-1, 0].mean(), avg[:-1, 1].mean(), avg[:-1, 2].mean(), avg[0:2 * L:2, 0].mean(), avg[1:2 * L:2, 0].mean()))
+
+
+if __name__ == "__main__":
+    main()
