@@ -192,7 +192,6 @@ int qp_backward(const QpArch* arch, const float* const* tensors_host, const int6
   if (int e = check_arch(arch)) return e;
   QP_REQUIRE(tensors_host && x && h && d && dlogits && grads_host && ws, "backward: NULL pointer");
   QP_REQUIRE(flags & QP_F_SAVE, "backward: the forward pass must have run with QP_F_SAVE");
-  QP_REQUIRE(!(flags & QP_F_BF16), "backward: bf16 tensor-core path not built yet");
   reset_launch_count();
   TfPlan p;
   size_t need = make_tf_plan(arch, B, T, F, bl, M, flags, ws, ws_bytes, &p);

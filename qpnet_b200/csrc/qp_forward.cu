@@ -4,6 +4,7 @@
 //   per block: [past-row index kernel] -> gate GEMM (+sigmoid*tanh) -> res/skip GEMM
 //   head: relu -> 1x1 -> relu -> 1x1
 #include "qp_gemm_f32.cuh"
+#include "qp_tc.cuh"
 #include "qp_tf_plan.cuh"
 
 namespace qp {
@@ -113,6 +114,82 @@ int tf_forward_f32(const QpArch* arch, const float* const* tensors, const int64_
   return QP_OK;
 }
 
+// ------------------------------------------------------------------ bf16 tensor-core path
+// Same dataflow as tf_forward_f32 with every contraction on tcgen05 (qp_tc.cu).  The residual
+// stream X stays fp32 (read / written by the res epilogue); GEMM operands are bf16 copies.
+// With QP_F_SAVE the epilogues also emit the fp32 Z and sigmoid/tanh values backward consumes.
+int tf_forward_bf16(const QpArch* arch, const float* const* tensors, const int64_t* x, const float* h, const float* d,
+                    const TfPlan& p, float* logits, uint32_t flags, cudaStream_t st) {
+  const PackedDims& pd = p.pd;
+  const TensorMap tm = tensor_map(arch);
+  const int C = pd.C, S = pd.S, Q = pd.Q, A = pd.A, B = p.B, L0 = p.L0, bl = p.bl, Kgp = p.Kgp;
+  const bool save = flags & QP_F_SAVE;
+  QP_CUDA(cudaMemsetAsync(p.status, 0, sizeof(int32_t), st));
+  if (int e = upload_tensor_table(arch, tensors, p.tab, st)) return e;
+  if (int e = pack_f32(arch, p.tab, p.W, st)) return e;
+  if (int e = tc::pack_wg_bf16(p.W.Wg, (long long)pd.L * 2 * C, 2 * C, pd.Kg, Kgp, p.Wg_bf, st)) return e;
+  if (int e = tc::f32_to_bf16_pad(p.W.Wrs, (long long)pd.L * (C + S), C, C, p.Wrs_bf, 0, st)) return e;
+  if (int e = tc::f32_to_bf16_pad(tensors[tm.post1_w()], S, S, S, p.W1_bf, 0, st)) return e;
+  if (int e = tc::f32_to_bf16_pad(tensors[tm.post2_w()], Q, S, S, p.W2_bf, 0, st)) return e;
+  embed_kernel<<<dim3(L0, B), 128, 0, st>>>(x, p.T, L0, C, Q, p.W.E0, p.W.E1, tensors[tm.causal_b()], p.X[0]);
+  QP_LAUNCH_CHECK();
+  if (int e = tc::f32_to_bf16_pad(p.X[0], (long long)B * L0, C, C, p.Xbf[0], 0, st)) return e;
+  upsample_kernel<<<dim3((unsigned)(((int64_t)L0 * A + 255) / 256), B), 256, 0, st>>>(
+      h, A, p.F, pd.U, L0, tensors[tm.up_w()], tensors[tm.up_b()], p.Hup);
+  QP_LAUNCH_CHECK();
+  if (int e = tc::f32_to_bf16_pad(p.Hup, (long long)B * L0, A, 64, p.Hup_bf, 0, st)) return e;
+  for (int l = 0; l < pd.L; ++l) {
+    const int Lin = p.Lin[l], sh = p.shift[l], n = Lin - sh;
+    const int* rowmap = nullptr;
+    if (l >= pd.nF) {
+      int* pr = p.pastrow[l - pd.nF];
+      pastrow_kernel<<<dim3((n + 255) / 256, B), 256, 0, st>>>(d, p.T, n, Lin, p.dil[l], pr, p.status);
+      QP_LAUNCH_CHECK();
+      rowmap = pr;
+    }
+    const __nv_bfloat16* Xin = p.Xbf[l & 1];
+    tc::Args g = {};
+    g.seg[0] = tc::Seg{Xin, (long long)Lin * C, C, rowmap, 0, Lin, C};
+    g.seg[1] = tc::Seg{Xin, (long long)Lin * C, C, nullptr, sh, Lin, C};
+    g.seg[2] = tc::Seg{p.Hup_bf, (long long)L0 * 64, 64, nullptr, L0 - n, L0, 64};
+    g.nseg = 3;
+    g.W = p.Wg_bf + (size_t)l * 2 * C * Kgp; g.ldw = Kgp;
+    g.bias = p.W.bg + (size_t)2 * C * l;
+    g.B = B; g.n_rows = n; g.N = 2 * C; g.n_begin = 0; g.BN = 2 * C < 256 ? 2 * C : 256;
+    g.z_bf = p.Zbf; g.z_f32 = save ? p.Z[l] : nullptr; g.gsave = save ? p.G[l] : nullptr;
+    if (int e = tc::gemm_gate(g, st)) return e;
+
+    tc::Args r = {};
+    r.seg[0] = tc::Seg{p.Zbf, (long long)n * C, C, nullptr, 0, n, C};
+    r.nseg = 1;
+    r.W = p.Wrs_bf + (size_t)l * (C + S) * C; r.ldw = C;
+    r.bias = p.W.brs + (size_t)(C + S) * l;
+    r.B = B; r.n_rows = n; r.N = C + S;
+    r.n_begin = (l == pd.L - 1) ? C : 0;   // the last block's residual projection is dead (caveat C7)
+    r.BN = (r.N - r.n_begin) < 256 ? (r.N - r.n_begin) : 256;
+    r.C = C; r.S = S;
+    r.xcur = p.X[l]; r.xcur_bstride = (long long)Lin * C; r.xcur_off = sh;
+    r.xnext = (l + 1 < pd.L) ? p.X[l + 1] : nullptr; r.xnext_bf = p.Xbf[(l + 1) & 1];
+    r.skip = p.skipsum; r.skip_bstride = (long long)bl * S; r.skip_row0 = n - bl; r.skip_accum = l > 0;
+    if (int e = tc::gemm_resskip(r, st)) return e;
+  }
+  // head (qpnet.py:566-571)
+  if (int e = tc::f32_to_bf16_pad(p.skipsum, (long long)B * bl, S, S, p.skip_bf, 1, st)) return e;
+  tc::Args h1 = {};
+  h1.seg[0] = tc::Seg{p.skip_bf, (long long)bl * S, S, nullptr, 0, bl, S};
+  h1.nseg = 1; h1.W = p.W1_bf; h1.ldw = S; h1.bias = tensors[tm.post1_b()];
+  h1.B = B; h1.n_rows = bl; h1.N = S; h1.BN = S < 256 ? S : 256;
+  h1.out = p.H1; h1.out_bstride = (long long)bl * S; h1.ldo = S; h1.out_relu_bf = p.H1_bf;
+  if (int e = tc::gemm_head(h1, st)) return e;
+  tc::Args h2 = {};
+  h2.seg[0] = tc::Seg{p.H1_bf, (long long)bl * S, S, nullptr, 0, bl, S};
+  h2.nseg = 1; h2.W = p.W2_bf; h2.ldw = S; h2.bias = tensors[tm.post2_b()];
+  h2.B = B; h2.n_rows = bl; h2.N = Q; h2.BN = Q < 256 ? Q : 256;
+  h2.out = logits; h2.out_bstride = (long long)bl * Q; h2.ldo = Q;
+  if (int e = tc::gemm_head(h2, st)) return e;
+  return QP_OK;
+}
+
 // ------------------------------------------------------------------ fused softmax-CE
 // one warp per row: loss_sum += -log p[target];  dlogits = (p - onehot) * scale
 __global__ void cross_entropy_kernel(const float* __restrict__ logits, const int64_t* __restrict__ target, int64_t rows,
@@ -170,11 +247,14 @@ int qp_forward(const QpArch* arch, const float* const* tensors_host, const int64
   if (int e = check_device()) return e;
   if (int e = validate_tf(arch, B, T, F, bl, M)) return e;
   QP_REQUIRE(tensors_host && x && h && d && logits && ws, "forward: NULL pointer");
-  QP_REQUIRE(!(flags & QP_F_BF16), "forward: bf16 tensor-core path not built yet");
+  if (flags & QP_F_BF16)
+    QP_REQUIRE(arch->n_resch % 64 == 0 && arch->n_skipch % 64 == 0 && arch->n_quantize % 32 == 0 && arch->n_aux <= 64,
+               "forward: the bf16 tensor-core path needs n_resch %% 64 == 0, n_skipch %% 64 == 0, n_quantize %% 32 == 0");
   reset_launch_count();
   TfPlan p;
   size_t need = make_tf_plan(arch, B, T, F, bl, M, flags, ws, ws_bytes, &p);
   if (need > ws_bytes) return set_error(QP_EWORKSPACE, "forward: workspace %zu < %zu bytes", ws_bytes, need);
+  if (flags & QP_F_BF16) return tf_forward_bf16(arch, tensors_host, x, h, d, p, logits, flags, (cudaStream_t)stream);
   return tf_forward_f32(arch, tensors_host, x, h, d, p, logits, flags, (cudaStream_t)stream);
 }
 

@@ -277,12 +277,13 @@ __device__ __forceinline__ void mma_bf16(float (&c)[4], unsigned a0, unsigned a1
       : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
 }
 
-__device__ __forceinline__ float fast_sigmoid(float x) { return 1.f / (1.f + __expf(-x)); }
+// MUFU.TANH (max relative error 2^-11, far below the bf16 rounding of z); sigmoid(x) = 0.5 tanh(x/2) + 0.5
 __device__ __forceinline__ float fast_tanh(float x) {
-  float e = __expf(-2.f * fabsf(x));
-  float t = (1.f - e) / (1.f + e);
-  return copysignf(t, x);
+  float y;
+  asm("tanh.approx.f32 %0, %1;\n" : "=f"(y) : "f"(x));
+  return y;
 }
+__device__ __forceinline__ float fast_sigmoid(float x) { return fmaf(0.5f, fast_tanh(0.5f * x), 0.5f); }
 
 // bf16 bits of x, round-to-nearest-even
 __device__ __forceinline__ unsigned bf16_rne(float x) { return (unsigned)__bfloat16_as_ushort(__float2bfloat16_rn(x)); }
@@ -336,6 +337,10 @@ struct Smem {
   __device__ __forceinline__ float* Pp(int sel) const { return Pp0 + sel * ppstride; }
   float* xcarry;       // [Bpad][4] fp32 residual stream of the owned channels
   float* skipacc;      // [Bpad][4]
+  float* bg;           // [L][8] gate biases of the owned rows
+  float* brs;          // [L][8] res / skip biases
+  float* b1;           // [nt1*8]
+  float* b2;           // [nt2*8]
   int* abort;          // [1]
 };
 
@@ -354,26 +359,30 @@ __device__ __forceinline__ bool spin_failed(const GenPlan& p, unsigned& spins, l
 }
 
 // Poll CHUNK rows of K tagged bf16 from an exchange buffer into sm.A (row pitch pitchA).
-// Every 32-bit word must carry tag `par`.  First an optimistic round over all of this
-// thread's chunks; while something is still stale only ONE chunk is probed per round (failed
-// probes are pure L2 traffic shared by 128 CTAs), and a hit triggers another full round.
+// Every 32-bit word must carry tag `par`.  A failed probe is pure L2 traffic multiplied by 128
+// CTAs, and the producers' stores need ~one L2 latency to become visible, so a thread first
+// watches ONE of its 16-byte pieces (rotated by row, so the CTA as a whole watches every
+// producer) until it turns fresh, then loads the rest in one burst; pieces that are still stale
+// after a burst are re-probed one at a time, and a hit triggers another burst.
 // Returns nonzero when the watchdog fired.
 __device__ __forceinline__ int poll_rows(const Smem& sm, const GenPlan& p, const __nv_bfloat16* src, int K, int chunk,
                                          unsigned par, int pitchA) {
   const int row = threadIdx.x >> 3, c0 = threadIdx.x & 7;
-  const int nchunks = K >> 3;
+  const int npieces = K >> 3;
   const uint4* g = (const uint4*)(src + (size_t)(chunk * CHUNK + row) * K);
   uint4* d = (uint4*)(sm.A + row * pitchA);
   int fail = 0;
-  for (int cb = c0; cb < nchunks && !fail; cb += 64) {
+  for (int cb = c0; cb < npieces && !fail; cb += 64) {
     uint4 v[8];
     unsigned pend = 0;
 #pragma unroll
     for (int i = 0; i < 8; ++i)
-      if (cb + 8 * i < nchunks) pend |= 1u << i;
+      if (cb + 8 * i < npieces) pend |= 1u << i;
     unsigned spins = 0;
     long long t0 = 0;
-    bool burst = true;
+    bool burst = false;
+    int ip = row & 7;
+    if (!(pend & (1u << ip))) ip = __ffs(pend) - 1;
     while (pend) {
       if (burst) {
 #pragma unroll
@@ -387,11 +396,11 @@ __device__ __forceinline__ int poll_rows(const Smem& sm, const GenPlan& p, const
             if (!bad) { d[cb + 8 * i] = v[i]; pend &= ~(1u << i); }
           }
         burst = pend != before && pend != 0;   // progress: try the rest again right away
+        if (pend) ip = __ffs(pend) - 1;
       } else {
-        const int i = __ffs(pend) - 1;
-        uint4 w = ld_strong_v4(g + cb + 8 * i);
+        uint4 w = ld_strong_v4(g + cb + 8 * ip);
         unsigned bad = ((w.x ^ par) | (w.y ^ par) | (w.z ^ par) | (w.w ^ par)) & 1u;
-        if (!bad) { d[cb + 8 * i] = w; pend &= ~(1u << i); burst = true; }
+        if (!bad) { d[cb + 8 * ip] = w; pend &= ~(1u << ip); burst = true; }
         else if (spin_failed(p, spins, t0)) { fail = 1; break; }
       }
     }
@@ -419,19 +428,26 @@ __device__ __forceinline__ void store_partials(float* pw, const float (&acc)[2][
 
 // one n-tile: acc = A[chunk rows][K] * Wt[8 rows][K]^T, K split over the warps, partials to sm.P (16 cols).
 // Both m16 tiles are always computed (rows of padded utterances are finite garbage).
+template <int KSTEPS>
 __device__ __forceinline__ void mma_tile(const Smem& sm, int pitchA, const __nv_bfloat16* Wt, int pitchW, int ksteps,
                                          int col0) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   float acc[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
   const __nv_bfloat16* ap = sm.A + (lane & 15) * pitchA + (lane >> 4) * 8;
   const __nv_bfloat16* bp = Wt + (lane & 7) * pitchW + ((lane >> 3) & 1) * 8;
-  for (int ks = warp; ks < ksteps; ks += GEN_WARPS) {
+  auto kstep = [&](int ks) {
     unsigned b0, b1, a0, a1, a2, a3;
     ldmatrix_x2(b0, b1, bp + ks * 16);
     ldmatrix_x4(a0, a1, a2, a3, ap + ks * 16);
     mma_bf16(acc[0], a0, a1, a2, a3, b0, b1);
     ldmatrix_x4(a0, a1, a2, a3, ap + 16 * pitchA + ks * 16);
     mma_bf16(acc[1], a0, a1, a2, a3, b0, b1);
+  };
+  if (KSTEPS > 0) {
+#pragma unroll
+    for (int i = 0; i < KSTEPS / GEN_WARPS; ++i) kstep(warp + i * GEN_WARPS);
+  } else {
+    for (int ks = warp; ks < ksteps; ks += GEN_WARPS) kstep(ks);
   }
   store_partials(sm.P + warp * CHUNK * 16, acc, lane, 16, col0);
 }
@@ -440,8 +456,8 @@ __device__ __forceinline__ void mma_tile(const Smem& sm, int pitchA, const __nv_
 // inverse CDF on a uniform (or argmax).  PER = logits per lane (contiguous span, so the prefix
 // sum runs in symbol order).  Returns the symbol, or -1 when the watchdog fired.
 template <int PER>
-__device__ __forceinline__ int sample_symbol(const GenPlan& p, const GenArgsDev& g, const Smem& sm, int u, int t, int lane) {
-  const int Q = p.Q;
+__device__ __forceinline__ int sample_symbol(const GenPlan& p, const GenArgsDev& g, const Smem& sm, int Q, int u, int t,
+                                             int lane) {
   const float* lg = p.logitbuf + (size_t)u * Q;
   const unsigned par_t = (unsigned)t & 1u;
   const int per = (Q + 31) / 32;
@@ -514,9 +530,12 @@ __device__ __forceinline__ int sample_symbol(const GenPlan& p, const GenArgsDev&
   return sym;
 }
 
+// FULL = the SI default architecture (C 512, S 256, Q 256, A 39): loop bounds are compile-time constants.
+template <bool FULL, bool TRACE>
 __global__ void __launch_bounds__(GEN_THREADS, 1) gen_kernel(GenPlan p, GenArgsDev g) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  const int C = p.C, S = p.S, Q = p.Q, A = p.A, Ap = p.Ap, L = p.L, Kc = p.Kc;
+  const int C = FULL ? 512 : p.C, S = FULL ? 256 : p.S, Q = FULL ? 256 : p.Q, A = FULL ? 39 : p.A;
+  const int Ap = FULL ? 48 : p.Ap, L = p.L, Kc = C + Ap;
   const int pitchA = max(C, S) + 8, pitchH = Ap + 8, pitchWc = Kc + 8, pitchWp = C + 8, pitchWs = S + 8;
   const int wtile_elems = max(8 * pitchWc + 8 * pitchWp, 8 * max(p.nt1, p.nt2) * pitchWs);
   Smem sm;
@@ -530,6 +549,10 @@ __global__ void __launch_bounds__(GEN_THREADS, 1) gen_kernel(GenPlan p, GenArgsD
     sm.Hraw = (float*)q; q += (size_t)p.Bpad * p.A * 4;
     sm.xcarry = (float*)q; q += (size_t)p.Bpad * 4 * 4;
     sm.skipacc = (float*)q; q += (size_t)p.Bpad * 4 * 4;
+    sm.bg = (float*)q; q += (size_t)L * 8 * 4;
+    sm.brs = (float*)q; q += (size_t)L * 8 * 4;
+    sm.b1 = (float*)q; q += (size_t)p.nt1 * 8 * 4;
+    sm.b2 = (float*)q; q += (size_t)p.nt2 * 8 * 4;
     sm.abort = (int*)q;
   }
   const int s = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -542,11 +565,17 @@ __global__ void __launch_bounds__(GEN_THREADS, 1) gen_kernel(GenPlan p, GenArgsD
 
   for (int e = tid; e < CHUNK * pitchA; e += GEN_THREADS) sm.A[e] = __float2bfloat16(0.f);
   for (int e = tid; e < Bpad * pitchH; e += GEN_THREADS) sm.H[e] = __float2bfloat16(0.f);
+  for (int e = tid; e < L * 8; e += GEN_THREADS) {
+    sm.bg[e] = p.bgG[((size_t)(e >> 3) * nCTA + s) * 8 + (e & 7)];
+    sm.brs[e] = p.brsG[((size_t)(e >> 3) * nCTA + s) * 8 + (e & 7)];
+  }
+  for (int e = tid; e < p.nt1 * 8; e += GEN_THREADS) sm.b1[e] = p.b1G[(size_t)s * p.nt1 * 8 + e];
+  for (int e = tid; e < p.nt2 * 8; e += GEN_THREADS) sm.b2[e] = p.b2G[(size_t)s * p.nt2 * 8 + e];
   if (tid == 0) *sm.abort = 0;
   __syncthreads();
 
   auto trace = [&](int t, int phase, int ev) {
-    if (s == 0 && tid == 0 && t >= p.trace_step0 && t < p.trace_step0 + p.trace_nsteps)
+    if (TRACE && s == 0 && tid == 0 && t >= p.trace_step0 && t < p.trace_step0 + p.trace_nsteps)
       p.trace[((size_t)(t - p.trace_step0) * nphase + phase) * TRACE_EVENTS + ev] = clock64();
   };
 
@@ -667,7 +696,7 @@ __global__ void __launch_bounds__(GEN_THREADS, 1) gen_kernel(GenPlan p, GenArgsD
           const __nv_bfloat16* bc = Wc + (lane & 7) * pitchWc + boff;
           const __nv_bfloat16* bq = Wp + (lane & 7) * pitchWp + boff;
           const int ksm = C / 16, ksa = Ap / 16;
-          for (int ks = warp; ks < ksm; ks += GEN_WARPS) {
+          auto kstep = [&](int ks) {
             unsigned b0, b1, q0, q1, a0, a1, a2, a3;
             ldmatrix_x2(b0, b1, bc + ks * 16);
             ldmatrix_x2(q0, q1, bq + ks * 16);
@@ -677,6 +706,12 @@ __global__ void __launch_bounds__(GEN_THREADS, 1) gen_kernel(GenPlan p, GenArgsD
             ldmatrix_x4(a0, a1, a2, a3, ap + 16 * pitchA + ks * 16);
             mma_bf16(accc[1], a0, a1, a2, a3, b0, b1);
             mma_bf16(accp[1], a0, a1, a2, a3, q0, q1);
+          };
+          if (FULL) {
+#pragma unroll
+            for (int i = 0; i < 512 / 16 / GEN_WARPS; ++i) kstep(warp + i * GEN_WARPS);
+          } else {
+            for (int ks = warp; ks < ksm; ks += GEN_WARPS) kstep(ks);
           }
           if (warp < ksa) {  // aux columns of the current-tap tile (qpnet.py:663-664 / 632-633)
             const __nv_bfloat16* hp = sm.H + (ch * CHUNK + arow) * pitchH + warp * 16 + acol;
@@ -711,7 +746,7 @@ __global__ void __launch_bounds__(GEN_THREADS, 1) gen_kernel(GenPlan p, GenArgsD
             ring[(size_t)(t & (rs - 1)) * slot_stride] = pnew;
           }
           const float past = prime ? pnew : sm.Pp(l & 1)[u * 8 + n_own];
-          float pre = cur + past + p.bgG[((size_t)l * nCTA + s) * 8 + n_own];
+          float pre = cur + past + sm.bg[l * 8 + n_own];
           // rows 0-3 sigmoid, 4-7 tanh of channels 4s..4s+3: pair lanes n and n+4
           float other = __shfl_down_sync(0xffffffffu, pre, 4);
           float z = fast_sigmoid(pre) * fast_tanh(other);
@@ -740,13 +775,13 @@ __global__ void __launch_bounds__(GEN_THREADS, 1) gen_kernel(GenPlan p, GenArgsD
         cp_async_wait<1>();
         if (__syncthreads_or(fail | *sm.abort)) return;
         trace(t, 2 * l + 1, 1);
-        mma_tile(sm, pitchA, sm.W(wsel), pitchWp, C / 16, 0);
+        mma_tile<FULL ? 32 : 0>(sm, pitchA, sm.W(wsel), pitchWp, C / 16, 0);
         __syncthreads();
         trace(t, 2 * l + 1, 2);
         float v = 0.f;
 #pragma unroll
         for (int w = 0; w < GEN_WARPS; ++w) v += sm.P[w * CHUNK * 16 + m_own * 16 + n_own];
-        v += p.brsG[((size_t)l * nCTA + s) * 8 + n_own];
+        v += sm.brs[l * 8 + n_own];
         const int u = ch * CHUNK + m_own;
         float outv;
         if (n_own < 4) {
@@ -786,13 +821,13 @@ __global__ void __launch_bounds__(GEN_THREADS, 1) gen_kernel(GenPlan p, GenArgsD
         if (__syncthreads_or(fail | *sm.abort)) return;
         trace(t, 2 * L, 1);
         for (int tl = 0; tl < p.nt1; ++tl) {
-          mma_tile(sm, pitchA, sm.W(wsel) + tl * 8 * pitchWs, pitchWs, S / 16, 0);
+          mma_tile<FULL ? 16 : 0>(sm, pitchA, sm.W(wsel) + tl * 8 * pitchWs, pitchWs, S / 16, 0);
           __syncthreads();
           float v = 0.f;
 #pragma unroll
           for (int w = 0; w < GEN_WARPS; ++w) v += sm.P[w * CHUNK * 16 + m_own * 16 + n_own];
           const int rr = tl * 8 + n_own, rg = s * p.rp1 + rr;
-          v = fmaxf(v + p.b1G[(size_t)s * p.nt1 * 8 + rr], 0.f);
+          v = fmaxf(v + sm.b1[rr], 0.f);
           float nxt = __shfl_down_sync(0xffffffffu, v, 1);
           if (!(n_own & 1) && rr < p.rp1 && rg < S)
             st_strong_u32(p.h1buf + (size_t)(ch * CHUNK + m_own) * S + rg, pack_tagged(v, nxt, par_t));
@@ -810,13 +845,13 @@ __global__ void __launch_bounds__(GEN_THREADS, 1) gen_kernel(GenPlan p, GenArgsD
         if (__syncthreads_or(fail | *sm.abort)) return;
         trace(t, 2 * L + 1, 1);
         for (int tl = 0; tl < p.nt2; ++tl) {
-          mma_tile(sm, pitchA, sm.W(wsel) + tl * 8 * pitchWs, pitchWs, S / 16, 0);
+          mma_tile<FULL ? 16 : 0>(sm, pitchA, sm.W(wsel) + tl * 8 * pitchWs, pitchWs, S / 16, 0);
           __syncthreads();
           float v = 0.f;
 #pragma unroll
           for (int w = 0; w < GEN_WARPS; ++w) v += sm.P[w * CHUNK * 16 + m_own * 16 + n_own];
           const int rr = tl * 8 + n_own, rg = s * p.rp2 + rr;
-          v += p.b2G[(size_t)s * p.nt2 * 8 + rr];
+          v += sm.b2[rr];
           if (rr < p.rp2 && rg < Q)
             st_strong_u32(p.logitbuf + (size_t)(ch * CHUNK + m_own) * Q + rg, (__float_as_uint(v) & ~1u) | par_t);
           __syncthreads();
@@ -837,7 +872,7 @@ __global__ void __launch_bounds__(GEN_THREADS, 1) gen_kernel(GenPlan p, GenArgsD
       if (prime) {
         fed = u < B ? (int)(((g.seed[u] % Q) + Q) % Q) : half;  // qpnet.py:356-358: pad with Q/2, keep the seed last
       } else if (u < B) {
-        int sym = Q <= 256 ? sample_symbol<8>(p, g, sm, u, t, lane) : sample_symbol<32>(p, g, sm, u, t, lane);
+        int sym = Q <= 256 ? sample_symbol<8>(p, g, sm, Q, u, t, lane) : sample_symbol<32>(p, g, sm, Q, u, t, lane);
         if (sym < 0) break;   // watchdog
         fed = g.force ? g.force[(long long)u * g.ld_force + t] : sym;
       } else {
@@ -860,7 +895,7 @@ static size_t gen_smem_bytes(const GenPlan& p) {
   int wtile = std::max(8 * pitchWc + 8 * pitchWp, 8 * std::max(p.nt1, p.nt2) * pitchWs);
   size_t b = (size_t)CHUNK * pitchA * 2 + (size_t)p.Bpad * pitchH * 2 + (size_t)wtile * 2 * 2 +
              GEN_WARPS * CHUNK * 16 * 4 + (size_t)p.Bpad * 8 * 4 * 2 + (size_t)p.Bpad * p.A * 4 +
-             (size_t)p.Bpad * 4 * 4 * 2 + 64;
+             (size_t)p.Bpad * 4 * 4 * 2 + (size_t)p.L * 8 * 4 * 2 + (size_t)(p.nt1 + p.nt2) * 8 * 4 + 64;
   return align_up(b, 16);
 }
 
@@ -917,14 +952,18 @@ int qp_generate(const QpArch* arch, const float* const* tensors_host, const QpGe
   g.out = a->out; g.ld_out = a->ld_out; g.logits_out = a->logits_out;
   g.mode = a->mode; g.max_steps = a->max_steps; g.d_is_f64 = a->d_is_f64;
   g.causal_b = tensors_host[tm.causal_b()]; g.up_w = tensors_host[tm.up_w()]; g.up_b = tensors_host[tm.up_b()];
-  QP_CUDA(cudaFuncSetAttribute(gen_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const bool full = p.C == 512 && p.S == 256 && p.Q == 256 && p.A == 39;
+  const bool tr = getenv("QPNET_GEN_TRACE_STEP") != nullptr;
+  const void* kern = full ? (tr ? (const void*)gen_kernel<true, true> : (const void*)gen_kernel<true, false>)
+                          : (const void*)gen_kernel<false, false>;
+  QP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int occ = 0;
-  QP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, gen_kernel, GEN_THREADS, smem));
+  QP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, GEN_THREADS, smem));
   QP_REQUIRE(occ >= 1 && occ * nsm >= p.nCTA, "generate: cooperative grid of %d CTAs does not fit (occ %d x %d SMs)",
              p.nCTA, occ, nsm);
   void* kargs[] = {(void*)&p, (void*)&g};
   // cooperative launch = guaranteed co-residency of the dataflow graph's CTAs
-  QP_CUDA(cudaLaunchCooperativeKernel((const void*)gen_kernel, dim3(p.nCTA), dim3(GEN_THREADS), kargs, smem, st));
+  QP_CUDA(cudaLaunchCooperativeKernel(kern, dim3(p.nCTA), dim3(GEN_THREADS), kargs, smem, st));
   count_launch();
   return QP_OK;
 }

@@ -34,6 +34,17 @@ struct TfPlan {
   float* dH1;                   // (B, bl, S)
   float* dHup;                  // (B, L0, A)
   float* dWp1; float* dbp1; float* dWp2; float* dbp2; float* dup;  // head + upsampler grads
+  // bf16 tensor-core path (QP_F_BF16 only): packed weights and GEMM operand copies
+  int Kgp;                      // gate K with the aux segment padded to 64: 2C + 64
+  __nv_bfloat16* Wg_bf;         // (L, 2C, Kgp)
+  __nv_bfloat16* Wrs_bf;        // (L, C+S, C)
+  __nv_bfloat16* W1_bf;         // (S, S)
+  __nv_bfloat16* W2_bf;         // (Q, S)
+  __nv_bfloat16* Xbf[2];        // ping-pong block inputs (B, L0, C)
+  __nv_bfloat16* Zbf;           // (B, nmax, C)
+  __nv_bfloat16* Hup_bf;        // (B, L0, 64)
+  __nv_bfloat16* skip_bf;       // (B, bl, S) relu(sum of skips)
+  __nv_bfloat16* H1_bf;         // (B, bl, S) relu(head-1)
 };
 
 // Fills `p`; returns total bytes.  `base` may be NULL (sizing only).
@@ -104,6 +115,19 @@ inline size_t make_tf_plan(const QpArch* a, int B, int T, int F, int bl, int M, 
     p->dWp2 = ar.take<float>((size_t)Q * S);
     p->dbp2 = ar.take<float>(Q);
     p->dup = ar.take<float>(pd.U + 1);
+  }
+  p->Kgp = 2 * C + 64;
+  if (flags & QP_F_BF16) {
+    p->Wg_bf = ar.take<__nv_bfloat16>((size_t)pd.L * 2 * C * p->Kgp);
+    p->Wrs_bf = ar.take<__nv_bfloat16>((size_t)pd.L * (C + S) * C);
+    p->W1_bf = ar.take<__nv_bfloat16>((size_t)S * S);
+    p->W2_bf = ar.take<__nv_bfloat16>((size_t)Q * S);
+    p->Xbf[0] = ar.take<__nv_bfloat16>((size_t)B * p->L0 * C);
+    p->Xbf[1] = ar.take<__nv_bfloat16>((size_t)B * p->L0 * C);
+    p->Zbf = ar.take<__nv_bfloat16>((size_t)B * p->nmax * C);
+    p->Hup_bf = ar.take<__nv_bfloat16>((size_t)B * p->L0 * 64);
+    p->skip_bf = ar.take<__nv_bfloat16>((size_t)B * bl * S);
+    p->H1_bf = ar.take<__nv_bfloat16>((size_t)B * bl * S);
   }
   return align_up(ar.off, 256);
 }

@@ -85,6 +85,8 @@ class _TeacherForced(torch.autograd.Function):
         B, T = x.shape
         F = h.shape[2]
         flags = _lib.QP_F_SAVE if need_grad else 0
+        if model.tensor_cores:
+            flags |= _lib.QP_F_BF16
         arch = model._arch
         nbytes = lib.qp_forward_workspace_bytes(arch, B, T, bl, M, flags)
         if nbytes == 0:
@@ -163,6 +165,9 @@ class QPNet(nn.Module):
         if n_expected != len(list(self.parameters())):
             raise RuntimeError("parameter table does not match the library's layout")
         self.check_range = True     # mirror the reference's gather assert (costs one sync)
+        # teacher-forced contractions on tcgen05 (bf16 operands, fp32 accumulate) when the shapes allow
+        # it; False selects the exact fp32 SIMT path (tight-tolerance parity)
+        self.tensor_cores = (n_resch % 64 == 0 and n_skipch % 64 == 0 and n_quantize % 32 == 0 and n_aux <= 64)
         self.last_launches = 0      # kernels launched by the most recent call (bench accounting)
         self.philox_seed = 100      # qpnet_decode.py:58 default --seed
 

@@ -30,10 +30,13 @@ def dev():
     return torch.device("cuda:0")
 
 
-def _model(kw, p, dev):
+def _model(kw, p, dev, tensor_cores=False):
+    """tensor_cores=False selects the exact fp32 SIMT teacher-forced path (tight tolerances);
+    the bf16 tcgen05 path has its own tests below."""
     from qpnet_b200.qpnet import QPNet
     m = QPNet(**kw)
     m.load_state_dict(p)
+    m.tensor_cores = tensor_cores
     return m.to(dev)
 
 
@@ -128,6 +131,64 @@ def test_forward_logits_vs_reference_goldens(dev, name):
     assert logits.shape == (1, bl, a.Q)
     err = np.abs(logits[0].cpu().numpy() - g[f"{name}/logits"]).max()
     assert err < 2e-4, err
+
+
+def test_forward_bf16_tensor_cores_vs_reference_golden(dev):
+    """SI default model on the tcgen05 path (bf16 operands, fp32 accumulate / residual stream)
+    against the logits the reference produced in fp32.  Tolerance 0.05 absolute: the measured
+    noise of bf16 operands over 16 blocks (logits are O(1))."""
+    g = cases.load("forward")
+    name = "full_s4_b1"
+    kw, a, p, x, h, d, t, bl = cases.forward_inputs(name)
+    m = _model(kw, p, dev, tensor_cores=True)
+    with torch.no_grad():
+        logits = m(x.to(dev), h.to(dev), d.to(dev), torch.tensor([bl], device=dev))
+    ref = g[f"{name}/logits"]
+    err = np.abs(logits[0].cpu().numpy() - ref).max()
+    print("bf16 tcgen05 forward: max |dlogit| =", err, "max |logit| =", np.abs(ref).max())
+    assert err < 0.05, err
+
+
+@pytest.mark.parametrize("C,S,B,frames,bl,fac", [(64, 64, 1, 12, 330, 1.0), (128, 64, 2, 14, 457, 1.0),
+                                                 (64, 128, 1, 22, 220, 0.5), (192, 64, 1, 12, 129, 1.5)])
+def test_forward_bf16_tensor_cores_vs_fp32_path(dev, C, S, B, frames, bl, fac):
+    """tcgen05 path against the exact fp32 path on shapes that exercise partial row tiles
+    (bl, n not multiples of 128), column tiles narrower than 256, the gathered past tap under
+    x0.5 / x1.5 F0, and B > 1.  Also checks the tensors saved for backward."""
+    kw = dict(n_resch=C, n_skipch=S)
+    a = orc.Arch(**kw)
+    p = orc.init_params(a, 31, 0.1)
+    T = frames * a.U
+    xs, hs, ds = [], [], []
+    for b in range(B):
+        hh, f0, _ = synth.utterance(frames, 40 + b, fac, a.A)
+        ds.append(torch.from_numpy(cases.d_from_f0(f0)).float()[:T])
+        hs.append(torch.from_numpy(hh.T.copy()))
+        xs.append(torch.from_numpy(np.random.RandomState(b).randint(0, a.Q, size=T)).long())
+    x, h, d = torch.stack(xs).to(dev), torch.stack(hs).to(dev), torch.stack(ds).to(dev)
+    blt = torch.tensor([bl] * B, device=dev)
+    m32 = _model(kw, p, dev, tensor_cores=False)
+    mtc = _model(kw, p, dev, tensor_cores=True)
+    with torch.no_grad():
+        want = m32(x, h, d, blt)
+        got = mtc(x, h, d, blt)
+    err = float((got - want).abs().max())
+    print(f"C={C} S={S}: bf16 vs fp32 max |dlogit| = {err:.4f}, max |logit| = {float(want.abs().max()):.3f}")
+    assert err < 0.05, err
+    # gradients through the mixed path (bf16 forward, fp32 backward on the saved activations)
+    tgt = torch.from_numpy(np.random.RandomState(7).randint(0, a.Q, size=(B, bl))).long().to(dev)
+    grads = []
+    for m in (m32, mtc):
+        m.zero_grad()
+        loss = torch.nn.functional.cross_entropy(m(x, h, d, blt).reshape(-1, a.Q), tgt.reshape(-1))
+        loss.backward()
+        grads.append({k: v.grad.clone() for k, v in m.named_parameters()})
+    worst = 0.0
+    for k in grads[0]:
+        scale = max(float(grads[0][k].abs().max()), 1e-6)
+        worst = max(worst, float((grads[0][k] - grads[1][k]).abs().max()) / scale)
+    print("worst relative-to-max gradient difference bf16-forward vs fp32:", worst)
+    assert worst < 0.08, worst
 
 
 def test_forward_batch_elements_are_independent(dev):
@@ -278,3 +339,35 @@ def test_generator_rejects_bad_mode(dev):
     g, kw, a, p, x, h, d, n_list, mode, xm, m, uni = _gen_setup("small_argmax", dev)
     with pytest.raises(SystemExit):                      # qpnet.py:513-515
         m.batch_fast_generate(x, h, list(n_list), d, None, "nucleus")
+
+
+@pytest.mark.parametrize("kw,B,groups", [(cases.SMALL, 21, None), (cases.SMALL, 37, "1"), (cases.SMALL, 37, "2"),
+                                         (cases.FULL, 19, None)])
+def test_generator_utterance_groups_vs_oracle(dev, monkeypatch, kw, B, groups):
+    """More than one 16-utterance chunk: chunks are dealt to co-resident CTA groups (and looped
+    inside a group when there are more chunks than groups, forced here with QPNET_GEN_GROUPS).
+    Teacher-forced per-step logits of EVERY utterance against the oracle."""
+    if groups is not None:
+        monkeypatch.setenv("QPNET_GEN_GROUPS", groups)
+    a = orc.Arch(**kw)
+    p = orc.init_params(a, 21, 0.1)
+    m = _model(kw, p, dev)
+    frames, steps = 2, 40 if kw else 12
+    h = np.zeros((B, a.A, frames), np.float32)
+    d = np.zeros((B, frames * a.U), np.float64)
+    for b in range(B):
+        hs, f0, _ = synth.utterance(frames, 300 + b, 1.0, a.A)
+        h[b] = hs.T
+        d[b] = cases.d_from_f0(f0)
+    x = torch.full((B, 1), a.Q // 2, dtype=torch.long)
+    forced = torch.from_numpy(np.random.RandomState(5).randint(0, a.Q, size=(B, steps))).long()
+    lg = []
+    with torch.no_grad():
+        orc.generate(a, p, x, torch.from_numpy(h), [steps] * B, d, mode="argmax", force=forced, logits_out=lg,
+                     max_steps=steps)
+    want = torch.stack(lg, dim=1)
+    res, got = m.batch_fast_generate(x, torch.from_numpy(h), [steps] * B, d, None, "argmax", False, force=forced,
+                                     return_logits=True)
+    err = (got.cpu() - want).abs().amax(dim=(1, 2))
+    print("groups", groups, "per-utterance max |dlogit|", float(err.max()))
+    assert float(err.max()) < 0.06, err
