@@ -25,8 +25,9 @@
 //   * priming (qpnet.py:355-440) is evaluated on a length-1 time axis: the pad region is
 //     constant, so step "-1" runs the stack with P(t-k) := P'(t) and fills every ring slot.
 #include <algorithm>
+#include <string.h>
 
-#include "qp_common.cuh"
+#include "qp_gen_common.cuh"
 #include "qp_pack.cuh"
 
 namespace qp {
@@ -34,7 +35,6 @@ namespace qp {
 constexpr int GEN_THREADS = 256;
 constexpr int GEN_WARPS = 8;
 constexpr int CHUNK = 32;  // utterances per MMA pass (two m16 tiles)
-constexpr long long GEN_TIMEOUT_CYCLES = 6000000000LL;  // ~3 s: watchdog, not a schedule
 constexpr int TRACE_EVENTS = 4;
 
 struct GenPlan {
@@ -228,102 +228,6 @@ __global__ void gen_pack_kernel(TensorMap tm, GenPlan p, const float* const* __r
   }
 }
 
-// ------------------------------------------------------------------ device helpers
-__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
-  unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sa), "l"(gmem) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
-
-__device__ __forceinline__ uint4 ld_strong_v4(const void* p) {
-  uint4 v;
-  asm volatile("ld.relaxed.gpu.global.v4.u32 {%0,%1,%2,%3}, [%4];\n"
-               : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
-  return v;
-}
-__device__ __forceinline__ uint2 ld_strong_v2(const void* p) {
-  uint2 v;
-  asm volatile("ld.relaxed.gpu.global.v2.u32 {%0,%1}, [%2];\n" : "=r"(v.x), "=r"(v.y) : "l"(p) : "memory");
-  return v;
-}
-__device__ __forceinline__ unsigned ld_strong_u32(const void* p) {
-  unsigned v;
-  asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];\n" : "=r"(v) : "l"(p) : "memory");
-  return v;
-}
-__device__ __forceinline__ void st_strong_u32(void* p, unsigned v) {
-  asm volatile("st.relaxed.gpu.global.u32 [%0], %1;\n" ::"l"(p), "r"(v) : "memory");
-}
-__device__ __forceinline__ void st_strong_v2(void* p, unsigned a, unsigned b) {
-  asm volatile("st.relaxed.gpu.global.v2.u32 [%0], {%1,%2};\n" ::"l"(p), "r"(a), "r"(b) : "memory");
-}
-
-__device__ __forceinline__ void ldmatrix_x4(unsigned& a0, unsigned& a1, unsigned& a2, unsigned& a3, const void* p) {
-  unsigned sa = (unsigned)__cvta_generic_to_shared(p);
-  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];\n"
-               : "=r"(a0), "=r"(a1), "=r"(a2), "=r"(a3) : "r"(sa));
-}
-__device__ __forceinline__ void ldmatrix_x2(unsigned& b0, unsigned& b1, const void* p) {
-  unsigned sa = (unsigned)__cvta_generic_to_shared(p);
-  asm volatile("ldmatrix.sync.aligned.m8n8.x2.shared.b16 {%0,%1}, [%2];\n" : "=r"(b0), "=r"(b1) : "r"(sa));
-}
-__device__ __forceinline__ void mma_bf16(float (&c)[4], unsigned a0, unsigned a1, unsigned a2, unsigned a3, unsigned b0,
-                                         unsigned b1) {
-  asm volatile(
-      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
-      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
-      : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
-}
-
-// MUFU.TANH (max relative error 2^-11, far below the bf16 rounding of z); sigmoid(x) = 0.5 tanh(x/2) + 0.5
-__device__ __forceinline__ float fast_tanh(float x) {
-  float y;
-  asm("tanh.approx.f32 %0, %1;\n" : "=f"(y) : "f"(x));
-  return y;
-}
-__device__ __forceinline__ float fast_sigmoid(float x) { return fmaf(0.5f, fast_tanh(0.5f * x), 0.5f); }
-
-// bf16 bits of x, round-to-nearest-even
-__device__ __forceinline__ unsigned bf16_rne(float x) { return (unsigned)__bfloat16_as_ushort(__float2bfloat16_rn(x)); }
-// bf16 bits of x rounded to the nearest value whose mantissa LSB equals `par` (error <= 1 ulp)
-__device__ __forceinline__ unsigned bf16_tagged(float x, unsigned par) {
-  unsigned u = __float_as_uint(x);
-  unsigned hi = u >> 16, rem = u & 0xFFFFu;
-  unsigned r = hi + ((rem > 0x8000u) || (rem == 0x8000u && (hi & 1u)));
-  if ((r & 1u) != par) r = (r > hi) ? r - 1u : r + 1u;
-  return r & 0xFFFFu;
-}
-// one exchange word: two channels, epoch tag in bit 0
-__device__ __forceinline__ unsigned pack_tagged(float lo, float hi, unsigned par) {
-  return bf16_tagged(lo, par) | (bf16_rne(hi) << 16);
-}
-
-// Philox4x32-10, one draw per (utterance, step)
-__device__ __forceinline__ float philox_uniform(unsigned long long seed, unsigned utt, unsigned step) {
-  unsigned k0 = (unsigned)seed, k1 = (unsigned)(seed >> 32);
-  unsigned c0 = step, c1 = utt, c2 = 0x51504e45u, c3 = 0x42323030u;
-#pragma unroll
-  for (int r = 0; r < 10; ++r) {
-    unsigned hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
-    unsigned hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
-    unsigned n0 = hi1 ^ c1 ^ k0, n1 = lo1, n2 = hi0 ^ c3 ^ k1, n3 = lo0;
-    c0 = n0; c1 = n1; c2 = n2; c3 = n3;
-    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
-  }
-  return (float)(c0 >> 8) * (1.0f / 16777216.0f);
-}
-
-struct GenArgsDev {
-  const int64_t* seed; const float* h; const void* d; const int32_t* n_samples;
-  const float* uniforms; long long ld_uniforms; unsigned long long philox_seed;
-  const int32_t* force; long long ld_force;
-  int32_t* out; long long ld_out; float* logits_out;
-  int mode, max_steps, d_is_f64;
-  const float* causal_b; const float* up_w; const float* up_b;
-};
-
 struct Smem {
   __nv_bfloat16* A;    // [CHUNK][pitchA]  polled operand rows (x(t) / z / skip / head-1)
   __nv_bfloat16* H;    // [Bpad][pitchH]   aux rows of the current step
@@ -380,7 +284,7 @@ __device__ __forceinline__ int poll_rows(const Smem& sm, const GenPlan& p, const
       if (cb + 8 * i < npieces) pend |= 1u << i;
     unsigned spins = 0;
     long long t0 = 0;
-    bool burst = false;
+    bool burst = true;   // measured (tools/ubench_exchange.cu): bursting first beats probing one piece first
     int ip = row & 7;
     if (!(pend & (1u << ip))) ip = __ffs(pend) - 1;
     while (pend) {
@@ -888,6 +792,21 @@ __global__ void __launch_bounds__(GEN_THREADS, 1) gen_kernel(GenPlan p, GenArgsD
 
 }  // namespace qp
 
+namespace qp {
+// cluster generator for the SI default widths (qp_generate_cl.cu)
+int cl_generate(const QpArch* arch, const float* const* tensors_host, const QpGenerateArgs* a, void* ws, size_t ws_bytes,
+                cudaStream_t st);
+size_t cl_workspace_bytes(const QpArch* arch, int B, int M);
+bool cl_supported(const QpArch* arch, int B);
+int cl_trace_copy(const QpArch* arch, int B, int M, void* ws, size_t ws_bytes, long long* out_host, int n, cudaStream_t st);
+static thread_local int g_last_kernel = 0;   // 1: cluster generator, 0: generic
+static bool want_cluster(const QpArch* arch, int B) {
+  const char* e = getenv("QPNET_GEN_KERNEL");
+  if (e && strcmp(e, "generic") == 0) return false;
+  return cl_supported(arch, B);
+}
+}  // namespace qp
+
 using namespace qp;
 
 static size_t gen_smem_bytes(const GenPlan& p) {
@@ -917,7 +836,9 @@ extern "C" {
 size_t qp_generate_workspace_bytes(const QpArch* arch, int32_t B, int32_t M) {
   if (check_arch(arch) != QP_OK || B < 1 || M < 1) return 0;
   GenPlan p;
-  return make_gen_plan(arch, B, 1, M, nullptr, 0, &p);
+  size_t n = make_gen_plan(arch, B, 1, M, nullptr, 0, &p);
+  if (cl_supported(arch, B)) n = std::max(n, cl_workspace_bytes(arch, B, M));
+  return n;
 }
 
 int qp_generate(const QpArch* arch, const float* const* tensors_host, const QpGenerateArgs* a, void* ws,
@@ -927,6 +848,12 @@ int qp_generate(const QpArch* arch, const float* const* tensors_host, const QpGe
   QP_REQUIRE(tensors_host && ws, "generate: NULL pointer");
   reset_launch_count();
   cudaStream_t st = (cudaStream_t)stream;
+  g_last_kernel = 0;
+  if (want_cluster(arch, a->B)) {
+    int r = cl_generate(arch, tensors_host, a, ws, ws_bytes, st);
+    if (r != 1) { g_last_kernel = 1; return r; }   // 1: the clusters cannot be co-resident here -> generic kernel
+    reset_launch_count();
+  }
   GenPlan p;
   size_t need = make_gen_plan(arch, a->B, a->F, a->M, ws, ws_bytes, &p);
   if (need > ws_bytes) return set_error(QP_EWORKSPACE, "generate: workspace %zu < %zu bytes", ws_bytes, need);
@@ -982,6 +909,7 @@ int qp_workspace_status(const void* ws, void* stream) {
 // debug only (not part of the public header): copy the per-phase clock64 trace of CTA 0
 int qp_debug_gen_trace(const QpArch* arch, int32_t B, int32_t M, void* ws, size_t ws_bytes, long long* out_host,
                        int32_t n, void* stream) {
+  if (g_last_kernel == 1) return cl_trace_copy(arch, B, M, ws, ws_bytes, out_host, n, (cudaStream_t)stream);
   GenPlan p;
   make_gen_plan(arch, B, 1, M, ws, ws_bytes, &p);
   int total = 8 * (2 * p.L + 3) * TRACE_EVENTS;
