@@ -29,8 +29,11 @@
 //   * aux 1x1 (qpnet.py:663-664, 632-633) is a 6-MMA side product of the owner warp, computed while
 //     the partial tiles are in flight.
 // Exchange words carry a 1-bit epoch tag (LSB of the low bf16 / of the fp32 logit); consumers poll
-// the data itself.  Every spin has a watchdog (QP_ETIMEOUT) and every exit goes through a cluster barrier.
+// the data itself.  A CTA can publish version v+2 of its block while a slow consumer in ANOTHER cluster
+// still reads v+1 (it cannot get further: v+2 needs every owner's v+1, published after that owner
+// consumed v), so x / z versions alternate between two buffers and the tag is bit 1 of the version.  Every spin has a watchdog (QP_ETIMEOUT) and every exit goes through a cluster barrier.
 #include <algorithm>
+#include <type_traits>
 
 #include <cuda_fp16.h>
 
@@ -74,8 +77,8 @@ struct Plan {
   float* T0;              // [NOWN][3][Q][8]  block-0 gate tables: cur symbol, previous, the one before
   float* Eo;              // [NOWN][2][Q][4]  causal-layer rows of the owned channels (bias folded into tap 1)
   __nv_bfloat16* ring[MAXL];  // [ring_size][NOWN][UB][KS], l >= 1
-  uint32_t* v512;         // [NOWN][UB][2]  x / z exchange, alternating epochs
-  uint32_t* v256;         // [NOWN][UB]     relu(skip sum) / relu(head-1)
+  uint32_t* v512;         // [2][NOWN][UB][2]  x / z exchange: version v lives in buffer v & 1 with tag (v >> 1) & 1
+  uint32_t* v256;         // [2][NOWN][UB]     buffer 0 relu(skip sum), buffer 1 relu(head-1); tag = step & 1
   uint32_t* vlog;         // [NOWN][UB][2]  fp32 logits
   uint32_t* vsym;         // [UB][32]       fed-back symbol, one line per utterance
   void* tagged_begin; size_t tagged_bytes;
@@ -114,8 +117,8 @@ size_t make_plan(const QpArch* a, int B, int F, int M, void* base, size_t cap, P
   }
   ar.off = align_up(ar.off, 256);
   size_t t0 = ar.off;
-  p->v512 = ar.take<uint32_t>((size_t)NOWN * UB * 2);
-  p->v256 = ar.take<uint32_t>((size_t)NOWN * UB);
+  p->v512 = ar.take<uint32_t>((size_t)2 * NOWN * UB * 2);
+  p->v256 = ar.take<uint32_t>((size_t)2 * NOWN * UB);
   p->vlog = ar.take<uint32_t>((size_t)NOWN * UB * 2);
   p->vsym = ar.take<uint32_t>((size_t)UB * 32);
   ar.off = align_up(ar.off, 256);
@@ -343,9 +346,14 @@ __global__ void __launch_bounds__(NT, 1) cl_gen_kernel(Plan p, GenArgsDev g) {
   const int half = Q / 2;
   const int nphase = 2 * L + 3;
   const long long ldd = (long long)p.F * U;
+  // roles: all 8 warps poll + run the tensor-core tile; warps 0-3 finish the owned rows (warp m: utterances
+  // q4 + 8m), warps 4-7 stream weights / past rows and build the aux tile; warp 7 of CTA u < B samples utterance u.
+  const bool finisher = warp < 4;
+  const int fu = q4 + 8 * warp;                 // utterance this thread finishes (finisher warps)
+  const int t128 = tid - 128;                   // index inside the streaming warps
 
   // ---- one-time staging ---------------------------------------------------------------
-  for (int e = tid; e < (sm.total - sm.acur) / 16; e += NT) ((uint4*)smem)[e] = make_uint4(0, 0, 0, 0);
+  for (int e = tid; e < sm.total / 16; e += NT) ((uint4*)smem)[e] = make_uint4(0, 0, 0, 0);
   __syncthreads();
   for (int e = tid; e < 3 * Q * 8; e += NT) ((float*)(smem + sm.t0))[e] = p.T0[(size_t)s * 3 * Q * 8 + e];
   for (int e = tid; e < 2 * Q * 4; e += NT) ((float*)(smem + sm.eo))[e] = p.Eo[(size_t)s * 2 * Q * 4 + e];
@@ -384,19 +392,24 @@ __global__ void __launch_bounds__(NT, 1) cl_gen_kernel(Plan p, GenArgsDev g) {
       p.trace[((size_t)(t - p.trace_step0) * nphase + phase) * TRACE_EVENTS + ev] = clock64();
   };
 
-  // ---- weight tile stream: one tile per MMA phase, NSLOT-deep ring, prefetch distance 2 ------
-  // per step: tile 2l = res l, tile 2l-1 = gate l (l >= 1), then head-1, head-2 (not in the priming step)
-  int pf_t = -1, pf_i = 0, pf_n = 0;   // cursor of the next tile to fetch
+  // ---- weight tile stream (streaming warps only): one tile per MMA phase, NSLOT-deep ring, prefetch
+  // distance 2.  Per step: tile 2l = res l, tile 2l-1 = gate l (l >= 1), then head-1, head-2 (not in
+  // the priming step).  A gate tile carries the block's past-tap rows behind the weights.
+  int pf_t = -1, pf_i = 0, pf_slot = 0;   // cursor of the next tile to fetch
   auto issue_next_tile = [&]() {
     if (pf_t < g.max_steps) {
-      unsigned char* dst = sW + (pf_n % NSLOT) * WSLOT;
+      unsigned char* dst = sW + pf_slot * WSLOT;
       if (pf_i < 2 * L - 1) {
-        if (pf_i & 1) {   // gate (pf_i + 1) / 2: weight tile + the past-tap rows x_l(t - k) of this CTA's K-share
+        if (pf_i & 1) {
           const int l = (pf_i + 1) >> 1;
           const __nv_bfloat16* src = p.Wgate + ((size_t)l * NOWN + s) * NR * 2 * KS;
-          for (int e = tid; e < NR * 32; e += NT) cp_async16(dst + ((e >> 5) * PWG + (e & 31) * 8) * 2, src + (e >> 5) * 2 * KS + (e & 31) * 8);
+#pragma unroll
+          for (int j = 0; j < NR * 32 / 128; ++j) {
+            const int e = t128 + 128 * j;
+            cp_async16(dst + ((e >> 5) * PWG + (e & 31) * 8) * 2, src + (e >> 5) * 2 * KS + (e & 31) * 8);
+          }
           if (pf_t >= 0) {
-            const int u = tid >> 3;
+            const int u = t128 >> 2;
             int k = p.dil[l];
             if (l >= p.nF) {   // pitch-dependent look-back of this step (qpnet.py:476-483, 613-624)
               k = 0;
@@ -409,34 +422,44 @@ __global__ void __launch_bounds__(NT, 1) cl_gen_kernel(Plan p, GenArgsDev g) {
             const __nv_bfloat16* rsrc = p.ring[l] + (((size_t)slot * NOWN + s) * UB + u) * KS;
             unsigned char* pdst = dst + WTILE + (u * PA) * 2;
 #pragma unroll
-            for (int cch = (tid & 7); cch < KS / 8; cch += 8) cp_async16(pdst + cch * 16, rsrc + cch * 8);
+            for (int j = 0; j < KS / 8 / 4; ++j) {
+              const int cch = (t128 & 3) + 4 * j;
+              cp_async16(pdst + cch * 16, rsrc + cch * 8);
+            }
           }
-        } else {          // res pf_i / 2
+        } else {
           const int l = pf_i >> 1;
           const __nv_bfloat16* src = p.Wres + ((size_t)l * NOWN + s) * NR * KS;
-          for (int e = tid; e < NR * 16; e += NT) cp_async16(dst + ((e >> 4) * PWR + (e & 15) * 8) * 2, src + (e >> 4) * KS + (e & 15) * 8);
+#pragma unroll
+          for (int j = 0; j < NR * 16 / 128; ++j) {
+            const int e = t128 + 128 * j;
+            cp_async16(dst + ((e >> 4) * PWR + (e & 15) * 8) * 2, src + (e >> 4) * KS + (e & 15) * 8);
+          }
         }
       } else {
         const int hd = pf_i - (2 * L - 1);
         const __nv_bfloat16* src = p.Whead + ((size_t)hd * NOWN + s) * NR * KH;
-        for (int e = tid; e < NR * 8; e += NT) cp_async16(dst + ((e >> 3) * PWH + (e & 7) * 8) * 2, src + (e >> 3) * KH + (e & 7) * 8);
+#pragma unroll
+        for (int j = 0; j < NR * 8 / 128; ++j) {
+          const int e = t128 + 128 * j;
+          cp_async16(dst + ((e >> 3) * PWH + (e & 7) * 8) * 2, src + (e >> 3) * KH + (e & 7) * 8);
+        }
       }
       ++pf_i;
       const int ntiles = pf_t < 0 ? 2 * L - 1 : 2 * L + 1;
       if (pf_i == ntiles) { pf_i = 0; ++pf_t; }
     }
-    ++pf_n;
+    pf_slot = pf_slot == NSLOT - 1 ? 0 : pf_slot + 1;
     cp_async_commit();
   };
-  issue_next_tile();
-  issue_next_tile();
+  if (!finisher) { issue_next_tile(); issue_next_tile(); }
 
-  // ---- owner-warp state ----------------------------------------------------------------
-  float xc[4][2], sk[4][2];          // fp32 residual carry (lanes i4 < 2) / skip accumulators (lanes i4 == 2)
-#pragma unroll
-  for (int m = 0; m < 4; ++m) { xc[m][0] = xc[m][1] = 0.f; sk[m][0] = sk[m][1] = 0.f; }
+  // ---- finisher state: this thread's utterance fu, rows (2*i4, 2*i4+1) of the owned 8 -------------
+  float xc0 = 0.f, xc1 = 0.f;          // fp32 residual carry (lanes i4 < 2)
+  float sk0 = 0.f, sk1 = 0.f;          // skip accumulators (lanes i4 == 2)
   int sy_c = half, sy_p1 = half, sy_p2 = half;   // lane u: s(t-1), s(t-2), s(t-3) of utterance u
-  int rp = 0;                                    // MMA phase counter: activation / receive / barrier double buffering
+  int rp = 0;                          // MMA phase counter: activation / receive / barrier double buffering
+  int cur_slot = 0;                    // weight slot of the current phase
 
   auto spin_check = [&](unsigned& spins, long long& t0) -> bool {
     if ((++spins & 1023u) != 0) return false;
@@ -446,30 +469,29 @@ __global__ void __launch_bounds__(NT, 1) cl_gen_kernel(Plan p, GenArgsDev g) {
     return false;
   };
 
-  // aux 1x1 of the owned 8 gate rows for all utterances: 6 MMAs (qpnet.py:663-664 / 632-633)
-  auto aux_mma = [&](int l, int t, float (&ax)[2][4]) {
-#pragma unroll
-    for (int m = 0; m < 2; ++m) ax[m][0] = ax[m][1] = ax[m][2] = ax[m][3] = 0.f;
-    const __nv_bfloat16* hp = sHaux + ((t & 1) * UB + (lane & 15)) * PH + (lane >> 4) * 8;
+  // aux 1x1 of the owned 8 gate rows for this warp's 8 utterances (its half of one m16 tile): 3 MMAs
+  // (qpnet.py:663-664 / 632-633).  Returns the (row 2*i4, row 2*i4+1) pair of utterance fu.
+  auto aux_pair = [&](int l, int t, float& a0_, float& a1_) {
+    float ax[4] = {0.f, 0.f, 0.f, 0.f};
+    const __nv_bfloat16* hp = sHaux + ((t & 1) * UB + 16 * (warp >> 1) + (lane & 15)) * PH + (lane >> 4) * 8;
     const __nv_bfloat16* vp = sVaux + (l * 8 + (lane & 7)) * PH + ((lane >> 3) & 1) * 8;
 #pragma unroll
     for (int ks = 0; ks < AP / 16; ++ks) {
       unsigned b0, b1, a0, a1, a2, a3;
       ldmatrix_x2(b0, b1, vp + ks * 16);
       ldmatrix_x4(a0, a1, a2, a3, hp + ks * 16);
-      mma_bf16(ax[0], a0, a1, a2, a3, b0, b1);
-      ldmatrix_x4(a0, a1, a2, a3, hp + 16 * PH + ks * 16);
-      mma_bf16(ax[1], a0, a1, a2, a3, b0, b1);
+      mma_bf16(ax, a0, a1, a2, a3, b0, b1);
     }
+    a0_ = (warp & 1) ? ax[2] : ax[0];
+    a1_ = (warp & 1) ? ax[3] : ax[1];
   };
-  // gate non-linearity + publication of the owned z slice (epoch = parity of the 512-vector write counter)
-  auto publish_gate = [&](int l, const float (&pre)[4][2], unsigned par) {
-#pragma unroll
-    for (int m = 0; m < 4; ++m) {
-      float z = fast_sigmoid(pre[m][0] + sBg[l * 8 + 2 * i4]) * fast_tanh(pre[m][1] + sBg[l * 8 + 2 * i4 + 1]);
-      float zn = __shfl_xor_sync(0xffffffffu, z, 1);
-      if (!(i4 & 1)) st_strong_u32(p.v512 + ((size_t)s * UB + q4 + 8 * m) * 2 + (i4 >> 1), pack_tagged(z, zn, par));
-    }
+  // gate non-linearity + publication of (utterance fu, owned channel i4)
+  // word of (owner block s, utterance fu) in the buffer of x / z version `ver`
+  auto v512_word = [&](unsigned ver) -> uint32_t* { return p.v512 + ((size_t)(ver & 1u) * NOWN * UB + (size_t)s * UB + fu) * 2; };
+  auto publish_gate = [&](int l, float pre_s, float pre_t, unsigned ver) {
+    const float z = fast_sigmoid(pre_s + sBg[l * 8 + 2 * i4]) * fast_tanh(pre_t + sBg[l * 8 + 2 * i4 + 1]);
+    const float zn = __shfl_xor_sync(0xffffffffu, z, 1);
+    if (!(i4 & 1)) st_strong_u32(v512_word(ver) + (i4 >> 1), pack_tagged(z, zn, (ver >> 1) & 1u));
   };
 
   // =========================================================================== time loop
@@ -479,7 +501,7 @@ __global__ void __launch_bounds__(NT, 1) cl_gen_kernel(Plan p, GenArgsDev g) {
 
     // ================================================================ block 0 gate: symbols -> tables
     trace(t, 0, 0);
-    if (warp == 0) {
+    if (finisher) {
       int bad = 0;
       if (t == 0) {
         sy_p2 = sy_p1; sy_p1 = sy_c;
@@ -503,26 +525,19 @@ __global__ void __launch_bounds__(NT, 1) cl_gen_kernel(Plan p, GenArgsDev g) {
       if (bad) {
         if (lane == 0) *sAbort = 1;
       } else {
-        float ax[2][4];
-        aux_mma(0, t, ax);
-        float pre[4][2];
-#pragma unroll
-        for (int m = 0; m < 4; ++m) {
-          const int u = q4 + 8 * m;
-          const int c_ = __shfl_sync(0xffffffffu, sy_c, u), a_ = __shfl_sync(0xffffffffu, sy_p1, u), b_ = __shfl_sync(0xffffffffu, sy_p2, u);
-          const float2 ta = *(const float2*)(sT0 + ((0 * Q + c_) * 8 + 2 * i4));
-          const float2 tb = *(const float2*)(sT0 + ((1 * Q + a_) * 8 + 2 * i4));
-          const float2 tc = *(const float2*)(sT0 + ((2 * Q + b_) * 8 + 2 * i4));
-          pre[m][0] = ta.x + tb.x + tc.x + ax[m >> 1][(m & 1) * 2];
-          pre[m][1] = ta.y + tb.y + tc.y + ax[m >> 1][(m & 1) * 2 + 1];
-          if (i4 < 2) {   // fp32 residual stream of the owned channels restarts from the causal layer
-            const float2 e0 = *(const float2*)(sEo + ((0 * Q + a_) * 4 + 2 * i4));
-            const float2 e1 = *(const float2*)(sEo + ((1 * Q + c_) * 4 + 2 * i4));
-            xc[m][0] = e0.x + e1.x; xc[m][1] = e0.y + e1.y;
-          }
-          sk[m][0] = sk[m][1] = 0.f;
+        float a0_, a1_;
+        aux_pair(0, t, a0_, a1_);
+        const int c_ = __shfl_sync(0xffffffffu, sy_c, fu), a_ = __shfl_sync(0xffffffffu, sy_p1, fu), b_ = __shfl_sync(0xffffffffu, sy_p2, fu);
+        const float2 ta = *(const float2*)(sT0 + ((0 * Q + c_) * 8 + 2 * i4));
+        const float2 tb = *(const float2*)(sT0 + ((1 * Q + a_) * 8 + 2 * i4));
+        const float2 tc = *(const float2*)(sT0 + ((2 * Q + b_) * 8 + 2 * i4));
+        if (i4 < 2) {   // fp32 residual stream of the owned channels restarts from the causal layer
+          const float2 e0 = *(const float2*)(sEo + ((0 * Q + a_) * 4 + 2 * i4));
+          const float2 e1 = *(const float2*)(sEo + ((1 * Q + c_) * 4 + 2 * i4));
+          xc0 = e0.x + e1.x; xc1 = e0.y + e1.y;
         }
-        publish_gate(0, pre, (w512 + 0u) & 1u);
+        sk0 = sk1 = 0.f;
+        publish_gate(0, ta.x + tb.x + tc.x + a0_, ta.y + tb.y + tc.y + a1_, w512);
       }
     }
     trace(t, 0, 3);
@@ -533,20 +548,25 @@ __global__ void __launch_bounds__(NT, 1) cl_gen_kernel(Plan p, GenArgsDev g) {
       int kind, l;
       if (ph < 2 * L - 1) { kind = (ph & 1) ? K_GATE : K_RES; l = (ph + 1) >> 1; }
       else { kind = ph == 2 * L - 1 ? K_HEAD1 : K_HEAD2; l = 0; }
+      const bool is512 = kind == K_GATE || kind == K_RES;
       const int tph = kind == K_GATE ? 2 * l : kind == K_RES ? 2 * l + 1 : kind == K_HEAD1 ? 2 * L : 2 * L + 1;
       trace(t, tph, 0);
       const int ab = rp & 1;
       __nv_bfloat16* Acur = sAcur + ab * UB * PA;
       const unsigned bar = smem_u32(&sBars[ab]);
       if (tid == 0) mbar_expect_tx(bar, NPART * 512);
+      // aux 1x1 of the owned rows needs nothing from this phase's exchange: run it while the input is in flight
+      float a0_ = 0.f, a1_ = 0.f;
+      if (finisher && kind == K_GATE) aux_pair(l, t, a0_, a1_);
 
       // ---- (1) poll this rank's K-share of the input vector, stage it as the MMA A tile
       int fail = 0;
-      if (kind == K_GATE || kind == K_RES) {
+      if (is512) {
         // res l reads z_l (write index 2l), gate l reads x_l (write index 2l - 1)
-        const unsigned par = (w512 + (unsigned)(kind == K_RES ? 2 * l : 2 * l - 1)) & 1u;
+        const unsigned ver = w512 + (unsigned)(kind == K_RES ? 2 * l : 2 * l - 1);
+        const unsigned par = (ver >> 1) & 1u;
         // share = owner blocks 32*rank .. 32*rank+31 (16 pieces of 16 bytes each): two pieces per thread
-        const uint4* src = (const uint4*)p.v512 + (size_t)(32 * rank) * 16 + tid;
+        const uint4* src = (const uint4*)p.v512 + (size_t)(ver & 1u) * NOWN * 16 + (size_t)(32 * rank) * 16 + tid;
         uint4 v[2];
         unsigned pend = 3;
         unsigned spins = 0; long long t0 = 0;
@@ -559,34 +579,39 @@ __global__ void __launch_bounds__(NT, 1) cl_gen_kernel(Plan p, GenArgsDev g) {
             if ((pend & (1u << j)) && fresh4(v[j], par)) pend &= ~(1u << j);
           if (pend && spin_check(spins, t0)) { fail = 1; break; }
         }
-        const int rs = kind == K_GATE ? p.ring_size[l] : 1;
-        const size_t slot_stride = (size_t)NOWN * UB * KS;
+        const int u0 = 2 * (tid & 15), col0 = 4 * (tid >> 4);
 #pragma unroll
         for (int j = 0; j < 2; ++j) {
-          const int pidx = tid + 256 * j;
-          const int u0 = 2 * (pidx & 15), col = 4 * (pidx >> 4);
-          *(uint2*)(Acur + u0 * PA + col) = make_uint2(v[j].x, v[j].y);
-          *(uint2*)(Acur + (u0 + 1) * PA + col) = make_uint2(v[j].z, v[j].w);
-          if (kind == K_GATE && !fail) {
-            // keep x_l(t) for the past taps of later steps; the priming step fills the whole ring with
-            // the constant of the pad region (qpnet.py:355-440)
-            __nv_bfloat16* r0 = p.ring[l] + ((size_t)s * UB + u0) * KS + col;
-            if (prime) {
-              for (int sl = 0; sl < rs; ++sl) {
-                *(uint2*)(r0 + sl * slot_stride) = make_uint2(v[j].x, v[j].y);
-                *(uint2*)(r0 + sl * slot_stride + KS) = make_uint2(v[j].z, v[j].w);
+          *(uint2*)(Acur + u0 * PA + col0 + 64 * j) = make_uint2(v[j].x, v[j].y);
+          *(uint2*)(Acur + (u0 + 1) * PA + col0 + 64 * j) = make_uint2(v[j].z, v[j].w);
+        }
+        if (kind == K_GATE && !fail) {
+          // keep x_l(t) for the past taps of later steps; the priming step fills the whole ring with
+          // the constant of the pad region (qpnet.py:355-440)
+          const int rs = p.ring_size[l];
+          const size_t slot_stride = (size_t)NOWN * UB * KS;
+          __nv_bfloat16* r0 = p.ring[l] + ((size_t)s * UB + u0) * KS + col0;
+          if (prime) {
+            for (int sl = 0; sl < rs; ++sl) {
+#pragma unroll
+              for (int j = 0; j < 2; ++j) {
+                *(uint2*)(r0 + sl * slot_stride + 64 * j) = make_uint2(v[j].x, v[j].y);
+                *(uint2*)(r0 + sl * slot_stride + KS + 64 * j) = make_uint2(v[j].z, v[j].w);
               }
-            } else {
-              __nv_bfloat16* r1 = r0 + (size_t)(t & (rs - 1)) * slot_stride;
-              *(uint2*)r1 = make_uint2(v[j].x, v[j].y);
-              *(uint2*)(r1 + KS) = make_uint2(v[j].z, v[j].w);
+            }
+          } else {
+            __nv_bfloat16* r1 = r0 + (size_t)(t & (rs - 1)) * slot_stride;
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+              *(uint2*)(r1 + 64 * j) = make_uint2(v[j].x, v[j].y);
+              *(uint2*)(r1 + KS + 64 * j) = make_uint2(v[j].z, v[j].w);
             }
           }
         }
       } else {
-        const unsigned par = kind == K_HEAD1 ? 0u : 1u;
+        const unsigned par = (unsigned)t & 1u;
         // share = owner blocks 32*rank .. 32*rank+31 (8 pieces each): one piece per thread
-        const uint4* src = (const uint4*)p.v256 + (size_t)(32 * rank) * 8 + tid;
+        const uint4* src = (const uint4*)p.v256 + (size_t)(kind == K_HEAD1 ? 0 : 1) * NOWN * 8 + (size_t)(32 * rank) * 8 + tid;
         uint4 v;
         unsigned spins = 0; long long t0 = 0;
         while (true) {
@@ -600,54 +625,62 @@ __global__ void __launch_bounds__(NT, 1) cl_gen_kernel(Plan p, GenArgsDev g) {
         *(unsigned*)(Acur + (u0 + 2) * PA + col) = v.z;
         *(unsigned*)(Acur + (u0 + 3) * PA + col) = v.w;
       }
-      cp_async_wait<1>();   // this phase's weight tile (and the past rows fetched with tile 1) have landed
+      cp_async_wait<1>();   // streaming warps: this phase's weight tile (and its past rows) have landed
       if (__syncthreads_or(fail | *sAbort)) goto done;
       trace(t, tph, 1);
-      issue_next_tile();
 
-      // ---- (2) tensor-core tile: 32 utterances x the 8 rows cluster rank `warp` owns, over this rank's K-share
-      {
-        float acc[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
-        const __nv_bfloat16* Wt = (const __nv_bfloat16*)(sW + (rp % NSLOT) * WSLOT);
-        const int pw = kind == K_GATE ? PWG : kind == K_RES ? PWR : PWH;
-        const int nt = warp & 3, kh = warp >> 2;   // owner rank whose 8 rows this warp computes, K-half of the share
-        const int kbase = kh * ((kind == K_HEAD1 || kind == K_HEAD2) ? KH / 2 : KS / 2);
-        const __nv_bfloat16* ap = Acur + (lane & 15) * PA + (lane >> 4) * 8 + kbase;
-        const __nv_bfloat16* bp = Wt + (8 * nt + (lane & 7)) * pw + ((lane >> 3) & 1) * 8 + kbase;
-        const int ksteps = (kind == K_HEAD1 || kind == K_HEAD2) ? KH / 32 : KS / 32;
-        for (int ks = 0; ks < ksteps; ++ks) {
-          unsigned b0, b1, a0, a1, a2, a3;
-          ldmatrix_x2(b0, b1, bp + ks * 16);
-          ldmatrix_x4(a0, a1, a2, a3, ap + ks * 16);
-          mma_bf16(acc[0], a0, a1, a2, a3, b0, b1);
-          ldmatrix_x4(a0, a1, a2, a3, ap + 16 * PA + ks * 16);
-          mma_bf16(acc[1], a0, a1, a2, a3, b0, b1);
-        }
-        if (kind == K_GATE) {
-          // past tap: x_l(t - k) rows that travelled with the weight tile; in the priming region past == present
-          const __nv_bfloat16* pp = prime ? ap : (const __nv_bfloat16*)((const unsigned char*)Wt + WTILE) + (lane & 15) * PA + (lane >> 4) * 8 + kbase;
+      // ---- (2) tensor-core tiles (warps 0-3): 32 utterances x the 16 rows owner ranks 2*(warp & 1), +1 finish,
+      // over K-half (warp >> 1).  2 x 2 register blocking halves the shared-memory operand traffic of 1 x 2.
+      if (finisher) {
+        float acc[2][2][4];   // [owner of the pair][m tile][fragment]
 #pragma unroll
-          for (int ks = 0; ks < KS / 32; ++ks) {
-            unsigned b0, b1, a0, a1, a2, a3;
-            ldmatrix_x2(b0, b1, bp + KS + ks * 16);
-            ldmatrix_x4(a0, a1, a2, a3, pp + ks * 16);
-            mma_bf16(acc[0], a0, a1, a2, a3, b0, b1);
-            ldmatrix_x4(a0, a1, a2, a3, pp + 16 * PA + ks * 16);
-            mma_bf16(acc[1], a0, a1, a2, a3, b0, b1);
+        for (int a_ = 0; a_ < 2; ++a_)
+#pragma unroll
+          for (int b_ = 0; b_ < 2; ++b_) acc[a_][b_][0] = acc[a_][b_][1] = acc[a_][b_][2] = acc[a_][b_][3] = 0.f;
+        const __nv_bfloat16* Wt = (const __nv_bfloat16*)(sW + cur_slot * WSLOT);
+        const int ntp = warp & 1, kh = warp >> 1;
+        auto kloop = [&](const __nv_bfloat16* ap, const __nv_bfloat16* bp, auto KSTEPS) {
+#pragma unroll
+          for (int ks = 0; ks < decltype(KSTEPS)::value; ++ks) {
+            unsigned b0, b1, b2, b3, a0, a1, a2, a3, c0, c1, c2, c3;
+            ldmatrix_x4(b0, b1, b2, b3, bp + ks * 16);   // rows 0-7 (k lo, k hi), rows 8-15 (k lo, k hi)
+            ldmatrix_x4(a0, a1, a2, a3, ap + ks * 16);
+            ldmatrix_x4(c0, c1, c2, c3, ap + 16 * PA + ks * 16);
+            mma_bf16(acc[0][0], a0, a1, a2, a3, b0, b1);
+            mma_bf16(acc[1][0], a0, a1, a2, a3, b2, b3);
+            mma_bf16(acc[0][1], c0, c1, c2, c3, b0, b1);
+            mma_bf16(acc[1][1], c0, c1, c2, c3, b2, b3);
           }
+        };
+        const int lrow = (lane & 15) * PA + (lane >> 4) * 8;
+        // B operand through ldmatrix.x4: lanes 0-7 rows 0-7 k lo, 8-15 rows 0-7 k hi, 16-23 rows 8-15 k lo, 24-31 rows 8-15 k hi
+        const int brow = 16 * ntp + (lane & 7) + ((lane >> 4) << 3), bcol = ((lane >> 3) & 1) * 8;
+        if (kind == K_GATE) {
+          const __nv_bfloat16* ap = Acur + lrow + kh * (KS / 2);
+          const __nv_bfloat16* bp = Wt + brow * PWG + bcol + kh * (KS / 2);
+          kloop(ap, bp, std::integral_constant<int, KS / 32>());
+          // past tap: x_l(t - k) rows that travelled with the weight tile; in the priming region past == present
+          const __nv_bfloat16* pp = prime ? ap : (const __nv_bfloat16*)((const unsigned char*)Wt + WTILE) + lrow + kh * (KS / 2);
+          kloop(pp, bp + KS, std::integral_constant<int, KS / 32>());
+        } else if (kind == K_RES) {
+          kloop(Acur + lrow + kh * (KS / 2), Wt + brow * PWR + bcol + kh * (KS / 2), std::integral_constant<int, KS / 32>());
+        } else {
+          kloop(Acur + lrow + kh * (KH / 2), Wt + brow * PWH + bcol + kh * (KH / 2), std::integral_constant<int, KH / 32>());
         }
-        // partial tile -> owner rank `warp`: utterances (q4, q4+8, q4+16, q4+24) x rows (2*i4, 2*i4+1), fp16
-        uint4 pk = make_uint4(pack_h2(acc[0][0], acc[0][1]), pack_h2(acc[0][2], acc[0][3]),
-                              pack_h2(acc[1][0], acc[1][1]), pack_h2(acc[1][2], acc[1][3]));
-        const unsigned dst = smem_u32(sRecv + (ab * NPART + rank * 2 + kh) * 32 + lane);
-        st_async_v4(mapa(dst, nt), pk, mapa(bar, nt));
+        // partial tiles -> owner ranks: utterances (q4, q4+8, q4+16, q4+24) x rows (2*i4, 2*i4+1), fp16
+#pragma unroll
+        for (int a_ = 0; a_ < 2; ++a_) {
+          const int nt = 2 * ntp + a_;
+          uint4 pk = make_uint4(pack_h2(acc[a_][0][0], acc[a_][0][1]), pack_h2(acc[a_][0][2], acc[a_][0][3]),
+                                pack_h2(acc[a_][1][0], acc[a_][1][1]), pack_h2(acc[a_][1][2], acc[a_][1][3]));
+          const unsigned dst = smem_u32(sRecv + (ab * NPART + rank * 2 + kh) * 32 + lane);
+          st_async_v4(mapa(dst, nt), pk, mapa(bar, nt));
+        }
       }
       trace(t, tph, 2);
 
-      // ---- (3) owner warp: sum the 8 partial tiles, finish the owned rows, publish
-      if (warp == 0) {
-        float ax[2][4];
-        if (kind == K_GATE) aux_mma(l, t, ax);
+      if (finisher) {
+        // ---- (3) finisher warps: sum the 8 partial tiles of (utterance fu, rows 2*i4, 2*i4+1), finish, publish
         int bad = 0;
         {
           unsigned spins = 0; long long t0 = 0;
@@ -659,84 +692,72 @@ __global__ void __launch_bounds__(NT, 1) cl_gen_kernel(Plan p, GenArgsDev g) {
         if (bad) {
           if (lane == 0) *sAbort = 1;
         } else {
-          float sum[4][2];
-#pragma unroll
-          for (int m = 0; m < 4; ++m) sum[m][0] = sum[m][1] = 0.f;
+          float s0 = 0.f, s1 = 0.f;
+          const unsigned* rw = (const unsigned*)(sRecv + ab * NPART * 32 + lane) + warp;
 #pragma unroll
           for (int srcr = 0; srcr < NPART; ++srcr) {
-            const uint4 qv = sRecv[(ab * NPART + srcr) * 32 + lane];
-            float2 f;
-            f = unpack_h2(qv.x); sum[0][0] += f.x; sum[0][1] += f.y;
-            f = unpack_h2(qv.y); sum[1][0] += f.x; sum[1][1] += f.y;
-            f = unpack_h2(qv.z); sum[2][0] += f.x; sum[2][1] += f.y;
-            f = unpack_h2(qv.w); sum[3][0] += f.x; sum[3][1] += f.y;
+            const float2 f = unpack_h2(rw[srcr * 32 * 4]);
+            s0 += f.x; s1 += f.y;
           }
           if (kind == K_GATE) {
-#pragma unroll
-            for (int m = 0; m < 4; ++m) { sum[m][0] += ax[m >> 1][(m & 1) * 2]; sum[m][1] += ax[m >> 1][(m & 1) * 2 + 1]; }
-            publish_gate(l, sum, (w512 + (unsigned)(2 * l)) & 1u);
+            publish_gate(l, s0 + a0_, s1 + a1_, w512 + (unsigned)(2 * l));
           } else if (kind == K_RES) {
             const bool last = l == L - 1;
-            const unsigned par = (w512 + (unsigned)(2 * l + 1)) & 1u;
-            const float b0 = sBr[l * 8 + 2 * i4], b1 = sBr[l * 8 + 2 * i4 + 1];
-#pragma unroll
-            for (int m = 0; m < 4; ++m) {
-              const int u = q4 + 8 * m;
-              const float v0 = sum[m][0] + b0, v1 = sum[m][1] + b1;
-              if (i4 < 2) {
-                // residual projection + current input (qpnet.py:669 / 639); dead after the last block (C7)
-                xc[m][0] += v0; xc[m][1] += v1;
-                if (!last) st_strong_u32(p.v512 + ((size_t)s * UB + u) * 2 + i4, pack_tagged(xc[m][0], xc[m][1], par));
-              } else if (i4 == 2) {
-                sk[m][0] += v0; sk[m][1] += v1;
-                if (last && !prime)
-                  st_strong_u32(p.v256 + (size_t)s * UB + u, pack_tagged(fmaxf(sk[m][0], 0.f), fmaxf(sk[m][1], 0.f), 0u));
+            const float v0 = s0 + sBr[l * 8 + 2 * i4], v1 = s1 + sBr[l * 8 + 2 * i4 + 1];
+            if (i4 < 2) {
+              // residual projection + current input (qpnet.py:669 / 639); dead after the last block (C7)
+              xc0 += v0; xc1 += v1;
+              if (!last) {
+                const unsigned ver = w512 + (unsigned)(2 * l + 1);
+                st_strong_u32(v512_word(ver) + i4, pack_tagged(xc0, xc1, (ver >> 1) & 1u));
               }
+            } else if (i4 == 2) {
+              sk0 += v0; sk1 += v1;
+              if (last && !prime)
+                st_strong_u32(p.v256 + (size_t)s * UB + fu, pack_tagged(fmaxf(sk0, 0.f), fmaxf(sk1, 0.f), (unsigned)t & 1u));
             }
           } else if (kind == K_HEAD1) {
-            if (i4 == 0) {
-#pragma unroll
-              for (int m = 0; m < 4; ++m)
-                st_strong_u32(p.v256 + (size_t)s * UB + q4 + 8 * m,
-                              pack_tagged(fmaxf(sum[m][0] + sBh[0], 0.f), fmaxf(sum[m][1] + sBh[1], 0.f), 1u));
-            }
+            if (i4 == 0)
+              st_strong_u32(p.v256 + (size_t)(NOWN + s) * UB + fu, pack_tagged(fmaxf(s0 + sBh[0], 0.f), fmaxf(s1 + sBh[1], 0.f), (unsigned)t & 1u));
           } else {
             if (i4 == 0) {
               const unsigned par_t = (unsigned)t & 1u;
-#pragma unroll
-              for (int m = 0; m < 4; ++m)
-                st_strong_v2(p.vlog + ((size_t)s * UB + q4 + 8 * m) * 2,
-                             (__float_as_uint(sum[m][0] + sBh[8]) & ~1u) | par_t, (__float_as_uint(sum[m][1] + sBh[9]) & ~1u) | par_t);
+              st_strong_v2(p.vlog + ((size_t)s * UB + fu) * 2, (__float_as_uint(s0 + sBh[8]) & ~1u) | par_t,
+                           (__float_as_uint(s1 + sBh[9]) & ~1u) | par_t);
             }
           }
         }
-      } else if (warp >= 2 && kind == K_RES && l == 0) {
-        // off the critical path: aux rows of the NEXT step, h_up[:, ta] = h[:, ta / U] * w[ta % U] + b (qpnet.py:143-158, 451)
-        const int tn = t + 1;
-        if (tn < g.max_steps) {
-          const int ta = tn < 0 ? 0 : tn;
-          const int f = ta / U, j = ta - f * U;
-          const int wt = tid - 64;
-          if (j == 0 && tn > 0) {
-            for (int e = wt; e < UB * A; e += NT - 64) {
-              int u = e / A, a = e - u * A;
-              sHraw[u * HR + a] = u < B ? g.h[((size_t)u * A + a) * p.F + f] : 0.f;
+      } else {
+        // ---- (3') streaming warps: next weight tile; once per step the aux rows of the NEXT step,
+        // h_up[:, ta] = h[:, ta / U] * w[ta % U] + b (qpnet.py:143-158, 451)
+        issue_next_tile();
+        if (kind == K_RES && l == 0) {
+          const int tn = t + 1;
+          if (tn < g.max_steps) {
+            const int ta = tn < 0 ? 0 : tn;
+            const int f = ta / U, j = ta - f * U;
+            if (j == 0 && tn > 0) {
+              for (int e = t128; e < UB * A; e += 128) {
+                int u = e / A, a = e - u * A;
+                sHraw[u * HR + a] = u < B ? g.h[((size_t)u * A + a) * p.F + f] : 0.f;
+              }
+              asm volatile("bar.sync 1, 128;\n" ::: "memory");
             }
-            asm volatile("bar.sync 1, 192;\n" ::: "memory");
-          }
-          const float w = g.up_w[j], bb = g.up_b[0];
-          for (int e = wt; e < UB * A; e += NT - 64) {
-            int u = e / A, a = e - u * A;
-            sHaux[((tn & 1) * UB + u) * PH + a] = __float2bfloat16(sHraw[u * HR + a] * w + bb);
+            const float w = g.up_w[j], bb = g.up_b[0];
+            for (int e = t128; e < UB * A; e += 128) {
+              int u = e / A, a = e - u * A;
+              sHaux[((tn & 1) * UB + u) * PH + a] = __float2bfloat16(sHraw[u * HR + a] * w + bb);
+            }
           }
         }
       }
       trace(t, tph, 3);
       ++rp;
+      cur_slot = cur_slot == NSLOT - 1 ? 0 : cur_slot + 1;
     }
 
     // ================================================================ sampling: one warp per utterance
-    if (!prime && warp == 1 && s < B) {
+    if (!prime && warp == 7 && s < B) {
       if (TRACE && s == 0 && lane == 0 && t >= p.trace_step0 && t < p.trace_step0 + p.trace_nsteps)
         p.trace[((size_t)(t - p.trace_step0) * nphase + 2 * L + 2) * TRACE_EVENTS + 0] = clock64();
       const int u = s;
@@ -847,7 +868,7 @@ int cl_generate(const QpArch* arch, const float* const* tensors_host, const QpGe
   int ncl = 0;
   QP_CUDA(cudaOccupancyMaxActiveClusters(&ncl, kern, &cfg));
   if (ncl < cl::NOWN / cl::CL) return 1;
-  cfg.numAttrs = 2;
+  cfg.numAttrs = getenv("QPNET_GEN_NOCOOP") ? 1 : 2;   // (profilers that cannot replay cooperative cluster launches)
 
   QP_CUDA(cudaMemsetAsync(p.status, 0, 256, st));
   QP_CUDA(cudaMemsetAsync(p.tagged_begin, 0xFF, p.tagged_bytes, st));   // every word starts with a stale tag

@@ -1,0 +1,66 @@
+"""CPU suite for the training-side host logic: the segmenter's length arithmetic
+(qpnet_train.py:268-284) and the data-parallel gradient bucket (world_size 2, gloo)."""
+import os
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+
+def test_segment_geometry_matches_reference_arithmetic():
+    from qpnet_b200.train import segment_geometry
+    # qpnet_train.py:181-199, 268-284 with the SI defaults: rf 1 / 45 / 15, U 110, batch_length 20000, max 30000
+    R, bl, h_bs, x_bs = segment_geometry(61.25, 20000, 110, 1, 45, 15, 30000)
+    assert (R, bl, h_bs, x_bs) == (976, 19924, 190, 20901)
+    assert (R + bl) % 110 == 0
+    # x0.5 F0 -> M = 123: R = 1 + 45 + 15 * 123 = 1891
+    R, bl, h_bs, x_bs = segment_geometry(122.5, 20000, 110, 1, 45, 15, 30000)
+    assert R == 1891 and (R + bl) % 110 == 0 and bl <= 20000 and x_bs == h_bs * 110 + 1
+    # max_length clamp (batch_mod1)
+    R, bl, _, _ = segment_geometry(61.25, 29900, 110, 1, 45, 15, 30000)
+    assert R + bl <= 30000 and (R + bl) % 110 == 0
+    with pytest.raises(ValueError):
+        segment_geometry(61.25, 100, 110, 1, 45, 15, 900)
+
+
+def _worker(rank, world, port, out):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from qpnet_b200.train import GradBucket
+    torch.manual_seed(0)
+    params = [torch.nn.Parameter(torch.zeros(3, 4)), torch.nn.Parameter(torch.zeros(5)), torch.nn.Parameter(torch.zeros(2, 2))]
+    params[0].grad = torch.full((3, 4), float(rank + 1))
+    params[1].grad = torch.arange(5, dtype=torch.float32) * (rank + 1)
+    # params[2] never receives a gradient (the dead resA_1x1 of the last block): must reduce as zeros
+    b = GradBucket(params)
+    assert b.numel == 12 + 5 + 4 and b.world == world
+    flat = b.allreduce_mean()
+    mean = (1 + world) / 2.0
+    ok = (torch.allclose(params[0].grad, torch.full((3, 4), mean))
+          and torch.allclose(params[1].grad, torch.arange(5, dtype=torch.float32) * mean)
+          and torch.equal(params[2].grad, torch.zeros(2, 2))
+          and flat.numel() == 21)
+    out[rank] = bool(ok)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_grad_bucket_allreduce_world2_gloo():
+    world = 2
+    port = 29500 + (os.getpid() % 2000)
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_worker, args=(world, port, out), nprocs=world, join=True)
+    assert dict(out) == {0: True, 1: True}
+
+
+def test_grad_bucket_single_process_is_identity():
+    from qpnet_b200.train import GradBucket
+    p = [torch.nn.Parameter(torch.zeros(4))]
+    p[0].grad = torch.tensor([1.0, 2.0, 3.0, 4.0])
+    b = GradBucket(p)
+    assert b.world == 1
+    b.allreduce_mean()
+    assert torch.equal(p[0].grad, torch.tensor([1.0, 2.0, 3.0, 4.0]))
