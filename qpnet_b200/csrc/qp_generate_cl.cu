@@ -20,10 +20,12 @@
 //     m16n8k16 tensor-core tiles (utterances = M, rows = N; warp w computes the 8 rows rank w & 3 owns
 //     over K-half w >> 2) and sends the 32x8 partial tile to that rank with ONE st.async per lane
 //     (fp16, 512 B per warp), completing on its mbarrier.  The owner warp sums the 8 partial tiles.
-//   * the past tap x(t-k) (qpnet.py:81-87, 457-502) comes from a per-CTA ring of its own K-share in
-//     global memory (the reference's FIFOs, qpnet.py:388-393, 431-437), prefetched with cp.async two
-//     phases ahead together with the block's weight tile; k = dil (fixed) or -round(-d[t]*dil) (adaptive, qpnet.py:616-617 / 621-622),
-//     k == 0 -> oldest entry (caveat C4).
+//   * the past tap Wp.x(t-k) (qpnet.py:81-87, 457-502) is never recomputed on the critical path: when
+//     x_l(t) is in shared memory the streaming warps also contract it with the PAST-tap weights and keep
+//     the fp32 partial tile P'(t) in a per-CTA ring in global memory (the reference's FIFOs,
+//     qpnet.py:388-393, 431-437, as partial sums); k steps later it is prefetched with cp.async behind
+//     the block's weight tile and seeds the accumulators.  k = dil (fixed) or -round(-d[t]*dil)
+//     (adaptive, qpnet.py:616-617 / 621-622), k == 0 -> oldest entry (caveat C4).
 //   * block 0 needs no exchange at all: its input is the causal layer, a function of the last three
 //     symbols, so its gate pre-activation is three table lookups (W.E folded at pack time, fp32).
 //   * aux 1x1 (qpnet.py:663-664, 632-633) is a 6-MMA side product of the owner warp, computed while
@@ -59,7 +61,7 @@ constexpr int WTILE = NR * PWG * 2;          // bytes of the largest weight tile
 constexpr int WSLOT = WTILE + UB * PA * 2;   // weight tile + the past-tap rows that travel with a gate tile
 constexpr int NSLOT = 3;
 constexpr int MAXL = 16;
-constexpr int TRACE_EVENTS = 4;
+constexpr int TRACE_EVENTS = 8;   // 0 start, 1 own pieces fresh, 2 barrier passed, 3 MMA done, 4 partials sent, 5 partials arrived, 6 published
 enum { K_GATE = 0, K_RES = 1, K_HEAD1 = 2, K_HEAD2 = 3 };
 
 struct Plan {
@@ -409,22 +411,25 @@ __global__ void __launch_bounds__(NT, 1) cl_gen_kernel(Plan p, GenArgsDev g) {
             cp_async16(dst + ((e >> 5) * PWG + (e & 31) * 8) * 2, src + (e >> 5) * 2 * KS + (e & 31) * 8);
           }
           if (pf_t >= 0) {
-            const int u = t128 >> 2;
-            int k = p.dil[l];
-            if (l >= p.nF) {   // pitch-dependent look-back of this step (qpnet.py:476-483, 613-624)
-              k = 0;
-              if (u < B)
-                k = g.d_is_f64 ? -gen_index_f64(((const double*)g.d)[(long long)u * ldd + pf_t], p.dil[l])
-                               : -gen_index_f32(((const float*)g.d)[(long long)u * ldd + pf_t], p.dil[l]);
-              if (k <= 0 || k > p.depth[l]) k = p.depth[l];   // k == 0: python index 0 = oldest entry (C4)
-            }
-            const int slot = (pf_t - k) & (p.ring_size[l] - 1);
-            const __nv_bfloat16* rsrc = p.ring[l] + (((size_t)slot * NOWN + s) * UB + u) * KS;
-            unsigned char* pdst = dst + WTILE + (u * PA) * 2;
+            // past-tap partial sums P'(t - k) = Wp . x_l(t - k) over this CTA's K-share, stored k steps ago in
+            // MMA fragment order: piece (warp w, utterance group m, lane) = 4 floats of utterance (lane >> 2) + 8m
+            const int ln = t128 & 31, w = t128 >> 5;
+            const float* ringf = (const float*)p.ring[l];
+            const int rmask = p.ring_size[l] - 1;
 #pragma unroll
-            for (int j = 0; j < KS / 8 / 4; ++j) {
-              const int cch = (t128 & 3) + 4 * j;
-              cp_async16(pdst + cch * 16, rsrc + cch * 8);
+            for (int m = 0; m < 4; ++m) {
+              const int u = (ln >> 2) + 8 * m;
+              int k = p.dil[l];
+              if (l >= p.nF) {   // pitch-dependent look-back of this step (qpnet.py:476-483, 613-624)
+                k = 0;
+                if (u < B)
+                  k = g.d_is_f64 ? -gen_index_f64(((const double*)g.d)[(long long)u * ldd + pf_t], p.dil[l])
+                                 : -gen_index_f32(((const float*)g.d)[(long long)u * ldd + pf_t], p.dil[l]);
+                if (k <= 0 || k > p.depth[l]) k = p.depth[l];   // k == 0: python index 0 = oldest entry (C4)
+              }
+              const int slot = (pf_t - k) & rmask;
+              cp_async16(dst + WTILE + ((w * 4 + m) * 32 + ln) * 16,
+                         ringf + (((size_t)slot * NOWN + s) * 4 + w) * 512 + (m * 32 + ln) * 4);
             }
           }
         } else {
@@ -540,16 +545,15 @@ __global__ void __launch_bounds__(NT, 1) cl_gen_kernel(Plan p, GenArgsDev g) {
         publish_gate(0, ta.x + tb.x + tc.x + a0_, ta.y + tb.y + tc.y + a1_, w512);
       }
     }
-    trace(t, 0, 3);
+    trace(t, 0, 6);
 
     // ================================================================ MMA phases
-    const int nmma = prime ? 2 * L - 1 : 2 * L + 1;
-    for (int ph = 0; ph < nmma; ++ph) {
-      int kind, l;
-      if (ph < 2 * L - 1) { kind = (ph & 1) ? K_GATE : K_RES; l = (ph + 1) >> 1; }
-      else { kind = ph == 2 * L - 1 ? K_HEAD1 : K_HEAD2; l = 0; }
-      const bool is512 = kind == K_GATE || kind == K_RES;
-      const int tph = kind == K_GATE ? 2 * l : kind == K_RES ? 2 * l + 1 : kind == K_HEAD1 ? 2 * L : 2 * L + 1;
+    // One phase = poll the K-share -> tensor-core tiles -> partial tiles to the owners -> finish + publish.
+    // KIND is a compile-time constant so every phase type gets straight-line code.
+    auto phase = [&](auto kc, const int l) -> bool {
+      constexpr int KIND = decltype(kc)::value;
+      constexpr bool is512 = KIND == K_GATE || KIND == K_RES;
+      const int tph = KIND == K_GATE ? 2 * l : KIND == K_RES ? 2 * l + 1 : KIND == K_HEAD1 ? 2 * L : 2 * L + 1;
       trace(t, tph, 0);
       const int ab = rp & 1;
       __nv_bfloat16* Acur = sAcur + ab * UB * PA;
@@ -557,13 +561,13 @@ __global__ void __launch_bounds__(NT, 1) cl_gen_kernel(Plan p, GenArgsDev g) {
       if (tid == 0) mbar_expect_tx(bar, NPART * 512);
       // aux 1x1 of the owned rows needs nothing from this phase's exchange: run it while the input is in flight
       float a0_ = 0.f, a1_ = 0.f;
-      if (finisher && kind == K_GATE) aux_pair(l, t, a0_, a1_);
+      if (KIND == K_GATE && finisher) aux_pair(l, t, a0_, a1_);
 
       // ---- (1) poll this rank's K-share of the input vector, stage it as the MMA A tile
       int fail = 0;
       if (is512) {
         // res l reads z_l (write index 2l), gate l reads x_l (write index 2l - 1)
-        const unsigned ver = w512 + (unsigned)(kind == K_RES ? 2 * l : 2 * l - 1);
+        const unsigned ver = w512 + (unsigned)(KIND == K_RES ? 2 * l : 2 * l - 1);
         const unsigned par = (ver >> 1) & 1u;
         // share = owner blocks 32*rank .. 32*rank+31 (16 pieces of 16 bytes each): two pieces per thread
         const uint4* src = (const uint4*)p.v512 + (size_t)(ver & 1u) * NOWN * 16 + (size_t)(32 * rank) * 16 + tid;
@@ -585,88 +589,77 @@ __global__ void __launch_bounds__(NT, 1) cl_gen_kernel(Plan p, GenArgsDev g) {
           *(uint2*)(Acur + u0 * PA + col0 + 64 * j) = make_uint2(v[j].x, v[j].y);
           *(uint2*)(Acur + (u0 + 1) * PA + col0 + 64 * j) = make_uint2(v[j].z, v[j].w);
         }
-        if (kind == K_GATE && !fail) {
-          // keep x_l(t) for the past taps of later steps; the priming step fills the whole ring with
-          // the constant of the pad region (qpnet.py:355-440)
-          const int rs = p.ring_size[l];
-          const size_t slot_stride = (size_t)NOWN * UB * KS;
-          __nv_bfloat16* r0 = p.ring[l] + ((size_t)s * UB + u0) * KS + col0;
-          if (prime) {
-            for (int sl = 0; sl < rs; ++sl) {
-#pragma unroll
-              for (int j = 0; j < 2; ++j) {
-                *(uint2*)(r0 + sl * slot_stride + 64 * j) = make_uint2(v[j].x, v[j].y);
-                *(uint2*)(r0 + sl * slot_stride + KS + 64 * j) = make_uint2(v[j].z, v[j].w);
-              }
-            }
-          } else {
-            __nv_bfloat16* r1 = r0 + (size_t)(t & (rs - 1)) * slot_stride;
-#pragma unroll
-            for (int j = 0; j < 2; ++j) {
-              *(uint2*)(r1 + 64 * j) = make_uint2(v[j].x, v[j].y);
-              *(uint2*)(r1 + KS + 64 * j) = make_uint2(v[j].z, v[j].w);
-            }
-          }
-        }
       } else {
         const unsigned par = (unsigned)t & 1u;
         // share = owner blocks 32*rank .. 32*rank+31 (8 pieces each): one piece per thread
-        const uint4* src = (const uint4*)p.v256 + (size_t)(kind == K_HEAD1 ? 0 : 1) * NOWN * 8 + (size_t)(32 * rank) * 8 + tid;
-        uint4 v;
+        const uint4* src = (const uint4*)p.v256 + (size_t)(KIND == K_HEAD1 ? 0 : 1) * NOWN * 8 + (size_t)(32 * rank) * 8 + tid;
+        uint4 w;
         unsigned spins = 0; long long t0 = 0;
         while (true) {
-          v = ld_strong_v4(src);
-          if (fresh4(v, par)) break;
+          w = ld_strong_v4(src);
+          if (fresh4(w, par)) break;
           if (spin_check(spins, t0)) { fail = 1; break; }
         }
-        const int u0 = 4 * (tid & 7), col = 2 * (tid >> 3);
-        *(unsigned*)(Acur + u0 * PA + col) = v.x;
-        *(unsigned*)(Acur + (u0 + 1) * PA + col) = v.y;
-        *(unsigned*)(Acur + (u0 + 2) * PA + col) = v.z;
-        *(unsigned*)(Acur + (u0 + 3) * PA + col) = v.w;
+        const int uh = 4 * (tid & 7), col = 2 * (tid >> 3);
+        *(unsigned*)(Acur + uh * PA + col) = w.x;
+        *(unsigned*)(Acur + (uh + 1) * PA + col) = w.y;
+        *(unsigned*)(Acur + (uh + 2) * PA + col) = w.z;
+        *(unsigned*)(Acur + (uh + 3) * PA + col) = w.w;
       }
-      cp_async_wait<1>();   // streaming warps: this phase's weight tile (and its past rows) have landed
-      if (__syncthreads_or(fail | *sAbort)) goto done;
       trace(t, tph, 1);
+      cp_async_wait<1>();   // streaming warps: this phase's weight tile (and its past partial sums) have landed
+      if (__syncthreads_or(fail | *sAbort)) return true;
+      trace(t, tph, 2);
 
-      // ---- (2) tensor-core tiles (warps 0-3): 32 utterances x the 16 rows owner ranks 2*(warp & 1), +1 finish,
-      // over K-half (warp >> 1).  2 x 2 register blocking halves the shared-memory operand traffic of 1 x 2.
-      if (finisher) {
-        float acc[2][2][4];   // [owner of the pair][m tile][fragment]
+      // ---- tensor-core tiles, shared by both roles: warp (w4 = warp & 3) contracts 32 utterances x the 16 rows
+      // owner ranks 2*(w4 & 1), +1 finish over K-half (w4 >> 1).  2 x 2 register blocking halves the
+      // shared-memory operand traffic of 1 x 2.
+      const __nv_bfloat16* Wt = (const __nv_bfloat16*)(sW + cur_slot * WSLOT);
+      const int w4 = warp & 3, ntp = w4 & 1, kh = w4 >> 1;
+      const int lrow = (lane & 15) * PA + (lane >> 4) * 8;
+      // B operand through ldmatrix.x4: lanes 0-7 rows 0-7 k lo, 8-15 rows 0-7 k hi, 16-23 rows 8-15 k lo, 24-31 rows 8-15 k hi
+      const int brow = 16 * ntp + (lane & 7) + ((lane >> 4) << 3), bcol = ((lane >> 3) & 1) * 8;
+      constexpr int PW = KIND == K_GATE ? PWG : KIND == K_RES ? PWR : PWH;
+      constexpr int KHALF = is512 ? KS / 2 : KH / 2;
+      const __nv_bfloat16* ap = Acur + lrow + kh * KHALF;
+      const __nv_bfloat16* bp = Wt + brow * PW + bcol + kh * KHALF;
+      auto kloop = [&](float (&acc)[2][2][4], const __nv_bfloat16* bq) {
 #pragma unroll
-        for (int a_ = 0; a_ < 2; ++a_)
-#pragma unroll
-          for (int b_ = 0; b_ < 2; ++b_) acc[a_][b_][0] = acc[a_][b_][1] = acc[a_][b_][2] = acc[a_][b_][3] = 0.f;
-        const __nv_bfloat16* Wt = (const __nv_bfloat16*)(sW + cur_slot * WSLOT);
-        const int ntp = warp & 1, kh = warp >> 1;
-        auto kloop = [&](const __nv_bfloat16* ap, const __nv_bfloat16* bp, auto KSTEPS) {
-#pragma unroll
-          for (int ks = 0; ks < decltype(KSTEPS)::value; ++ks) {
-            unsigned b0, b1, b2, b3, a0, a1, a2, a3, c0, c1, c2, c3;
-            ldmatrix_x4(b0, b1, b2, b3, bp + ks * 16);   // rows 0-7 (k lo, k hi), rows 8-15 (k lo, k hi)
-            ldmatrix_x4(a0, a1, a2, a3, ap + ks * 16);
-            ldmatrix_x4(c0, c1, c2, c3, ap + 16 * PA + ks * 16);
-            mma_bf16(acc[0][0], a0, a1, a2, a3, b0, b1);
-            mma_bf16(acc[1][0], a0, a1, a2, a3, b2, b3);
-            mma_bf16(acc[0][1], c0, c1, c2, c3, b0, b1);
-            mma_bf16(acc[1][1], c0, c1, c2, c3, b2, b3);
-          }
-        };
-        const int lrow = (lane & 15) * PA + (lane >> 4) * 8;
-        // B operand through ldmatrix.x4: lanes 0-7 rows 0-7 k lo, 8-15 rows 0-7 k hi, 16-23 rows 8-15 k lo, 24-31 rows 8-15 k hi
-        const int brow = 16 * ntp + (lane & 7) + ((lane >> 4) << 3), bcol = ((lane >> 3) & 1) * 8;
-        if (kind == K_GATE) {
-          const __nv_bfloat16* ap = Acur + lrow + kh * (KS / 2);
-          const __nv_bfloat16* bp = Wt + brow * PWG + bcol + kh * (KS / 2);
-          kloop(ap, bp, std::integral_constant<int, KS / 32>());
-          // past tap: x_l(t - k) rows that travelled with the weight tile; in the priming region past == present
-          const __nv_bfloat16* pp = prime ? ap : (const __nv_bfloat16*)((const unsigned char*)Wt + WTILE) + lrow + kh * (KS / 2);
-          kloop(pp, bp + KS, std::integral_constant<int, KS / 32>());
-        } else if (kind == K_RES) {
-          kloop(Acur + lrow + kh * (KS / 2), Wt + brow * PWR + bcol + kh * (KS / 2), std::integral_constant<int, KS / 32>());
-        } else {
-          kloop(Acur + lrow + kh * (KH / 2), Wt + brow * PWH + bcol + kh * (KH / 2), std::integral_constant<int, KH / 32>());
+        for (int ks = 0; ks < KHALF / 16; ++ks) {
+          unsigned b0, b1, b2, b3, a0, a1, a2, a3, c0, c1, c2, c3;
+          ldmatrix_x4(b0, b1, b2, b3, bq + ks * 16);   // rows 0-7 (k lo, k hi), rows 8-15 (k lo, k hi)
+          ldmatrix_x4(a0, a1, a2, a3, ap + ks * 16);
+          ldmatrix_x4(c0, c1, c2, c3, ap + 16 * PA + ks * 16);
+          mma_bf16(acc[0][0], a0, a1, a2, a3, b0, b1);
+          mma_bf16(acc[1][0], a0, a1, a2, a3, b2, b3);
+          mma_bf16(acc[0][1], c0, c1, c2, c3, b0, b1);
+          mma_bf16(acc[1][1], c0, c1, c2, c3, b2, b3);
         }
+      };
+      // fragment <-> ring piece: utterance group m = 2*mt + (f >> 1) holds {acc[0][mt][2(f>>1)..+1], acc[1][mt][2(f>>1)..+1]}
+      float acc[2][2][4];   // [owner of the pair][m tile][fragment]
+#pragma unroll
+      for (int a_ = 0; a_ < 2; ++a_)
+#pragma unroll
+        for (int b_ = 0; b_ < 2; ++b_) acc[a_][b_][0] = acc[a_][b_][1] = acc[a_][b_][2] = acc[a_][b_][3] = 0.f;
+
+      if (finisher) {
+        // ---- (2) current tap (+ the past-tap partial sums P'(t - k) that travelled with the weight tile)
+        if (KIND == K_GATE) {
+          if (!prime) {
+            const float4* pin = (const float4*)((const unsigned char*)Wt + WTILE) + w4 * 128 + lane;
+#pragma unroll
+            for (int m = 0; m < 4; ++m) {
+              const float4 q = pin[m * 32];
+              acc[0][m >> 1][(m & 1) * 2] = q.x; acc[0][m >> 1][(m & 1) * 2 + 1] = q.y;
+              acc[1][m >> 1][(m & 1) * 2] = q.z; acc[1][m >> 1][(m & 1) * 2 + 1] = q.w;
+            }
+          } else {
+            kloop(acc, bp + KS);   // priming region: the past equals the present (qpnet.py:355-440)
+          }
+        }
+        kloop(acc, bp);
+        trace(t, tph, 3);
         // partial tiles -> owner ranks: utterances (q4, q4+8, q4+16, q4+24) x rows (2*i4, 2*i4+1), fp16
 #pragma unroll
         for (int a_ = 0; a_ < 2; ++a_) {
@@ -676,11 +669,9 @@ __global__ void __launch_bounds__(NT, 1) cl_gen_kernel(Plan p, GenArgsDev g) {
           const unsigned dst = smem_u32(sRecv + (ab * NPART + rank * 2 + kh) * 32 + lane);
           st_async_v4(mapa(dst, nt), pk, mapa(bar, nt));
         }
-      }
-      trace(t, tph, 2);
+        trace(t, tph, 4);
 
-      if (finisher) {
-        // ---- (3) finisher warps: sum the 8 partial tiles of (utterance fu, rows 2*i4, 2*i4+1), finish, publish
+        // ---- (3) sum the 8 partial tiles of (utterance fu, rows 2*i4, 2*i4+1), finish, publish
         int bad = 0;
         {
           unsigned spins = 0; long long t0 = 0;
@@ -689,6 +680,7 @@ __global__ void __launch_bounds__(NT, 1) cl_gen_kernel(Plan p, GenArgsDev g) {
             if (spin_check(spins, t0)) { bad = 1; break; }
           }
         }
+        trace(t, tph, 5);
         if (bad) {
           if (lane == 0) *sAbort = 1;
         } else {
@@ -699,9 +691,9 @@ __global__ void __launch_bounds__(NT, 1) cl_gen_kernel(Plan p, GenArgsDev g) {
             const float2 f = unpack_h2(rw[srcr * 32 * 4]);
             s0 += f.x; s1 += f.y;
           }
-          if (kind == K_GATE) {
+          if (KIND == K_GATE) {
             publish_gate(l, s0 + a0_, s1 + a1_, w512 + (unsigned)(2 * l));
-          } else if (kind == K_RES) {
+          } else if (KIND == K_RES) {
             const bool last = l == L - 1;
             const float v0 = s0 + sBr[l * 8 + 2 * i4], v1 = s1 + sBr[l * 8 + 2 * i4 + 1];
             if (i4 < 2) {
@@ -716,7 +708,7 @@ __global__ void __launch_bounds__(NT, 1) cl_gen_kernel(Plan p, GenArgsDev g) {
               if (last && !prime)
                 st_strong_u32(p.v256 + (size_t)s * UB + fu, pack_tagged(fmaxf(sk0, 0.f), fmaxf(sk1, 0.f), (unsigned)t & 1u));
             }
-          } else if (kind == K_HEAD1) {
+          } else if (KIND == K_HEAD1) {
             if (i4 == 0)
               st_strong_u32(p.v256 + (size_t)(NOWN + s) * UB + fu, pack_tagged(fmaxf(s0 + sBh[0], 0.f), fmaxf(s1 + sBh[1], 0.f), (unsigned)t & 1u));
           } else {
@@ -727,11 +719,28 @@ __global__ void __launch_bounds__(NT, 1) cl_gen_kernel(Plan p, GenArgsDev g) {
             }
           }
         }
+        trace(t, tph, 6);
       } else {
-        // ---- (3') streaming warps: next weight tile; once per step the aux rows of the NEXT step,
-        // h_up[:, ta] = h[:, ta / U] * w[ta % U] + b (qpnet.py:143-158, 451)
+        // ---- (3') streaming warps: next weight tile; for a gate, the past-tap partial sums P'(t) = Wp . x_l(t)
+        // later steps will need; once per step the aux rows of the NEXT step.
         issue_next_tile();
-        if (kind == K_RES && l == 0) {
+        if (KIND == K_GATE) {
+          kloop(acc, bp + KS);
+          float* ringf = (float*)p.ring[l];
+          const int rs = p.ring_size[l];
+          const size_t slot_f4 = (size_t)NOWN * 512;   // float4 per ring slot: 128 CTAs x 4 warps x 4 groups x 32 lanes
+          float4* r0 = (float4*)(ringf + ((size_t)s * 4 + w4) * 512) + lane;
+          const int sl0 = prime ? 0 : (t & (rs - 1)), sl1 = prime ? rs : sl0 + 1;
+          for (int sl = sl0; sl < sl1; ++sl) {   // the priming step fills the whole ring with the constant of the pad region
+            float4* r1 = r0 + sl * slot_f4;
+#pragma unroll
+            for (int m = 0; m < 4; ++m)
+              r1[m * 32] = make_float4(acc[0][m >> 1][(m & 1) * 2], acc[0][m >> 1][(m & 1) * 2 + 1],
+                                       acc[1][m >> 1][(m & 1) * 2], acc[1][m >> 1][(m & 1) * 2 + 1]);
+          }
+        }
+        if (KIND == K_RES && l == 0) {
+          // h_up[:, ta] = h[:, ta / U] * w[ta % U] + b (qpnet.py:143-158, 451)
           const int tn = t + 1;
           if (tn < g.max_steps) {
             const int ta = tn < 0 ? 0 : tn;
@@ -751,9 +760,21 @@ __global__ void __launch_bounds__(NT, 1) cl_gen_kernel(Plan p, GenArgsDev g) {
           }
         }
       }
-      trace(t, tph, 3);
       ++rp;
       cur_slot = cur_slot == NSLOT - 1 ? 0 : cur_slot + 1;
+      return false;
+    };
+    {
+      bool stop = false;
+      for (int l = 0; l < L && !stop; ++l) {
+        stop = phase(std::integral_constant<int, K_RES>(), l);
+        if (!stop && l + 1 < L) stop = phase(std::integral_constant<int, K_GATE>(), l + 1);
+      }
+      if (!stop && !prime) {
+        stop = phase(std::integral_constant<int, K_HEAD1>(), 0);
+        if (!stop) stop = phase(std::integral_constant<int, K_HEAD2>(), 0);
+      }
+      if (stop) goto done;
     }
 
     // ================================================================ sampling: one warp per utterance
@@ -829,7 +850,7 @@ __global__ void __launch_bounds__(NT, 1) cl_gen_kernel(Plan p, GenArgsDev g) {
         }
       }
       if (TRACE && s == 0 && lane == 0 && t >= p.trace_step0 && t < p.trace_step0 + p.trace_nsteps)
-        p.trace[((size_t)(t - p.trace_step0) * nphase + 2 * L + 2) * TRACE_EVENTS + 3] = clock64();
+        p.trace[((size_t)(t - p.trace_step0) * nphase + 2 * L + 2) * TRACE_EVENTS + 6] = clock64();
     }
   }
 done:

@@ -312,8 +312,38 @@ def test_generator_free_running_vs_reference_goldens(dev, name):
         first = int(neq[0]) if len(neq) else len(ref)
         firsts.append(first)
         print(name, "utt", b, "match rate %.4f first divergence %d / %d" % (float((r == ref).mean()), first, len(ref)))
-    # a structural error diverges at step 0 or 1; arithmetic noise (bf16 + 1-bit epoch tags) later
-    assert min(firsts) >= 3, firsts
+    # Free-running trajectories are chaotic: with near-uniform posteriors a 0.02 logit difference flips the
+    # inverse-CDF draw every ~10 steps, so the first divergence is reported, not asserted.  The per-step
+    # agreement of the sampler is asserted by test_generator_sampled_symbols_under_reference_history.
+
+
+@pytest.mark.parametrize("name", [n for n, c in cases.GENERATE_CASES.items() if c[4] == "sampling"])
+def test_generator_sampled_symbols_under_reference_history(dev, name):
+    """Sample-match under shared pre-drawn uniforms, step by step: feed the reference's own symbols back
+    (so the history is the reference's) and compare the symbol OUR sampler draws at every step with the
+    reference's.  A mismatch is only legitimate when the uniform lies within `tol` of the reference CDF
+    boundary between the two symbols (tol 0.03 = the bf16 logit noise of ~0.02-0.03 mapped onto the CDF)."""
+    g, kw, a, p, x, h, d, n_list, mode, xm, m, uni = _gen_setup(name, dev)
+    B = len(n_list)
+    steps = min(n_list) if kw else 120
+    forced = torch.stack([torch.from_numpy(g[f"{name}/sym{b}"][:steps].astype(np.int64)) for b in range(B)])
+    lg = []
+    with torch.no_grad():
+        orc.generate(a, p, x, h, list(n_list), d, mode="argmax", force=forced, logits_out=lg, max_steps=steps)
+    cdf = torch.softmax(torch.stack(lg, dim=1).double(), dim=-1).cumsum(-1).numpy()      # (B, steps, Q)
+    dd = torch.from_numpy(d).float().to(dev) if xm else d
+    res = m.batch_fast_generate(x, h, [steps] * B, dd, None, "sampling", xm, uniforms=uni, force=forced)
+    tol, total, same = 0.03, 0, 0
+    for b in range(B):                                       # equal lengths retire in input order
+        ours, ref, u = res[b], forced[b].numpy(), uni[b, :steps].numpy().astype(np.float64)
+        for t in np.nonzero(ours != ref)[0]:
+            lo, hi = sorted((int(ours[t]), int(ref[t])))
+            gap = np.abs(cdf[b, t, lo:hi] - u[t]).max()
+            assert gap <= tol, (name, b, int(t), int(ours[t]), int(ref[t]), float(gap))
+        total += steps
+        same += int((ours == ref).sum())
+    print(name, "per-step sample match under the reference history: %.4f (%d / %d)" % (same / total, same, total))
+    assert same / total > 0.85
 
 
 def test_generator_is_deterministic_and_batch_independent(dev):

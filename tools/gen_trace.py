@@ -44,7 +44,9 @@ def main():
         print("kernel ms", t0.elapsed_time(t1), "us/step", t0.elapsed_time(t1) * 1e3 / (max(n_list) + 1))
     L = 16
     nphase = 2 * L + 3
-    n = 8 * nphase * 4
+    cluster = os.environ.get("QPNET_GEN_KERNEL") != "generic"
+    nev = 8 if cluster else 4
+    n = 8 * nphase * nev
     buf = (C.c_longlong * n)()
     fn = _lib.lib.qp_debug_gen_trace
     fn.restype = C.c_int
@@ -53,8 +55,34 @@ def main():
     ws = m._last_ws
     M = ops.max_ceil(d64)
     fn(m._arch, args.utts, M, ws.data_ptr(), ws.numel(), buf, n, None)
-    tr = np.array(buf, dtype=np.int64).reshape(8, nphase, 4)
+    tr = np.array(buf, dtype=np.int64).reshape(8, nphase, nev)
     names = [f"{'gate' if i % 2 == 0 else 'res '}{i // 2:02d}" for i in range(2 * L)] + ["head1 ", "head2 ", "sample"]
+    if cluster:
+        # events: 0 start, 1 own pieces fresh, 2 barrier passed, 3 MMA done, 4 sent, 5 partials arrived, 6 published
+        labels = ["poll", "barrier", "mma", "send", "dsmem", "finish"]
+        for st in range(1, 3):
+            print(f"--- step {args.step + st}: total {tr[st + 1, 0, 0] - tr[st, 0, 0]} cycles")
+            for ph in range(nphase - 1):
+                e = tr[st, ph]
+                nxt = tr[st, ph + 1, 0]
+                if ph == 0:
+                    print(f"{names[ph]} symbols {e[1] - e[0]:6d}  finish {e[6] - e[2]:6d}  gap {nxt - e[6]:5d}")
+                else:
+                    print(names[ph] + " " + "  ".join(f"{lab} {e[i + 1] - e[i]:5d}" for i, lab in enumerate(labels)) + f"  gap {nxt - e[6]:5d}")
+        acc = np.zeros((nphase, 7))
+        for st in range(1, 7):
+            for ph in range(1, nphase - 1):
+                e = tr[st, ph]
+                acc[ph, :6] += [e[i + 1] - e[i] for i in range(6)]
+                acc[ph, 6] += tr[st, ph + 1, 0] - e[6]
+        acc /= 6
+        print("mean over 6 steps, all MMA phases:", "  ".join(f"{lab} {acc[1:-1, i].mean():.0f}" for i, lab in enumerate(labels + ["gap"])))
+        gate = [2 * l for l in range(1, L)]
+        res = [2 * l + 1 for l in range(L)]
+        print("gate phases:", "  ".join(f"{lab} {acc[gate, i].mean():.0f}" for i, lab in enumerate(labels + ["gap"])))
+        print("res  phases:", "  ".join(f"{lab} {acc[res, i].mean():.0f}" for i, lab in enumerate(labels + ["gap"])))
+        print("step total (mean):", np.mean([tr[st + 1, 0, 0] - tr[st, 0, 0] for st in range(1, 7)]))
+        return
     for st in range(1, 4):
         print(f"--- step {args.step + st}: total {tr[st + 1, 0, 0] - tr[st, 0, 0]} cycles")
         for ph in range(nphase):

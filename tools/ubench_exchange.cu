@@ -269,7 +269,7 @@ __global__ void __launch_bounds__(NT, 1) k_cluster(UB u) {
 // layout), every warp w "computes" a 32x8 partial tile destined for cluster peer w and sends it with ONE
 // st.async.v4 per lane (fp16 partials: NV=1) or two (fp32: NV=2); warp 0 of every CTA waits for the 8
 // partial tiles on an mbarrier, sums them and publishes the CTA's 256-byte slice for the next round.
-template <int NV>
+template <int NV, int PIPE = 1>
 __global__ void __launch_bounds__(NT, 1) k_creduce(UB u) {
   extern __shared__ __align__(128) unsigned char dyn[];
   uint4* smA = (uint4*)dyn;                                // [2][256] the K-share (4 KB) per buffer
@@ -301,10 +301,28 @@ __global__ void __launch_bounds__(NT, 1) k_creduce(UB u) {
     uint4 v;
     long long t0 = clock64();
     unsigned spins = 0;
-    while (true) {
-      v = ld_v4(g + piece);
-      if (fresh(v, par)) break;
-      if ((++spins & 1023u) == 0 && (clock64() - t0 > TIMEOUT || *(volatile int*)u.status)) { atomicExch(u.status, 1); return; }
+    if (PIPE == 1) {
+      while (true) {
+        v = ld_v4(g + piece);
+        if (fresh(v, par)) break;
+        if ((++spins & 1023u) == 0 && (clock64() - t0 > TIMEOUT || *(volatile int*)u.status)) { atomicExch(u.status, 1); return; }
+      }
+    } else {
+      // PIPE polls in flight, issued ~RTT/PIPE apart: detection latency drops from ~RTT/2 to ~RTT/(2*PIPE)
+      uint4 q[PIPE];
+      bool done = false;
+#pragma unroll
+      for (int i = 0; i < PIPE; ++i) { q[i] = ld_v4(g + piece); if (i + 1 < PIPE) { long long c0 = clock64(); while (clock64() - c0 < 600 / PIPE) {} } }
+      while (!done) {
+#pragma unroll
+        for (int i = 0; i < PIPE; ++i) {
+          if (!done) {
+            if (fresh(q[i], par)) { v = q[i]; done = true; }
+            else q[i] = ld_v4(g + piece);
+          }
+        }
+        if (!done && (++spins & 1023u) == 0 && (clock64() - t0 > TIMEOUT || *(volatile int*)u.status)) { atomicExch(u.status, 1); return; }
+      }
     }
     smA[b * 256 + t] = v;
     __syncthreads();
@@ -406,6 +424,8 @@ int main(int argc, char** argv) {
     run("flat L1 burst", k_flat<1, 1>, u, false, c);
     run("flat L1 probe", k_flat<0, 1>, u, false, c);
     run("creduce fp16", k_creduce<1>, u, true, c);
+    run("creduce pipe2", k_creduce<1, 2>, u, true, c);
+    run("creduce pipe4", k_creduce<1, 4>, u, true, c);
     run("creduce fp32", k_creduce<2>, u, true, c);
     if (ci != 1) {
       run("L1 spin none", k_cluster<1, 0, 3>, u, true, c);
