@@ -306,7 +306,10 @@ def main():
     tps = ncu_traffic_per_step()
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": (tps * steps_per_launch if tps is not None else None), "peak_source": peak_src,
-                "kernel": "qp::gen_kernel", "us_per_sample_step": kernel_s / steps_per_launch * 1e6,
+                "kernel": "qp::cl::cl_gen_kernel (cluster generator)" if n_utts <= 32 else "qp::gen_kernel (generic)",
+                "us_per_sample_step": kernel_s / steps_per_launch * 1e6,
+                "note": "SURVEY.md 8(d) models the step as weight-bandwidth bound; ncu shows the weights L2-resident and the "
+                        "step bound by the chain of 35 cross-SM exchanges (profiles/r01e_*), so frac is small by construction",
                 "algorithmic_bytes_per_step": ALG_WEIGHT_BYTES + n_utts * ALG_STATE_BYTES}
 
     cpu = None

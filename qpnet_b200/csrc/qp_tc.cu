@@ -130,7 +130,8 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(Args a) {
     const int rr = min(r0 + tid, a.n_rows - 1);
     const uint32_t row_off = (uint32_t)((tid >> 3) * 1024 + (tid & 7) * 128), sw = (uint32_t)(tid & 7);
     const int w0 = min(n0 + tid, a.N - 1), w1 = min(n0 + 128 + tid, a.N - 1);
-    const bool two = a.BN > 128;
+    // a thread only copies the weight rows that exist in this tile (BN may be 32..256 in steps of 32)
+    const bool ldb0 = tid < a.BN, ldb1 = 128 + tid < a.BN;
     int kc = 0, koff = 0;
     for (int s = 0; s < a.nseg; ++s) {
       const Seg sg = a.seg[s];
@@ -146,9 +147,11 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(Args a) {
         const uint32_t sB = sA + BM * 128;
 #pragma unroll
         for (int c = 0; c < 8; ++c) cp_async16(sA + ((c ^ sw) << 4), arow + k0 + c * 8);
+        if (ldb0) {
 #pragma unroll
-        for (int c = 0; c < 8; ++c) cp_async16(sB + ((c ^ sw) << 4), wrow0 + k0 + c * 8);
-        if (two) {
+          for (int c = 0; c < 8; ++c) cp_async16(sB + ((c ^ sw) << 4), wrow0 + k0 + c * 8);
+        }
+        if (ldb1) {
 #pragma unroll
           for (int c = 0; c < 8; ++c) cp_async16(sB + 16 * 1024 + ((c ^ sw) << 4), wrow1 + k0 + c * 8);
         }
