@@ -255,49 +255,6 @@ __global__ void table_kernel(TensorMap tm, Plan p, const float* const* __restric
   T[(2 * Q + sym) * 8 + j] = tc;
 }
 
-// ------------------------------------------------------------------ device helpers
-__device__ __forceinline__ unsigned smem_u32(const void* q) { return (unsigned)__cvta_generic_to_shared(q); }
-__device__ __forceinline__ unsigned mapa(unsigned addr, unsigned rank) {
-  unsigned r;
-  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;\n" : "=r"(r) : "r"(addr), "r"(rank));
-  return r;
-}
-__device__ __forceinline__ unsigned cluster_rank() {
-  unsigned r;
-  asm volatile("mov.u32 %0, %%cluster_ctarank;\n" : "=r"(r));
-  return r;
-}
-__device__ __forceinline__ void cluster_sync() {
-  asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;\n" ::: "memory");
-}
-__device__ __forceinline__ void mbar_init(unsigned bar, unsigned count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(unsigned bar, unsigned bytes) {
-  asm volatile("{\n .reg .b64 st;\n mbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n}\n" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ bool mbar_try(unsigned bar, unsigned parity) {
-  unsigned ok;
-  asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}\n"
-               : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
-  return ok != 0;
-}
-__device__ __forceinline__ void st_async_v4(unsigned dst_cluster_addr, uint4 v, unsigned mbar_cluster_addr) {
-  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1,%2,%3,%4}, [%5];\n"
-               ::"r"(dst_cluster_addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w), "r"(mbar_cluster_addr) : "memory");
-}
-__device__ __forceinline__ bool fresh4(uint4 v, unsigned par) {
-  return (((v.x ^ par) | (v.y ^ par) | (v.z ^ par) | (v.w ^ par)) & 1u) == 0;
-}
-__device__ __forceinline__ unsigned pack_h2(float a, float b) {
-  __half2 h = __floats2half2_rn(a, b);
-  return *(unsigned*)&h;
-}
-__device__ __forceinline__ float2 unpack_h2(unsigned u) {
-  __half2 h = *(__half2*)&u;
-  return __half22float2(h);
-}
-
 struct SmemMap {   // byte offsets into the dynamic shared memory
   int acur, wslot, recv, t0, eo, vaux, haux, hraw, bg, br, bh, bars, abort, total;
 };

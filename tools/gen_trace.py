@@ -16,6 +16,52 @@ import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 
 
+def fold_trace(m, args, d64, L):
+    """folded generator: phases = block 0, fused 1..L-1, final skip, head-1, head-2, sampling; 8 events each:
+    0 start, 1 own pieces fresh, 2 barrier passed, 3 MMA done, 4 sent, 5 x published, 6 gate partials arrived,
+    7 z (or skip / head row) published"""
+    from qpnet_b200 import _lib, ops
+    nphase, nev = L + 4, 14
+    n = 8 * nphase * nev
+    buf = (C.c_longlong * n)()
+    fn = _lib.lib.qp_debug_gen_trace
+    fn.restype = C.c_int
+    fn.argtypes = [C.POINTER(_lib.QpArch), C.c_int32, C.c_int32, C.c_void_p, C.c_size_t, C.POINTER(C.c_longlong),
+                   C.c_int32, C.c_void_p]
+    ws = m._last_ws
+    M = ops.max_ceil(d64)
+    fn(m._arch, args.utts, M, ws.data_ptr(), ws.numel(), buf, n, None)
+    tr = np.array(buf, dtype=np.int64).reshape(8, nphase, nev)
+    names = ["blk0  "] + [f"fuse{j:02d}" for j in range(1, L)] + ["final ", "head1 ", "head2 ", "sample"]
+    labels = ["poll", "barrier", "mma", "send", "resX", "dsmemG", "pubZ"]
+    for st in range(1, 3):
+        print(f"--- step {args.step + st}: total {tr[st + 1, 0, 0] - tr[st, 0, 0]} cycles")
+        for ph in range(nphase - 1):
+            e = tr[st, ph]
+            nxt = tr[st, ph + 1, 0]
+            if ph == 0:
+                print(f"{names[ph]} symbols {e[1] - e[0]:6d}  finish {e[6] - e[2]:6d}  pubX {e[7] - e[6]:5d}  gap {nxt - e[7]:5d}")
+            elif ph < L:
+                print(names[ph] + " " + "  ".join(f"{lab} {e[i + 1] - e[i]:5d}" for i, lab in enumerate(labels)) + f"  gap {nxt - e[7]:5d}"
+                      + f"   | streamer (vs phase start): fresh {e[8] - e[0]:5d} tile {e[9] - e[0]:5d} [barrier {e[2] - e[0]:5d}] sent {e[10] - e[0]:5d} issued {e[12] - e[0]:5d} ringmma {e[13] - e[0]:5d} done {e[11] - e[0]:5d}")
+            elif ph == L:
+                print(f"{names[ph]} poll {e[1] - e[0]:5d}  barrier {e[2] - e[1]:5d}  res+finish {e[7] - e[2]:5d}  gap {nxt - e[7]:5d}")
+            else:
+                print(f"{names[ph]} poll {e[1] - e[0]:5d}  barrier {e[2] - e[1]:5d}  mma {e[3] - e[2]:5d}  send {e[4] - e[3]:5d}  finish {e[7] - e[4]:5d}  gap {nxt - e[7]:5d}")
+    acc = np.zeros((nphase, 8))
+    for st in range(1, 7):
+        for ph in range(1, L):
+            e = tr[st, ph]
+            acc[ph, :7] += [e[i + 1] - e[i] for i in range(7)]
+            acc[ph, 7] += tr[st, ph + 1, 0] - e[7]
+    acc /= 6
+    print("fused phases, mean over 6 steps:", "  ".join(f"{lab} {acc[1:L, i].mean():.0f}" for i, lab in enumerate(labels + ["gap"])),
+          " total/phase %.0f" % acc[1:L].sum(1).mean())
+    tot = [tr[st + 1, 0, 0] - tr[st, 0, 0] for st in range(1, 7)]
+    tail = [tr[st + 1, 0, 0] - tr[st, L, 0] for st in range(1, 7)]
+    print("step total (mean):", np.mean(tot), " of which final+head+sampling:", np.mean(tail))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--utts", type=int, default=32)
@@ -43,8 +89,11 @@ def main():
         torch.cuda.synchronize()
         print("kernel ms", t0.elapsed_time(t1), "us/step", t0.elapsed_time(t1) * 1e3 / (max(n_list) + 1))
     L = 16
+    kind = os.environ.get("QPNET_GEN_KERNEL", "fold")
+    if kind == "fold":
+        return fold_trace(m, args, d64, L)
     nphase = 2 * L + 3
-    cluster = os.environ.get("QPNET_GEN_KERNEL") != "generic"
+    cluster = kind != "generic"
     nev = 8 if cluster else 4
     n = 8 * nphase * nev
     buf = (C.c_longlong * n)()
