@@ -804,6 +804,7 @@ int fd_generate(const QpArch* arch, const float* const* tensors_host, const QpGe
 size_t fd_workspace_bytes(const QpArch* arch, int B, int M);
 bool fd_supported(const QpArch* arch, int B);
 int fd_trace_copy(const QpArch* arch, int B, int M, void* ws, size_t ws_bytes, long long* out_host, int n, cudaStream_t st);
+int fd_stats_copy(const QpArch* arch, int B, int M, void* ws, size_t ws_bytes, long long* out_host, int n, cudaStream_t st);
 static thread_local int g_last_kernel = 0;   // 2: folded cluster generator, 1: cluster generator, 0: generic
 // QPNET_GEN_KERNEL = fold (default) | cluster | generic selects the generator (debugging / A-B timing)
 static int wanted_kernel(const QpArch* arch, int B) {
@@ -936,6 +937,13 @@ int qp_debug_gen_trace(const QpArch* arch, int32_t B, int32_t M, void* ws, size_
   QP_CUDA(cudaMemcpyAsync(out_host, p.trace, sizeof(long long) * n, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
   QP_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
   return n;
+}
+
+// debug only: per-CTA cycle sums of the folded generator (QPNET_GEN_TRACE_STEP)
+int qp_debug_gen_stats(const QpArch* arch, int32_t B, int32_t M, void* ws, size_t ws_bytes, long long* out_host,
+                       int32_t n, void* stream) {
+  if (g_last_kernel != 2) return 0;
+  return fd_stats_copy(arch, B, M, ws, ws_bytes, out_host, n, (cudaStream_t)stream);
 }
 
 }  // extern "C"

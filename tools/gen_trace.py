@@ -57,6 +57,19 @@ def fold_trace(m, args, d64, L):
     acc /= 6
     print("fused phases, mean over 6 steps:", "  ".join(f"{lab} {acc[1:L, i].mean():.0f}" for i, lab in enumerate(labels + ["gap"])),
           " total/phase %.0f" % acc[1:L].sum(1).mean())
+    # per-CTA sums over 256 steps (tid 0): wait = phase start -> barrier, work = barrier -> z published (includes the two
+    # waits for the cluster's partial tiles, dsR / dsG), sym = wait for the fed-back symbol
+    sb = (C.c_longlong * (128 * 8))()
+    fs = _lib.lib.qp_debug_gen_stats
+    fs.restype = C.c_int
+    fs.argtypes = fn.argtypes
+    if fs(m._arch, args.utts, M, ws.data_ptr(), ws.numel(), sb, 128 * 8, None) > 0:
+        stt = np.array(sb, dtype=np.int64).reshape(128, 8)
+        per = stt[:, :5] / (256.0 * np.array([L - 1, L - 1, L - 1, L - 1, 1]))
+        print("per-CTA mean cycles per fused phase: wait / work / dsR / dsG ; symbol wait per step ; smid")
+        for c in range(128):
+            print(f"cta {c:3d} rank {c % 4} smid {stt[c, 5]:3d}: wait {per[c, 0]:6.0f} work {per[c, 1]:6.0f} dsR {per[c, 2]:6.0f} dsG {per[c, 3]:6.0f} sym {per[c, 4]:6.0f}")
+        print("by rank: " + "  ".join(f"r{r}: wait {per[r::4, 0].mean():.0f} work {per[r::4, 1].mean():.0f} dsR {per[r::4, 2].mean():.0f} dsG {per[r::4, 3].mean():.0f}" for r in range(4)))
     tot = [tr[st + 1, 0, 0] - tr[st, 0, 0] for st in range(1, 7)]
     tail = [tr[st + 1, 0, 0] - tr[st, L, 0] for st in range(1, 7)]
     print("step total (mean):", np.mean(tot), " of which final+head+sampling:", np.mean(tail))
