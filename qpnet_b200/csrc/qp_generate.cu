@@ -805,13 +805,20 @@ size_t fd_workspace_bytes(const QpArch* arch, int B, int M);
 bool fd_supported(const QpArch* arch, int B);
 int fd_trace_copy(const QpArch* arch, int B, int M, void* ws, size_t ws_bytes, long long* out_host, int n, cudaStream_t st);
 int fd_stats_copy(const QpArch* arch, int B, int M, void* ws, size_t ws_bytes, long long* out_host, int n, cudaStream_t st);
-static thread_local int g_last_kernel = 0;   // 2: folded cluster generator, 1: cluster generator, 0: generic
-// QPNET_GEN_KERNEL = fold (default) | cluster | generic selects the generator (debugging / A-B timing)
+int f2_generate(const QpArch* arch, const float* const* tensors_host, const QpGenerateArgs* a, void* ws, size_t ws_bytes,
+                cudaStream_t st);
+size_t f2_workspace_bytes(const QpArch* arch, int B, int M);
+bool f2_supported(const QpArch* arch, int B);
+int f2_trace_copy(const QpArch* arch, int B, int M, void* ws, size_t ws_bytes, long long* out_host, int n, cudaStream_t st);
+static thread_local int g_last_kernel = 0;   // 3: two-level folded, 2: folded, 1: cluster generator, 0: generic
+// QPNET_GEN_KERNEL = fold2 (default) | fold | cluster | generic selects the generator (debugging / A-B timing)
 static int wanted_kernel(const QpArch* arch, int B) {
   const char* e = getenv("QPNET_GEN_KERNEL");
-  int want = 2;
+  int want = 3;
   if (e && strcmp(e, "generic") == 0) want = 0;
   else if (e && strcmp(e, "cluster") == 0) want = 1;
+  else if (e && strcmp(e, "fold") == 0) want = 2;
+  if (want == 3 && !f2_supported(arch, B)) want = 2;
   if (want == 2 && !fd_supported(arch, B)) want = 1;
   if (want == 1 && !cl_supported(arch, B)) want = 0;
   return want;
@@ -850,6 +857,7 @@ size_t qp_generate_workspace_bytes(const QpArch* arch, int32_t B, int32_t M) {
   size_t n = make_gen_plan(arch, B, 1, M, nullptr, 0, &p);
   if (cl_supported(arch, B)) n = std::max(n, cl_workspace_bytes(arch, B, M));
   if (fd_supported(arch, B)) n = std::max(n, fd_workspace_bytes(arch, B, M));
+  if (f2_supported(arch, B)) n = std::max(n, f2_workspace_bytes(arch, B, M));
   return n;
 }
 
@@ -862,6 +870,12 @@ int qp_generate(const QpArch* arch, const float* const* tensors_host, const QpGe
   cudaStream_t st = (cudaStream_t)stream;
   g_last_kernel = 0;
   int want = wanted_kernel(arch, a->B);
+  if (want == 3) {
+    int r = f2_generate(arch, tensors_host, a, ws, ws_bytes, st);
+    if (r != 1) { g_last_kernel = 3; return r; }   // 1: the clusters cannot be co-resident here -> next kernel
+    reset_launch_count();
+    want = fd_supported(arch, a->B) ? 2 : 1;
+  }
   if (want == 2) {
     int r = fd_generate(arch, tensors_host, a, ws, ws_bytes, st);
     if (r != 1) { g_last_kernel = 2; return r; }   // 1: the clusters cannot be co-resident here -> next kernel
@@ -928,6 +942,7 @@ int qp_workspace_status(const void* ws, void* stream) {
 // debug only (not part of the public header): copy the per-phase clock64 trace of CTA 0
 int qp_debug_gen_trace(const QpArch* arch, int32_t B, int32_t M, void* ws, size_t ws_bytes, long long* out_host,
                        int32_t n, void* stream) {
+  if (g_last_kernel == 3) return f2_trace_copy(arch, B, M, ws, ws_bytes, out_host, n, (cudaStream_t)stream);
   if (g_last_kernel == 2) return fd_trace_copy(arch, B, M, ws, ws_bytes, out_host, n, (cudaStream_t)stream);
   if (g_last_kernel == 1) return cl_trace_copy(arch, B, M, ws, ws_bytes, out_host, n, (cudaStream_t)stream);
   GenPlan p;
