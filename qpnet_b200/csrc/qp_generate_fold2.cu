@@ -12,9 +12,11 @@
 // The bracket E_j (plus the past tap P_j(t-k) = Wp_j x_j(t-k)) only needs data that was exchanged one phase EARLIER, so
 // phase j-1 computes it after its own critical work ("late part") and ships it to the owners as partial rows.  A phase j
 // is then
-//   critical : poll z_{j-1} -> G_j z_{j-1} -> cluster reduction -> + E_j + aux + bias -> z_j = sigmoid * tanh -> publish
-//   late     : res/skip rows R_{j-1} z_{j-1} -> x_j published (consumed two phases later); poll x_{j-1};
-//              E_{j+1} = P_{j+1}(t-k) + H_{j+1} z_{j-1} + Wc_{j+1} x_{j-1} -> owners;  ring rows P_{j-1}(t) = Wp_{j-1} x_{j-1}
+//   warps 0-3 : poll z_{j-1} -> (H_j z_{j-2} kept from the last phase) + G_j z_{j-1} -> cluster reduction -> + E_j + aux
+//               + bias -> z_j = sigmoid * tanh -> publish; while the partial tiles travel: R,K_{j-1} z_{j-1} and H_{j+1} z_{j-1}
+//   warps 4-7 : x_{j-1} (published one phase ago) -> E_{j+1} = P_{j+1}(t-k) + Wc_{j+1} x_{j-1} -> owners; ring rows
+//               P_{j-1}(t) = Wp_{j-1} x_{j-1}; weight / past-tile fetch; residual + skip state: x_j published
+// The two halves of a CTA run their own loops and never meet at a CTA-wide barrier inside the time loop.
 // Blocks 1 and 2 reach the causal layer x_0, a function of two symbols: Wc_1 x_0 and Wc_2 x_0 are table lookups.
 // Block 0 is three table lookups as before.  A step is block 0, 15 fused phases, the final skip phase, head-1, head-2
 // and sampling: 20 exchanges, each carrying one vector and one cluster reduction on its critical path.
@@ -48,23 +50,23 @@ constexpr int KH = S / CL;                   // 64: K-share of a 256-vector
 constexpr int NR = 8 * CL;                   // 32 rows per cluster tile: 8 per owner rank
 constexpr int NPART = 8;                     // partial tiles an owner receives: CL ranks x 2 K-halves
 constexpr int PA = KS + 8;                   // activation tile pitch
-constexpr int PT = 3 * KS + 8;               // top sub-tile pitch: [G_j | H_{j+1} | Wc_{j+1}]
-constexpr int PB = 2 * KS + 8;               // bottom sub-tile pitch: [R,K_{j-1} | Wp_{j-1}]
+constexpr int PT2 = 2 * KS + 8;              // finisher tile, top part pitch: [G_j | H_{j+1}]
+constexpr int PS = KS + 8;                   // pitch of the single-block parts: R,K_{j-1} | Wc_{j+1} | Wp_{j-1}
 constexpr int PWH = KH + 8;                  // head tile pitch
 constexpr int PH = AP + 8;                   // aux tile pitch
 constexpr int HR = 40;                       // Hraw pitch (floats)
-constexpr int TOP_E = NR * PT, BOT_E = NR * PB;      // elements
-constexpr int TILE_E = TOP_E + BOT_E;
-constexpr int TILE_B = TILE_E * 2;           // 41,984 bytes, one bulk copy
+constexpr int FT_TOP = NR * PT2;                     // elements
+constexpr int FT_E = FT_TOP + NR * PS, FT_B = FT_E * 2;   // finisher tile [G|H ; R,K]: 25,600 bytes, one bulk copy
+constexpr int ST_E = 2 * NR * PS, ST_B = ST_E * 2;        // streamer tile [Wc ; Wp]: 17,408 bytes, one bulk copy
 constexpr int HTILE_E = NR * PWH, HTILE_B = HTILE_E * 2;   // head tile (padded pitch in global too)
 constexpr int PASTB = 4 * 4 * 32 * 16;       // past-tap partial tiles that travel with a fused tile (4 warps x 4 groups x 32 lanes x float4)
-constexpr int WSLOT = TILE_B + PASTB;
+constexpr int SSLOT = ST_B + PASTB;          // streamer slot: tile + the past-tap tiles that travel with it
 constexpr int NSLOT = 2;
 constexpr int MAXL = 16;
 constexpr int RINGF = 4 * 512;               // floats per CTA per ring slot
-// trace events (CTA 0, thread 0): 0 start, 1 own z pieces fresh, 2 barrier A passed, 3 gate MMA done, 4 gate partials sent,
-// 5 gate + E partials arrived, 6 z published, 7 x published, 8 barrier B passed, 9 late part done;
-// thread 128 (streaming warp 4): 10 barrier A + res tiles sent, 11 next tile issued, 12 late part done
+// trace events, CTA 0.  thread 0 (finisher): 0 start, 1 z pieces fresh, 2 finisher barrier passed, 3 gate MMA done, 4 gate
+// partials sent, 5 gate + E partials arrived, 6 z published, 7 phase done.  thread 128 (streamer): 8 x staged + tile landed,
+// 9 E sent, 10 ring stored, 11 x published, 12 next tile requested
 constexpr int TRACE_EVENTS = 13;
 enum { K_FUSED = 0, K_FINAL = 1, K_HEAD1 = 2, K_HEAD2 = 3 };
 
@@ -73,7 +75,8 @@ struct Plan {
   int dil[MAXL], depth[MAXL], ring_size[MAXL];
   int32_t* status;
   const float** tab;
-  __nv_bfloat16* Wf;      // [L][NOWN][TILE_E]   tile j-1 feeds phase j = 1..L (layout in pack_kernel)
+  __nv_bfloat16* Wf;      // [L][NOWN][FT_E]   finisher tile j-1 feeds phase j = 1..L (layout in pack_kernel)
+  __nv_bfloat16* Ws;      // [L][NOWN][ST_E]   streamer tile
   __nv_bfloat16* Whead;   // [2][NOWN][HTILE_E]  rows per owner rank: h0, h1, 0 ...
   __nv_bfloat16* Vaux;    // [L][NOWN][8][AP]
   float* bgate;           // [L][NOWN][8]
@@ -107,7 +110,8 @@ size_t make_plan(const QpArch* a, int B, int F, int M, void* base, size_t cap, P
   Arena ar(base, cap);
   p->status = ar.take<int32_t>(64);
   p->tab = ar.take<const float*>(tensor_map(a).count());
-  p->Wf = ar.take<__nv_bfloat16>((size_t)L * NOWN * TILE_E);
+  p->Wf = ar.take<__nv_bfloat16>((size_t)L * NOWN * FT_E);
+  p->Ws = ar.take<__nv_bfloat16>((size_t)L * NOWN * ST_E);
   p->Whead = ar.take<__nv_bfloat16>((size_t)2 * NOWN * HTILE_E);
   p->Vaux = ar.take<__nv_bfloat16>((size_t)L * NOWN * 8 * AP);
   p->bgate = ar.take<float>((size_t)L * NOWN * 8);
@@ -138,56 +142,70 @@ size_t make_plan(const QpArch* a, int B, int F, int M, void* base, size_t cap, P
 }
 
 // ------------------------------------------------------------------ weight packing
-// Tile j-1 (phase j, 1 <= j <= L) of CTA s = 4c + r; o = owner 4c + row / 8, j8 = row % 8; column kk of a 128-wide
+// Tiles j-1 (phase j, 1 <= j <= L) of CTA s = 4c + r; o = owner 4c + row / 8, j8 = row % 8; column kk of a 128-wide
 // block is input channel KS*r + kk.  Gate row j8: g = j8 & 1 (sigmoid / tanh), channel 4o + (j8 >> 1).
-//   top    (32 rows, pitch PT): [0,KS)     G_j = Wc_j R_{j-1}         (fold_kernel, 1 <= j <= L-1)
-//                               [KS,2KS)   H_{j+1} = Wc_{j+1} R_{j-1} (fold_kernel, 1 <= j <= L-2)
-//                               [2KS,3KS)  Wc_{j+1}                   (2 <= j <= L-2; block 2 reaches x_0 through a table)
-//   bottom (32 rows, pitch PB): [0,KS)     j8 < 4: R_{j-1} row 4o+j8 (zero for the dead last projection, C7); j8 = 4,5: K_{j-1} row 2o+j8-4
-//                               [KS,2KS)   Wp_{j-1} gate row j8 (past tap of block j-1; zero for block 0, which uses tables)
+//   finisher tile, top (32 rows, pitch PT2): [0,KS)    G_j = Wc_j R_{j-1}         (fold_kernel, 1 <= j <= L-1)
+//                                            [KS,2KS)  H_{j+1} = Wc_{j+1} R_{j-1} (fold_kernel, 1 <= j <= L-2)
+//   finisher tile, bottom (32 rows, pitch PS): j8 < 4: R_{j-1} row 4o+j8 (zero for the dead last projection, C7); j8 = 4,5: K_{j-1} row 2o+j8-4
+//   streamer tile, first  (32 rows, pitch PS): Wc_{j+1}   (2 <= j <= L-2; block 2 reaches x_0 through a table)
+//   streamer tile, second (32 rows, pitch PS): Wp_{j-1} gate row j8 (past tap of block j-1; zero for block 0, which uses tables)
 // Everything not listed is zero (the workspace arena is not cleared, so pack_kernel writes every element).
 __global__ void pack_kernel(TensorMap tm, Plan p, const float* const* __restrict__ tab) {
   const int L = p.L, A = p.A, nF = p.nF;
-  const size_t n_wf = (size_t)L * NOWN * TILE_E, n_wh = (size_t)2 * NOWN * HTILE_E;
+  const size_t n_wf = (size_t)L * NOWN * FT_E, n_ws = (size_t)L * NOWN * ST_E, n_wh = (size_t)2 * NOWN * HTILE_E;
   const size_t n_va = (size_t)L * NOWN * 8 * AP, n_b = (size_t)L * NOWN * 8, n_bh = (size_t)2 * NOWN * 8;
   const size_t n_eo = (size_t)NOWN * 2 * Q * 4;
-  const size_t total = n_wf + n_wh + n_va + 2 * n_b + n_bh + n_eo;
+  const size_t total = n_wf + n_ws + n_wh + n_va + 2 * n_b + n_bh + n_eo;
   for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
     size_t k = idx;
     if (k < n_wf) {
-      int e = (int)(k % TILE_E); size_t q = k / TILE_E;
+      int e = (int)(k % FT_E); size_t q = k / FT_E;
       int s = (int)(q % NOWN), j = (int)(q / NOWN) + 1;
-      const bool top = e < TOP_E;
-      int row, cc;
-      if (top) { row = e / PT; cc = e % PT; } else { row = (e - TOP_E) / PB; cc = (e - TOP_E) % PB; }
-      const int blk = cc / KS, kk = cc % KS;
+      if (e < FT_TOP) {
+        if (e % PT2 < 2 * KS) continue;              // G_j / H_{j+1}: fold_kernel writes these (zeros where undefined)
+        p.Wf[k] = __float2bfloat16(0.f);
+        continue;
+      }
+      const int row = (e - FT_TOP) / PS, kk = (e - FT_TOP) % PS;
       int r = s % CL, o = (s / CL) * CL + row / 8, j8 = row % 8;
       int col = KS * r + kk;
-      int g = j8 & 1, ch = 4 * o + (j8 >> 1);
+      const int l = j - 1;
       float v = 0.f;
-      if (top) {
-        if (blk < 2 && cc < 2 * KS) continue;        // G_j / H_{j+1}: fold_kernel writes these (zeros where undefined)
-        if (blk == 2 && cc < 3 * KS && j >= 2 && j <= L - 2) {
-          const int gl = j + 1;
-          v = gl < nF ? tab[tm.dilF_w(g, gl)][((size_t)ch * C + col) * 2 + 1] : tab[tm.dilA_wC(g, gl - nF)][(size_t)ch * C + col];
-        }
-      } else {
-        const int l = j - 1;
-        if (blk == 0) {
-          if (j8 < 4) {
-            if (l < L - 1) { int c2 = 4 * o + j8; v = l < nF ? tab[tm.resF_w(l)][(size_t)c2 * C + col] : tab[tm.resA_w(l - nF)][(size_t)c2 * C + col]; }
-          } else if (j8 < 6) {
-            int sr = 2 * o + j8 - 4;
-            v = l < nF ? tab[tm.skipF_w(l)][(size_t)sr * C + col] : tab[tm.skipA_w(l - nF)][(size_t)sr * C + col];
-          }
-        } else if (blk == 1 && cc < 2 * KS && l >= 1) {
-          v = l < nF ? tab[tm.dilF_w(g, l)][((size_t)ch * C + col) * 2 + 0] : tab[tm.dilA_wP(g, l - nF)][(size_t)ch * C + col];
+      if (kk < KS) {
+        if (j8 < 4) {
+          if (l < L - 1) { int c2 = 4 * o + j8; v = l < nF ? tab[tm.resF_w(l)][(size_t)c2 * C + col] : tab[tm.resA_w(l - nF)][(size_t)c2 * C + col]; }
+        } else if (j8 < 6) {
+          int sr = 2 * o + j8 - 4;
+          v = l < nF ? tab[tm.skipF_w(l)][(size_t)sr * C + col] : tab[tm.skipA_w(l - nF)][(size_t)sr * C + col];
         }
       }
       p.Wf[k] = __float2bfloat16(v);
       continue;
     }
     k -= n_wf;
+    if (k < n_ws) {
+      int e = (int)(k % ST_E); size_t q = k / ST_E;
+      int s = (int)(q % NOWN), j = (int)(q / NOWN) + 1;
+      const int blk = e / (NR * PS), row = (e % (NR * PS)) / PS, kk = e % PS;
+      int r = s % CL, o = (s / CL) * CL + row / 8, j8 = row % 8;
+      int col = KS * r + kk;
+      int g = j8 & 1, ch = 4 * o + (j8 >> 1);
+      float v = 0.f;
+      if (kk < KS) {
+        if (blk == 0) {
+          if (j >= 2 && j <= L - 2) {
+            const int gl = j + 1;
+            v = gl < nF ? tab[tm.dilF_w(g, gl)][((size_t)ch * C + col) * 2 + 1] : tab[tm.dilA_wC(g, gl - nF)][(size_t)ch * C + col];
+          }
+        } else {
+          const int l = j - 1;
+          if (l >= 1) v = l < nF ? tab[tm.dilF_w(g, l)][((size_t)ch * C + col) * 2 + 0] : tab[tm.dilA_wP(g, l - nF)][(size_t)ch * C + col];
+        }
+      }
+      p.Ws[k] = __float2bfloat16(v);
+      continue;
+    }
+    k -= n_ws;
     if (k < n_wh) {
       int cc = (int)(k % PWH); size_t q = k / PWH;
       int row = (int)(q % NR); q /= NR;
@@ -277,7 +295,7 @@ __global__ void __launch_bounds__(256) fold_kernel(TensorMap tm, Plan p, const f
     for (int e = tid; e < 8 * C; e += 256) {
       int j8 = e / C, k = e % C;
       int sdst = c4 * CL + k / KS;
-      p.Wf[((size_t)ti * NOWN + sdst) * TILE_E + (8 * orank + j8) * PT + which * KS + (k % KS)] = __float2bfloat16(0.f);
+      p.Wf[((size_t)ti * NOWN + sdst) * FT_E + (8 * orank + j8) * PT2 + which * KS + (k % KS)] = __float2bfloat16(0.f);
     }
     return;
   }
@@ -303,9 +321,9 @@ __global__ void __launch_bounds__(256) fold_kernel(TensorMap tm, Plan p, const f
   for (int hh = 0; hh < 2; ++hh) {
     const int k = tid + 256 * hh;
     const int sdst = c4 * CL + k / KS;
-    __nv_bfloat16* dst = p.Wf + ((size_t)ti * NOWN + sdst) * TILE_E + (8 * orank) * PT + which * KS + (k % KS);
+    __nv_bfloat16* dst = p.Wf + ((size_t)ti * NOWN + sdst) * FT_E + (8 * orank) * PT2 + which * KS + (k % KS);
 #pragma unroll
-    for (int j8 = 0; j8 < 8; ++j8) dst[(size_t)j8 * PT] = __float2bfloat16(acc[j8][hh]);
+    for (int j8 = 0; j8 < 8; ++j8) dst[(size_t)j8 * PT2] = __float2bfloat16(acc[j8][hh]);
   }
   if (tid < 8) {
     const float* rb = rl < nF ? tab[tm.resF_b(rl)] : tab[tm.resA_b(rl - nF)];
@@ -359,7 +377,7 @@ __device__ __forceinline__ void bulk_g2s(unsigned dst, const void* src, unsigned
 }
 
 struct SmemMap {   // byte offsets into the dynamic shared memory
-  int az, ax, wslot, recvg, recvr, recve, t0, vaux, haux, hraw, bg, br, bh, sym, bars, abort, total;
+  int az, ax, wf, ws, whead, recvg, recvr, recve, t0, vaux, haux, hraw, bg, br, bh, sym, bars, total;
 };
 __host__ __device__ inline SmemMap smem_map(int L) {
   SmemMap m;
@@ -367,10 +385,12 @@ __host__ __device__ inline SmemMap smem_map(int L) {
   m.az = o; o += 2 * UB * PA * 2;
   m.ax = o; o += UB * PA * 2;
   o = (o + 127) & ~127;
-  m.wslot = o; o += NSLOT * WSLOT;
+  m.wf = o; o += NSLOT * FT_B;
+  m.ws = o; o += NSLOT * SSLOT;
+  m.whead = o; o += 2 * HTILE_B;
   m.recvg = o; o += 2 * NPART * 32 * 16;
-  m.recvr = o; o += 2 * NPART * 32 * 16;
-  m.recve = o; o += 2 * NPART * 32 * 16;
+  m.recvr = o; o += 3 * NPART * 32 * 16;
+  m.recve = o; o += 3 * NPART * 32 * 16;
   m.t0 = o; o += 3 * Q * 8 * 4;
   m.vaux = o; o += L * 8 * PH * 2;
   m.haux = o; o += 2 * UB * PH * 2;
@@ -380,12 +400,18 @@ __host__ __device__ inline SmemMap smem_map(int L) {
   m.bh = o; o += 2 * 8 * 4;
   m.sym = o; o += UB * 4;
   o = (o + 15) & ~15;
-  m.bars = o; o += 8 * 8;     // [0,1] res / head partials, [2,3] gate partials, [4,5] E partials, [6,7] weight slots
-  m.abort = o; o += 16;
+  m.bars = o; o += 12 * 8;     // [0,1] gate / head partials, [2,3,4] res / skip partials, [5,6,7] E partials, [8,9] finisher tiles, [10,11] streamer tiles
   m.total = o;
   return m;
 }
 
+// Role-split persistent kernel.  Warps 0-3 ("finishers") and warps 4-7 ("streamers") run their own loops over the
+// same schedule and only meet through mbarriers (partial tiles, weight slots), the exchange vectors in global memory
+// and one named barrier per step (the fed-back symbols).  There is no CTA-wide barrier inside the time loop.
+//   finishers : every tile that contracts z_{j-1}, the gate non-linearity, z_j published, the two head projections
+//   streamers : every tile that contracts x_{j-1}, the fp32 residual / skip state, x_j published, the past-tap rings,
+//               weight / past-tile fetches, the aux tile, sampling (warp 7 of CTA u < B)
+// A lost exchange word fires the watchdog, which records QP_ETIMEOUT and traps (a role cannot unwind the other one).
 template <bool TRACE>
 __global__ void __launch_bounds__(NT, 1) f2_gen_kernel(Plan p, GenArgsDev g) {
   extern __shared__ __align__(128) unsigned char smem[];
@@ -393,7 +419,9 @@ __global__ void __launch_bounds__(NT, 1) f2_gen_kernel(Plan p, GenArgsDev g) {
   const SmemMap sm = smem_map(L);
   __nv_bfloat16* const sAz = (__nv_bfloat16*)(smem + sm.az);
   __nv_bfloat16* const sAx = (__nv_bfloat16*)(smem + sm.ax);
-  unsigned char* const sW = smem + sm.wslot;
+  unsigned char* const sWF = smem + sm.wf;
+  unsigned char* const sWS = smem + sm.ws;
+  const __nv_bfloat16* const sWh = (const __nv_bfloat16*)(smem + sm.whead);
   uint4* const sRecvG = (uint4*)(smem + sm.recvg);
   uint4* const sRecvR = (uint4*)(smem + sm.recvr);
   uint4* const sRecvE = (uint4*)(smem + sm.recve);
@@ -406,7 +434,7 @@ __global__ void __launch_bounds__(NT, 1) f2_gen_kernel(Plan p, GenArgsDev g) {
   float* const sBh = (float*)(smem + sm.bh);
   int* const sSym = (int*)(smem + sm.sym);
   unsigned long long* const sBars = (unsigned long long*)(smem + sm.bars);
-  volatile int* const sAbort = (volatile int*)(smem + sm.abort);
+  const unsigned barG0 = smem_u32(&sBars[0]), barR0 = smem_u32(&sBars[2]), barE0 = smem_u32(&sBars[5]), barTF0 = smem_u32(&sBars[8]), barTS0 = smem_u32(&sBars[10]);
 
   const int s = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const unsigned rank = cluster_rank();
@@ -414,12 +442,10 @@ __global__ void __launch_bounds__(NT, 1) f2_gen_kernel(Plan p, GenArgsDev g) {
   const int half = Q / 2;
   const int nphase = L + 4;
   const long long ldd = (long long)p.F * U;
-  // roles: all 8 warps poll; warps 0-3 ("finishers") run the gate tiles, finish the owned rows (warp m: utterances
-  // q4 + 8m) and run the E tiles of the next gate; warps 4-7 ("streamers") run the res/skip and ring tiles, fetch
-  // weights / past tiles and build the aux tile; warp 7 of CTA u < B samples utterance u.
   const bool finisher = warp < 4;
-  const int fu = q4 + 8 * warp;                 // utterance this thread finishes (finisher warps)
-  const int t128 = tid - 128;                   // index inside the streaming warps
+  const int w4 = warp & 3, ntp = w4 & 1, kh = w4 >> 1;   // tile of this warp: rows 16*ntp.., K-half kh of the 128-share
+  const int fu = q4 + 8 * w4;                   // utterance this thread finishes (gate rows: finishers, res / skip rows: streamers)
+  const int t128 = tid & 127;                   // index inside the role
 
   // ---- one-time staging ---------------------------------------------------------------
   for (int e = tid; e < sm.total / 16; e += NT) ((uint4*)smem)[e] = make_uint4(0, 0, 0, 0);
@@ -429,13 +455,15 @@ __global__ void __launch_bounds__(NT, 1) f2_gen_kernel(Plan p, GenArgsDev g) {
     int l = e / (8 * AP), rem = e - l * 8 * AP, j = rem / AP, a = rem - j * AP;
     sVaux[(l * 8 + j) * PH + a] = p.Vaux[((size_t)l * NOWN + s) * 8 * AP + rem];
   }
+  for (int e = tid; e < 2 * HTILE_E; e += NT)   // both head tiles stay resident
+    ((__nv_bfloat16*)(smem + sm.whead))[e] = p.Whead[((size_t)(e / HTILE_E) * NOWN + s) * HTILE_E + (e % HTILE_E)];
   for (int e = tid; e < L * 8; e += NT) {
     sBg[e] = p.bgate[((size_t)(e >> 3) * NOWN + s) * 8 + (e & 7)];
     sBr[e] = p.bres[((size_t)(e >> 3) * NOWN + s) * 8 + (e & 7)];
   }
   if (tid < 16) sBh[tid] = p.bhead[((size_t)(tid >> 3) * NOWN + s) * 8 + (tid & 7)];
   if (tid == 0) {
-    for (int i = 0; i < 8; ++i) mbar_init(smem_u32(&sBars[i]), 1);
+    for (int i = 0; i < 12; ++i) mbar_init(smem_u32(&sBars[i]), 1);
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
   }
   // aux rows of the priming region: h_up[:, 0] (replicate pad, qpnet.py:359), both slots
@@ -457,49 +485,365 @@ __global__ void __launch_bounds__(NT, 1) f2_gen_kernel(Plan p, GenArgsDev g) {
   __syncthreads();
   cluster_sync();
 
-  auto trace = [&](int t, int phase, int ev) {
-    if (TRACE && s == 0 && tid == 0 && t >= p.trace_step0 && t < p.trace_step0 + p.trace_nsteps)
-      p.trace[((size_t)(t - p.trace_step0) * nphase + phase) * TRACE_EVENTS + ev] = clock64();
-  };
-  auto trace_s = [&](int t, int phase, int ev) {   // streaming warp 4
-    if (TRACE && s == 0 && tid == 128 && t >= p.trace_step0 && t < p.trace_step0 + p.trace_nsteps)
+  auto trace = [&](int t, int phase, int ev) {   // thread 0 (finisher) events 0-7, thread 128 (streamer) events 8-12
+    if (TRACE && s == 0 && t128 == 0 && t >= p.trace_step0 && t < p.trace_step0 + p.trace_nsteps)
       p.trace[((size_t)(t - p.trace_step0) * nphase + phase) * TRACE_EVENTS + ev] = clock64();
   };
 
-  auto spin_check = [&](unsigned& spins, long long& t0) -> bool {
-    if ((++spins & 1023u) != 0) return false;
-    if (t0 == 0) t0 = clock64();
-    if (*((volatile int32_t*)p.status) != 0) return true;
-    if (clock64() - t0 > GEN_TIMEOUT_CYCLES) { atomicExch(p.status, QP_ETIMEOUT); return true; }
-    return false;
-  };
-  auto mbar_wait = [&](unsigned bar, unsigned parity) -> bool {   // false when the watchdog fired
-    unsigned spins = 0; long long t0 = 0;
-    while (!mbar_try(bar, parity)) {
-      if (spin_check(spins, t0)) return false;
+  // the watchdog: a word that never arrives is a bug, not a schedule; record it and stop the grid
+  auto spin_check = [&](unsigned& spins, long long& t0) {
+    if ((++spins & 1023u) != 0) return;
+    if (t0 == 0) { t0 = clock64(); return; }
+    if (*((volatile int32_t*)p.status) != 0 || clock64() - t0 > GEN_TIMEOUT_CYCLES) {
+      atomicExch(p.status, QP_ETIMEOUT);
+      __threadfence_system();
+      __trap();
     }
-    return true;
+  };
+  auto mbar_wait = [&](unsigned bar, unsigned parity) {
+    unsigned spins = 0; long long t0 = 0;
+    while (!mbar_try(bar, parity)) spin_check(spins, t0);
   };
 
-  // ---- weight tile stream (streaming warps): one tile per MMA phase, two slots, prefetch distance 1: the tile of
-  // phase n+1 is requested right after barrier A of phase n (its slot was last read in the late part of phase n-1).
-  // Per step: tiles 0..L-1 = fused phases 1..L (the last one is the final skip phase), then head-1, head-2 (not in the
-  // priming passes).  Tile n completes phase (n / 2) & 1 of the mbarrier of slot n & 1.  A fused tile also carries the
-  // past-tap partial tiles its LATE part needs: block j+1 of the same step (j <= L-2), or block 1 of the next step (j == L).
-  int pf_t = -L, pf_i = 0, pf_slot = 0;   // cursor of the next tile to fetch
-  auto issue_next_tile = [&]() {
-    if (pf_t < g.max_steps) {
-      unsigned char* dst = sW + pf_slot * WSLOT;
-      const unsigned bar = smem_u32(&sBars[6 + pf_slot]);
-      if (pf_i < L) {
+  // ---- shared tile helpers ---------------------------------------------------------------
+  const int lrow = (lane & 15) * PA + (lane >> 4) * 8;
+  // B operand through ldmatrix.x4: lanes 0-7 rows 0-7 k lo, 8-15 rows 0-7 k hi, 16-23 rows 8-15 k lo, 24-31 rows 8-15 k hi
+  const int brow = 16 * ntp + (lane & 7) + ((lane >> 4) << 3), bcol = ((lane >> 3) & 1) * 8;
+  // 32 utterances x 16 rows over NK k-steps of 16: 2 x 2 register blocking
+  auto kloop = [&](auto nk, float (&acc)[2][2][4], const __nv_bfloat16* aq, const __nv_bfloat16* bq) {
+    constexpr int NK = decltype(nk)::value;
+#pragma unroll
+    for (int ks = 0; ks < NK; ++ks) {
+      unsigned b0, b1, b2, b3, a0, a1, a2, a3, c0, c1, c2, c3;
+      ldmatrix_x4(b0, b1, b2, b3, bq + ks * 16);   // rows 0-7 (k lo, k hi), rows 8-15 (k lo, k hi)
+      ldmatrix_x4(a0, a1, a2, a3, aq + ks * 16);
+      ldmatrix_x4(c0, c1, c2, c3, aq + 16 * PA + ks * 16);
+      mma_bf16(acc[0][0], a0, a1, a2, a3, b0, b1);
+      mma_bf16(acc[1][0], a0, a1, a2, a3, b2, b3);
+      mma_bf16(acc[0][1], c0, c1, c2, c3, b0, b1);
+      mma_bf16(acc[1][1], c0, c1, c2, c3, b2, b3);
+    }
+  };
+  using K4 = std::integral_constant<int, KS / 32>;   // a 128-share split over two K-halves: 4 k-steps
+  using K2 = std::integral_constant<int, KH / 32>;   // a 64-share: 2 k-steps
+  auto zero = [&](float (&acc)[2][2][4]) {
+#pragma unroll
+    for (int a_ = 0; a_ < 2; ++a_)
+#pragma unroll
+      for (int b_ = 0; b_ < 2; ++b_) acc[a_][b_][0] = acc[a_][b_][1] = acc[a_][b_][2] = acc[a_][b_][3] = 0.f;
+  };
+  // partial tiles -> owner ranks: utterances (q4, q4+8, q4+16, q4+24) x rows (2*i4, 2*i4+1), fp16
+  auto send = [&](const float (&acc)[2][2][4], uint4* recv, int buf, unsigned bar) {
+#pragma unroll
+    for (int a_ = 0; a_ < 2; ++a_) {
+      const int nt = 2 * ntp + a_;
+      uint4 pk = make_uint4(pack_h2(acc[a_][0][0], acc[a_][0][1]), pack_h2(acc[a_][0][2], acc[a_][0][3]),
+                            pack_h2(acc[a_][1][0], acc[a_][1][1]), pack_h2(acc[a_][1][2], acc[a_][1][3]));
+      const unsigned dst = smem_u32(recv + (buf * NPART + rank * 2 + kh) * 32 + lane);
+      st_async_v4(mapa(dst, nt), pk, mapa(bar, nt));
+    }
+  };
+  // sum of the 8 partial tiles of (utterance fu, rows 2*i4, 2*i4+1)
+  auto gather = [&](const uint4* recv, int buf, unsigned bar, unsigned parity, float& s0, float& s1) {
+    mbar_wait(bar, parity);
+    s0 = 0.f; s1 = 0.f;
+    const unsigned* rw = (const unsigned*)(recv + buf * NPART * 32 + lane) + w4;
+#pragma unroll
+    for (int srcr = 0; srcr < NPART; ++srcr) {
+      const float2 f = unpack_h2(rw[srcr * 32 * 4]);
+      s0 += f.x; s1 += f.y;
+    }
+  };
+  // poll this rank's K-share of one tagged 512-vector (owner blocks 32*rank .. 32*rank+31, 16 pieces of 16 bytes each:
+  // four pieces per thread of the role) and stage it as an MMA A tile
+  auto poll512 = [&](const uint32_t* vec, int j, unsigned tag, __nv_bfloat16* dstA) {
+    const uint4* src = (const uint4*)vec + ((size_t)j * NOWN + 32 * rank) * 16 + t128;
+    uint4 v[4];
+    unsigned pend = 0xF;
+    unsigned spins = 0; long long t0 = 0;
+    while (pend) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+        if (pend & (1u << i)) v[i] = ld_strong_v4(src + 128 * i);
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+        if ((pend & (1u << i)) && fresh4(v[i], tag)) pend &= ~(1u << i);
+      if (pend) spin_check(spins, t0);
+    }
+    // piece e = t128 + 128 i: owner-in-share e >> 4 -> channels 4 (e >> 4) .., utterances 2 (e & 15), +1
+    const int u0 = 2 * (t128 & 15);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int col = 4 * ((t128 >> 4) + 8 * i);
+      *(uint2*)(dstA + u0 * PA + col) = make_uint2(v[i].x, v[i].y);
+      *(uint2*)(dstA + (u0 + 1) * PA + col) = make_uint2(v[i].z, v[i].w);
+    }
+  };
+  // the schedule both roles follow: does the late part of 512-phase j of step t produce an E exchange?
+  auto makes_e_of = [&](int t, int j) -> bool { return j == L ? (t + 1 < g.max_steps) : (j <= L - 2); };
+
+  int sy_c = half, sy_p1 = half, sy_p2 = half;   // lane u: s(t-1), s(t-2), s(t-3) of utterance u
+  // symbols of step t -> (sy_c, sy_p1, sy_p2); finishers fetch them (warp 0 polls), streamers pick them up
+  auto step_symbols = [&](int t) {
+    if (t == 0) {
+      sy_p2 = sy_p1; sy_p1 = sy_c;
+      sy_c = lane < B ? (int)(((g.seed[lane] % Q) + Q) % Q) : half;   // qpnet.py:356-358: pad with Q/2, keep the seed last
+    } else if (t >= 1) {
+      if (finisher) {
+        if (warp == 0) {
+          int nw = half;
+          if (lane < B) {
+            const unsigned want = ((unsigned)(t - 1) & 1u) << 30;
+            unsigned spins = 0; long long t0 = 0;
+            while (true) {
+              unsigned w = ld_strong_u32(p.vsym + lane * 32);
+              if (((w ^ want) & 0x40000000u) == 0) { nw = (int)(w & 0xFFFFu) % Q; break; }
+              spin_check(spins, t0);
+            }
+          }
+          sSym[lane] = nw;
+        }
+        asm volatile("bar.sync 2, 128;\n" ::: "memory");
+        asm volatile("bar.arrive 3, 256;\n" ::: "memory");
+      } else {
+        asm volatile("bar.sync 3, 256;\n" ::: "memory");
+      }
+      const int nw = sSym[lane];
+      sy_p2 = sy_p1; sy_p1 = sy_c; sy_c = nw;
+    }
+  };
+
+  if (finisher) {
+    // ======================================================================================= finishers
+    float2 tb1 = make_float2(0.f, 0.f), tb2 = make_float2(0.f, 0.f);   // Wc_1 . x_0 and Wc_2 . x_0 of (fu, rows 2*i4, +1)
+    float carry[2][2][4];                // H_{j+1} z_{j-1} of this warp's tile, added to the next gate tile
+    zero(carry);
+    int nf = 0;                          // finisher phases so far: z tile = nf & 1
+    int ng = 0;                          // gate / head exchanges so far: receive buffer = ng & 1.  (Counted separately: the
+                                         // final skip phase has no such exchange, and a peer may only reuse a buffer after an
+                                         // exchange in between that needed this CTA's partial tiles.)
+    int mf = 0;                          // 512-phases so far = weight tile sequence number; R buffer = mf % 3
+    int ec = 0;                          // E exchanges consumed so far: buffer = ec % 3
+    unsigned gpar = 0, epar = 0;         // wait parities, one bit per buffer
+    bool have_e = false;
+    // finisher tiles [G|H ; R,K]: one per 512-phase, two slots, requested by thread 0 one phase ahead (right after the
+    // finisher barrier of phase m, when every finisher warp is done with phase m-1).  Tile m completes phase
+    // (m / 2) & 1 of the mbarrier of slot m & 1.
+    int pf_t = -L, pf_i = 0, pf_slot = 0;
+    auto issue_f_tile = [&]() {
+      if (tid == 0 && pf_t < g.max_steps) {
+        const unsigned bar = barTF0 + 8 * pf_slot;
+        mbar_expect_tx(bar, FT_B);
+        bulk_g2s(smem_u32(sWF + pf_slot * FT_B), p.Wf + ((size_t)pf_i * NOWN + s) * FT_E, FT_B, bar);
+        if (++pf_i == L) { pf_i = 0; ++pf_t; }
+      }
+      pf_slot ^= 1;
+    };
+    issue_f_tile();
+
+    // aux 1x1 of the owned 8 gate rows for this warp's 8 utterances (its half of one m16 tile): 3 MMAs
+    // (qpnet.py:663-664 / 632-633).  Returns the (row 2*i4, row 2*i4+1) pair of utterance fu.
+    auto aux_pair = [&](int l, int t, float& a0_, float& a1_) {
+      float ax[4] = {0.f, 0.f, 0.f, 0.f};
+      const __nv_bfloat16* hp = sHaux + ((t & 1) * UB + 16 * (warp >> 1) + (lane & 15)) * PH + (lane >> 4) * 8;
+      const __nv_bfloat16* vp = sVaux + (l * 8 + (lane & 7)) * PH + ((lane >> 3) & 1) * 8;
+#pragma unroll
+      for (int ks = 0; ks < AP / 16; ++ks) {
+        unsigned b0, b1, a0, a1, a2, a3;
+        ldmatrix_x2(b0, b1, vp + ks * 16);
+        ldmatrix_x4(a0, a1, a2, a3, hp + ks * 16);
+        mma_bf16(ax, a0, a1, a2, a3, b0, b1);
+      }
+      a0_ = (warp & 1) ? ax[2] : ax[0];
+      a1_ = (warp & 1) ? ax[3] : ax[1];
+    };
+    // gate non-linearity + publication of (utterance fu, owned channel i4)
+    auto publish_gate = [&](int l, float pre_s, float pre_t, unsigned tag) {
+      const float z = fast_sigmoid(pre_s + sBg[l * 8 + 2 * i4]) * fast_tanh(pre_t + sBg[l * 8 + 2 * i4 + 1]);
+      const float zn = __shfl_xor_sync(0xffffffffu, z, 1);
+      if (!(i4 & 1)) st_strong_u32(p.vz + (((size_t)l * NOWN + s) * UB + fu) * 2 + (i4 >> 1), pack_tagged(z, zn, tag));
+    };
+
+    for (int t = -L; t < g.max_steps; ++t) {
+      const bool prime = t < 0;
+      const unsigned tagn = (unsigned)(t + L) & 1u;   // epoch tag of every z / x word of this step
+      // ---------------------------------------------------------------- block 0 gate: symbols -> tables
+      trace(t, 0, 0);
+      step_symbols(t);
+      trace(t, 0, 1);
+      {
+        const int c_ = __shfl_sync(0xffffffffu, sy_c, fu), a_ = __shfl_sync(0xffffffffu, sy_p1, fu), b_ = __shfl_sync(0xffffffffu, sy_p2, fu);
+        float a0_, a1_;
+        aux_pair(0, t, a0_, a1_);
+        const float2 ta = *(const float2*)(sT0 + ((0 * Q + c_) * 8 + 2 * i4));
+        const float2 tb = *(const float2*)(sT0 + ((1 * Q + a_) * 8 + 2 * i4));
+        const float2 tc = *(const float2*)(sT0 + ((2 * Q + b_) * 8 + 2 * i4));
+        publish_gate(0, ta.x + tb.x + tc.x + a0_, ta.y + tb.y + tc.y + a1_, tagn);
+        trace(t, 0, 6);
+        // off the critical path: the x_0 terms of blocks 1 and 2
+        const float* T = p.T12 + (size_t)s * 4 * Q * 8 + 2 * i4;
+        const float2 u1 = __ldg((const float2*)(T + (0 * Q + c_) * 8)), v1 = __ldg((const float2*)(T + (1 * Q + a_) * 8));
+        const float2 u2 = __ldg((const float2*)(T + (2 * Q + c_) * 8)), v2 = __ldg((const float2*)(T + (3 * Q + a_) * 8));
+        tb1 = make_float2(u1.x + v1.x, u1.y + v1.y);
+        tb2 = make_float2(u2.x + v2.x, u2.y + v2.y);
+      }
+      trace(t, 0, 7);
+
+      // ---------------------------------------------------------------- 512-phases j = 1 .. L (L = final skip phase)
+      for (int j = 1; j <= L; ++j) {
+        const bool fused = j < L;
+        trace(t, j, 0);
+        const int ab = nf & 1, gb = ng & 1, slot_i = mf & 1, rb = mf % 3;
+        __nv_bfloat16* Az = sAz + ab * UB * PA;
+        const unsigned barG = barG0 + 8 * gb;
+        if (tid == 0 && fused) mbar_expect_tx(barG, NPART * 512);
+        float a0_ = 0.f, a1_ = 0.f;
+        if (fused) aux_pair(j, t, a0_, a1_);   // needs nothing from this phase's exchange
+        // Flow control: a finisher may run at most two 512-phases ahead of its own streamers (three res / skip buffers).
+        // The E exchange bounds the lead almost everywhere, but the final skip phase needs no E, and priming passes have
+        // no head phases to stall on either.
+        if (mf >= 2) { if (mf & 1) asm volatile("bar.sync 7, 256;\n" ::: "memory"); else asm volatile("bar.sync 6, 256;\n" ::: "memory"); }
+        poll512(p.vz, j - 1, tagn, Az);
+        trace(t, j, 1);
+        mbar_wait(barTF0 + 8 * slot_i, (unsigned)(mf >> 1) & 1u);   // this phase's weight tile has landed
+        asm volatile("bar.sync 5, 128;\n" ::: "memory");
+        issue_f_tile();   // next phase's tile into the other slot
+        trace(t, j, 2);
+        const __nv_bfloat16* Wtop = (const __nv_bfloat16*)(sWF + slot_i * FT_B);
+        const __nv_bfloat16* Wrk = Wtop + FT_TOP;
+        const __nv_bfloat16* aq = Az + lrow + kh * (KS / 2);
+        float acc[2][2][4];
+        if (fused) {
+          // gate: carry = H_j z_{j-2} from the previous phase, + G_j z_{j-1}
+#pragma unroll
+          for (int a_ = 0; a_ < 2; ++a_)
+#pragma unroll
+            for (int b_ = 0; b_ < 2; ++b_)
+#pragma unroll
+              for (int c_ = 0; c_ < 4; ++c_) acc[a_][b_][c_] = carry[a_][b_][c_];
+          kloop(K4(), acc, aq, Wtop + brow * PT2 + bcol + kh * (KS / 2));
+          trace(t, j, 3);
+          send(acc, sRecvG, gb, barG);
+          trace(t, j, 4);
+        }
+        // while the gate partial tiles travel: res / skip rows of block j-1 (finished by the streaming warps) ...
+        zero(acc);
+        kloop(K4(), acc, aq, Wrk + brow * PS + bcol + kh * (KS / 2));
+        send(acc, sRecvR, rb, barR0 + 8 * rb);
+        // ... and the part of the NEXT gate that z_{j-1} already determines
+        zero(carry);
+        if (j <= L - 2) kloop(K4(), carry, aq, Wtop + brow * PT2 + bcol + KS + kh * (KS / 2));
+        if (fused) {
+          float s0, s1, e0 = 0.f, e1 = 0.f;
+          gather(sRecvG, gb, barG, (gpar >> gb) & 1u, s0, s1);
+          gpar ^= 1u << gb;
+          ++ng;
+          if (have_e) {
+            const int eb = ec % 3;
+            gather(sRecvE, eb, barE0 + 8 * eb, (epar >> eb) & 1u, e0, e1);
+            epar ^= 1u << eb;
+            ++ec;
+          }
+          trace(t, j, 5);
+          if (j == 1) { e0 += tb1.x; e1 += tb1.y; }
+          if (j == 2) { e0 += tb2.x; e1 += tb2.y; }
+          publish_gate(j, s0 + e0 + a0_, s1 + e1 + a1_, tagn);
+          trace(t, j, 6);
+          have_e = false;
+        }
+        if (makes_e_of(t, j)) have_e = true;
+        ++nf; ++mf;
+        trace(t, j, 7);
+      }
+      // ---------------------------------------------------------------- head 1, head 2 (resident weights)
+      if (!prime) {
+        for (int hd = 0; hd < 2; ++hd) {
+          const int tph = L + 1 + hd;
+          trace(t, tph, 0);
+          const int ab = nf & 1, gb = ng & 1;
+          __nv_bfloat16* Az = sAz + ab * UB * PA;
+          const unsigned barG = barG0 + 8 * gb;
+          if (tid == 0) mbar_expect_tx(barG, NPART * 512);
+          {
+            // share = owner blocks 32*rank .. 32*rank+31 (8 pieces each): two pieces per finisher thread
+            const unsigned par = (unsigned)t & 1u;
+            const uint4* src = (const uint4*)p.v256 + (size_t)hd * NOWN * 8 + (size_t)(32 * rank) * 8 + t128;
+            uint4 w[2];
+            unsigned pend = 3;
+            unsigned spins = 0; long long t0 = 0;
+            while (pend) {
+#pragma unroll
+              for (int i = 0; i < 2; ++i)
+                if (pend & (1u << i)) w[i] = ld_strong_v4(src + 128 * i);
+#pragma unroll
+              for (int i = 0; i < 2; ++i)
+                if ((pend & (1u << i)) && fresh4(w[i], par)) pend &= ~(1u << i);
+              if (pend) spin_check(spins, t0);
+            }
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+              const int e = t128 + 128 * i;
+              const int uh = 4 * (e & 7), col = 2 * (e >> 3);
+              *(unsigned*)(Az + uh * PA + col) = w[i].x;
+              *(unsigned*)(Az + (uh + 1) * PA + col) = w[i].y;
+              *(unsigned*)(Az + (uh + 2) * PA + col) = w[i].z;
+              *(unsigned*)(Az + (uh + 3) * PA + col) = w[i].w;
+            }
+          }
+          trace(t, tph, 1);
+          asm volatile("bar.sync 5, 128;\n" ::: "memory");
+          trace(t, tph, 2);
+          float acc[2][2][4];
+          zero(acc);
+          kloop(K2(), acc, Az + lrow + kh * (KH / 2), sWh + hd * HTILE_E + brow * PWH + bcol + kh * (KH / 2));
+          trace(t, tph, 3);
+          send(acc, sRecvG, gb, barG);
+          trace(t, tph, 4);
+          float s0, s1;
+          gather(sRecvG, gb, barG, (gpar >> gb) & 1u, s0, s1);
+          gpar ^= 1u << gb;
+          ++ng;
+          if (hd == 0) {
+            if (i4 == 0)
+              st_strong_u32(p.v256 + (size_t)(NOWN + s) * UB + fu, pack_tagged(fmaxf(s0 + sBh[0], 0.f), fmaxf(s1 + sBh[1], 0.f), (unsigned)t & 1u));
+          } else {
+            if (i4 == 0) {
+              const unsigned par_t = (unsigned)t & 1u;
+              st_strong_v2(p.vlog + ((size_t)s * UB + fu) * 2, (__float_as_uint(s0 + sBh[8]) & ~1u) | par_t,
+                           (__float_as_uint(s1 + sBh[9]) & ~1u) | par_t);
+            }
+          }
+          ++nf;
+          trace(t, tph, 7);
+        }
+      }
+    }
+  } else {
+    // ======================================================================================= streamers
+    float xc0 = 0.f, xc1 = 0.f;          // fp32 residual carry (lanes i4 < 2)
+    float sk0 = 0.f, sk1 = 0.f;          // skip accumulators (lanes i4 == 2)
+    int ms = 0;                          // 512-phases so far = weight tile sequence number; R buffer = ms % 3
+    int ep = 0;                          // E exchanges produced so far: buffer = ep % 3
+    unsigned rpar = 0;                   // wait parities of the R buffers
+
+    // ---- streamer tiles [Wc ; Wp] + past-tap tiles: one per 512-phase, two slots, requested at the START of the
+    // previous phase (the slot was last read two phases ago, by the streamers only).  Tile m completes phase
+    // (m / 2) & 1 of the mbarrier of slot m & 1; the past tiles are cp.async groups of the requesting threads.
+    // The past-tap partial tiles are those the E part needs: block j+1 of the same step (j <= L-2), or block 1 of the
+    // next step (j == L).
+    int pf_t = -L, pf_i = 0, pf_slot = 0;   // cursor of the next tile to fetch
+    auto issue_next_tile = [&]() {
+      if (pf_t < g.max_steps) {
+        unsigned char* dst = sWS + pf_slot * SSLOT;
+        const unsigned bar = barTS0 + 8 * pf_slot;
         const int j = pf_i + 1;
         if (t128 == 0) {
-          mbar_expect_tx(bar, TILE_B);
-          bulk_g2s(smem_u32(dst), p.Wf + ((size_t)pf_i * NOWN + s) * TILE_E, TILE_B, bar);
+          mbar_expect_tx(bar, ST_B);
+          bulk_g2s(smem_u32(dst), p.Ws + ((size_t)pf_i * NOWN + s) * ST_E, ST_B, bar);
         }
-        const int gl = j == L ? 1 : j + 1;          // gate block whose past tap the late part of phase j seeds
+        const int gl = j == L ? 1 : j + 1;          // gate block whose past tap the E part of phase j seeds
         const int tt = j == L ? pf_t + 1 : pf_t;    // its step
-        // the first priming pass has no ring contents yet; its very last late part feeds a step that does not exist
+        // the first priming pass has no ring contents yet; the very last E part would feed a step that does not exist
         if (j != L - 1 && tt > -L && tt < g.max_steps) {
           // past-tap partial tiles P_gl(tt - k) = Wp_gl . x_gl(tt - k) over this CTA's K-share, stored k steps ago in
           // MMA fragment order: piece (warp w, utterance group m, lane) = 4 floats of utterance (lane >> 2) + 8m.
@@ -536,431 +880,178 @@ __global__ void __launch_bounds__(NT, 1) f2_gen_kernel(Plan p, GenArgsDev g) {
           }
 #pragma unroll
           for (int m = 0; m < 4; ++m)
-            cp_async16(dst + TILE_B + ((w * 4 + m) * 32 + ln) * 16,
+            cp_async16(dst + ST_B + ((w * 4 + m) * 32 + ln) * 16,
                        ringf + ((size_t)slot[m] * NOWN + s) * RINGF + w * 512 + (m * 32 + ln) * 4);
         }
-      } else if (t128 == 0) {
-        const int hd = pf_i - L;
-        mbar_expect_tx(bar, HTILE_B);
-        bulk_g2s(smem_u32(dst), p.Whead + ((size_t)hd * NOWN + s) * HTILE_E, HTILE_B, bar);
+        ++pf_i;
+        if (pf_i == L) { pf_i = 0; ++pf_t; }
       }
-      ++pf_i;
-      const int ntiles = pf_t < 0 ? L : L + 2;
-      if (pf_i == ntiles) { pf_i = 0; ++pf_t; }
-    }
-    pf_slot ^= 1;
-    cp_async_commit();
-  };
-  if (!finisher) issue_next_tile();
+      pf_slot ^= 1;
+      cp_async_commit();
+    };
+    issue_next_tile();
 
-  // ---- finisher state: this thread's utterance fu, rows (2*i4, 2*i4+1) of the owned 8 -------------
-  float xc0 = 0.f, xc1 = 0.f;          // fp32 residual carry (lanes i4 < 2)
-  float sk0 = 0.f, sk1 = 0.f;          // skip accumulators (lanes i4 == 2)
-  float2 tb1 = make_float2(0.f, 0.f), tb2 = make_float2(0.f, 0.f);   // Wc_1 . x_0 and Wc_2 . x_0 of (fu, rows 2*i4, +1)
-  int sy_c = half, sy_p1 = half, sy_p2 = half;   // lane u: s(t-1), s(t-2), s(t-3) of utterance u
-  int rp = 0;                          // MMA phase counter = tile sequence number
-  unsigned gpar = 0, epar = 0;         // wait parities of the gate-partial / E-partial barriers (bit = buffer)
-  int ecnt = 0;                        // E exchanges so far: buffer = ecnt & 1 (producer and consumer count alike)
-  bool have_e = false;                 // an E exchange for the next gate phase is in flight / landed
-
-  // aux 1x1 of the owned 8 gate rows for this warp's 8 utterances (its half of one m16 tile): 3 MMAs
-  // (qpnet.py:663-664 / 632-633).  Returns the (row 2*i4, row 2*i4+1) pair of utterance fu.
-  auto aux_pair = [&](int l, int t, float& a0_, float& a1_) {
-    float ax[4] = {0.f, 0.f, 0.f, 0.f};
-    const __nv_bfloat16* hp = sHaux + ((t & 1) * UB + 16 * (warp >> 1) + (lane & 15)) * PH + (lane >> 4) * 8;
-    const __nv_bfloat16* vp = sVaux + (l * 8 + (lane & 7)) * PH + ((lane >> 3) & 1) * 8;
-#pragma unroll
-    for (int ks = 0; ks < AP / 16; ++ks) {
-      unsigned b0, b1, a0, a1, a2, a3;
-      ldmatrix_x2(b0, b1, vp + ks * 16);
-      ldmatrix_x4(a0, a1, a2, a3, hp + ks * 16);
-      mma_bf16(ax, a0, a1, a2, a3, b0, b1);
-    }
-    a0_ = (warp & 1) ? ax[2] : ax[0];
-    a1_ = (warp & 1) ? ax[3] : ax[1];
-  };
-  // words of (block j, owner s, utterance fu) in the z / x exchange
-  auto vz_word = [&](int j) -> uint32_t* { return p.vz + (((size_t)j * NOWN + s) * UB + fu) * 2; };
-  auto vx_word = [&](int j) -> uint32_t* { return p.vx + (((size_t)j * NOWN + s) * UB + fu) * 2; };
-  // gate non-linearity + publication of (utterance fu, owned channel i4)
-  auto publish_gate = [&](int l, float pre_s, float pre_t, unsigned tag) {
-    const float z = fast_sigmoid(pre_s + sBg[l * 8 + 2 * i4]) * fast_tanh(pre_t + sBg[l * 8 + 2 * i4 + 1]);
-    const float zn = __shfl_xor_sync(0xffffffffu, z, 1);
-    if (!(i4 & 1)) st_strong_u32(vz_word(l) + (i4 >> 1), pack_tagged(z, zn, tag));
-  };
-  // poll this rank's K-share of one tagged 512-vector (owner blocks 32*rank .. 32*rank+31, 16 pieces of 16 bytes each:
-  // two pieces per thread) and stage it as an MMA A tile; nonzero when the watchdog fired
-  auto poll512 = [&](const uint32_t* vec, int j, unsigned tag, __nv_bfloat16* dstA) -> int {
-    const uint4* src = (const uint4*)vec + ((size_t)j * NOWN + 32 * rank) * 16 + tid;
-    uint4 v[2];
-    unsigned pend = 3;
-    unsigned spins = 0; long long t0 = 0;
-    int fail = 0;
-    while (pend) {
-#pragma unroll
-      for (int i = 0; i < 2; ++i)
-        if (pend & (1u << i)) v[i] = ld_strong_v4(src + 256 * i);
-#pragma unroll
-      for (int i = 0; i < 2; ++i)
-        if ((pend & (1u << i)) && fresh4(v[i], tag)) pend &= ~(1u << i);
-      if (pend && spin_check(spins, t0)) { fail = 1; break; }
-    }
-    const int u0 = 2 * (tid & 15), col0 = 4 * (tid >> 4);
-#pragma unroll
-    for (int i = 0; i < 2; ++i) {
-      *(uint2*)(dstA + u0 * PA + col0 + 64 * i) = make_uint2(v[i].x, v[i].y);
-      *(uint2*)(dstA + (u0 + 1) * PA + col0 + 64 * i) = make_uint2(v[i].z, v[i].w);
-    }
-    return fail;
-  };
-
-  // =========================================================================== time loop
-  for (int t = -L; t < g.max_steps; ++t) {
-    const bool prime = t < 0;
-    const unsigned tagn = (unsigned)(t + L) & 1u;   // epoch tag of every z / x word of this step
-
-    // ================================================================ block 0 gate: symbols -> tables
-    trace(t, 0, 0);
-    if (finisher) {
-      int bad = 0;
-      if (t == 0) {
-        sy_p2 = sy_p1; sy_p1 = sy_c;
-        sy_c = lane < B ? (int)(((g.seed[lane] % Q) + Q) % Q) : half;   // qpnet.py:356-358: pad with Q/2, keep the seed last
-      } else if (t >= 1) {
-        // one warp per CTA watches the fed-back symbols and hands them on
-        if (warp == 0) {
-          int nw = half;
-          if (lane < B) {
-            const unsigned want = ((unsigned)(t - 1) & 1u) << 30;
-            unsigned spins = 0; long long t0 = 0;
-            while (true) {
-              unsigned w = ld_strong_u32(p.vsym + lane * 32);
-              if (((w ^ want) & 0x40000000u) == 0) { nw = (int)(w & 0xFFFFu) % Q; break; }
-              if (spin_check(spins, t0)) { nw = -1; break; }
-            }
-          }
-          sSym[lane] = nw;
-        }
-        asm volatile("bar.sync 2, 128;\n" ::: "memory");
-        int nw = sSym[lane];
-        if (nw < 0) { bad = 1; nw = half; }
-        sy_p2 = sy_p1; sy_p1 = sy_c; sy_c = nw;
-      }
-      bad = __any_sync(0xffffffffu, bad);
-      trace(t, 0, 1);
-      if (bad) {
-        if (lane == 0) *sAbort = 1;
-      } else {
-        const int c_ = __shfl_sync(0xffffffffu, sy_c, fu), a_ = __shfl_sync(0xffffffffu, sy_p1, fu), b_ = __shfl_sync(0xffffffffu, sy_p2, fu);
-        float a0_, a1_;
-        aux_pair(0, t, a0_, a1_);
-        const float2 ta = *(const float2*)(sT0 + ((0 * Q + c_) * 8 + 2 * i4));
-        const float2 tb = *(const float2*)(sT0 + ((1 * Q + a_) * 8 + 2 * i4));
-        const float2 tc = *(const float2*)(sT0 + ((2 * Q + b_) * 8 + 2 * i4));
+    for (int t = -L; t < g.max_steps; ++t) {
+      const bool prime = t < 0;
+      const unsigned tagn = (unsigned)(t + L) & 1u;
+      // ---------------------------------------------------------------- block 0: the fp32 residual stream of the owned
+      // channels restarts from the causal layer x_0; skip sums restart
+      step_symbols(t);
+      {
+        const int c_ = __shfl_sync(0xffffffffu, sy_c, fu), a_ = __shfl_sync(0xffffffffu, sy_p1, fu);
         sk0 = sk1 = 0.f;
-        publish_gate(0, ta.x + tb.x + tc.x + a0_, ta.y + tb.y + tc.y + a1_, tagn);
-        trace(t, 0, 6);
-        // off the critical path: the owned channels of x_0 (fp32 residual stream restarts from the causal layer) and
-        // the x_0 terms of blocks 1 and 2
         if (i4 < 2) {
           const float2 e0 = __ldg((const float2*)(p.Eo + (((size_t)s * 2 + 0) * Q + a_) * 4 + 2 * i4));
           const float2 e1 = __ldg((const float2*)(p.Eo + (((size_t)s * 2 + 1) * Q + c_) * 4 + 2 * i4));
           xc0 = e0.x + e1.x; xc1 = e0.y + e1.y;
         }
-        const float* T = p.T12 + (size_t)s * 4 * Q * 8 + 2 * i4;
-        const float2 u1 = __ldg((const float2*)(T + (0 * Q + c_) * 8)), v1 = __ldg((const float2*)(T + (1 * Q + a_) * 8));
-        const float2 u2 = __ldg((const float2*)(T + (2 * Q + c_) * 8)), v2 = __ldg((const float2*)(T + (3 * Q + a_) * 8));
-        tb1 = make_float2(u1.x + v1.x, u1.y + v1.y);
-        tb2 = make_float2(u2.x + v2.x, u2.y + v2.y);
       }
-    }
-    trace(t, 0, 7);
-
-    // ================================================================ MMA phases
-    // KIND is a compile-time constant so every phase type gets straight-line code.
-    auto phase = [&](auto kc, const int j) -> bool {
-      constexpr int KIND = decltype(kc)::value;
-      constexpr bool is512 = KIND == K_FUSED || KIND == K_FINAL;
-      const int tph = is512 ? j : KIND == K_HEAD1 ? L + 1 : L + 2;
-      trace(t, tph, 0);
-      const int ab = rp & 1;                      // buffer of this phase: z tile, receive buffers, weight slot
-      __nv_bfloat16* Az = sAz + ab * UB * PA;
-      const unsigned barR = smem_u32(&sBars[ab]), barG = smem_u32(&sBars[2 + ab]), barT = smem_u32(&sBars[6 + ab]);
-      // late part of this phase: E for gate block j+1 (or block 1 of the next step after the final phase)
-      const bool makes_e = is512 && (KIND == K_FINAL ? (t + 1 < g.max_steps) : (j <= L - 2));
-      const bool takes_e = KIND == K_FUSED && have_e;
-      const int eb_in = (ecnt - 1) & 1, eb_out = ecnt & 1;   // E buffers: consumed now / produced in the late part
-      if (tid == 0) {
-        mbar_expect_tx(barR, NPART * 512);
-        if (KIND == K_FUSED) mbar_expect_tx(barG, NPART * 512);
-        if (makes_e) mbar_expect_tx(smem_u32(&sBars[4 + eb_out]), NPART * 512);
-      }
-      // aux 1x1 of the owned rows needs nothing from this phase's exchange: run it while the input is in flight
-      float a0_ = 0.f, a1_ = 0.f;
-      if (KIND == K_FUSED && finisher) aux_pair(j, t, a0_, a1_);
-
-      // ---- (1) poll this rank's K-share of the input vector, stage it as the MMA A tile
-      int fail = 0;
-      if (is512) {
-        fail = poll512(p.vz, j - 1, tagn, Az);
-      } else {
-        const unsigned par = (unsigned)t & 1u;
-        // share = owner blocks 32*rank .. 32*rank+31 (8 pieces each): one piece per thread
-        const uint4* src = (const uint4*)p.v256 + (size_t)(KIND == K_HEAD1 ? 0 : 1) * NOWN * 8 + (size_t)(32 * rank) * 8 + tid;
-        uint4 w;
-        unsigned spins = 0; long long t0 = 0;
-        while (true) {
-          w = ld_strong_v4(src);
-          if (fresh4(w, par)) break;
-          if (spin_check(spins, t0)) { fail = 1; break; }
+      for (int j = 1; j <= L; ++j) {
+        const bool fused = j < L;
+        const int slot_i = ms & 1, rb = ms % 3;
+        const bool makes_e = makes_e_of(t, j);
+        const int eb = ep % 3;
+        if (t128 == 0) {
+          mbar_expect_tx(barR0 + 8 * rb, NPART * 512);
+          if (makes_e) mbar_expect_tx(barE0 + 8 * eb, NPART * 512);
         }
-        const int uh = 4 * (tid & 7), col = 2 * (tid >> 3);
-        *(unsigned*)(Az + uh * PA + col) = w.x;
-        *(unsigned*)(Az + (uh + 1) * PA + col) = w.y;
-        *(unsigned*)(Az + (uh + 2) * PA + col) = w.z;
-        *(unsigned*)(Az + (uh + 3) * PA + col) = w.w;
-      }
-      trace(t, tph, 1);
-      if (!fail && !mbar_wait(barT, (unsigned)(rp >> 1) & 1u)) fail = 1;   // this phase's weight tile has landed
-      if (__syncthreads_or(fail | *sAbort)) return true;                   // ---- barrier A
-      trace(t, tph, 2);
-
-      // ---- tensor-core tiles: warp (w4 = warp & 3) contracts 32 utterances x the 16 rows owner ranks
-      // 2*(w4 & 1), +1 finish over K-half (w4 >> 1) of a 128-share.  2 x 2 register blocking.
-      const unsigned char* slot = sW + ab * WSLOT;
-      const __nv_bfloat16* Wtop = (const __nv_bfloat16*)slot;
-      const __nv_bfloat16* Wbot = Wtop + TOP_E;
-      const int w4 = warp & 3, ntp = w4 & 1, kh = w4 >> 1;
-      const int lrow = (lane & 15) * PA + (lane >> 4) * 8;
-      // B operand through ldmatrix.x4: lanes 0-7 rows 0-7 k lo, 8-15 rows 0-7 k hi, 16-23 rows 8-15 k lo, 24-31 rows 8-15 k hi
-      const int brow = 16 * ntp + (lane & 7) + ((lane >> 4) << 3), bcol = ((lane >> 3) & 1) * 8;
-      constexpr int KHALF = is512 ? KS / 2 : KH / 2;
-      const int aoff = lrow + kh * KHALF;
-      auto kloop = [&](float (&acc)[2][2][4], const __nv_bfloat16* aq, const __nv_bfloat16* bq) {
+        // every streaming warp is done with the previous phase: its x tile and the other weight slot may be overwritten
+        asm volatile("bar.sync 4, 128;\n" ::: "memory");
+        issue_next_tile();   // next phase's tile into the other slot
+        const bool need_x = j >= 2;   // x_{j-1} was published during phase j-1; block 0's x_0 never travels (tables)
+        if (need_x) poll512(p.vx, j - 1, tagn, sAx);
+        cp_async_wait<1>();                                            // the past tiles of this phase's slot
+        mbar_wait(barTS0 + 8 * slot_i, (unsigned)(ms >> 1) & 1u);      // and its weight tile have landed
+        asm volatile("bar.sync 4, 128;\n" ::: "memory");
+        trace(t, j, 8);
+        const unsigned char* slot = sWS + slot_i * SSLOT;
+        const __nv_bfloat16* Wc = (const __nv_bfloat16*)slot;
+        const __nv_bfloat16* Wp = Wc + NR * PS;
+        // E for gate block gl (past-tap partial tiles + Wc_gl x_{j-1}) and the ring rows P_{j-1}(t) = Wp_{j-1} x_{j-1}(t)
+        // share the activation fragments
+        float acc[2][2][4], acce[2][2][4];
+        zero(acc);
+        zero(acce);
+        if (makes_e) {
+          const int tt = fused ? t : t + 1;
+          if (tt > -L) {
+            const float4* pin = (const float4*)(slot + ST_B) + w4 * 128 + lane;
 #pragma unroll
-        for (int ks = 0; ks < KHALF / 16; ++ks) {
-          unsigned b0, b1, b2, b3, a0, a1, a2, a3, c0, c1, c2, c3;
-          ldmatrix_x4(b0, b1, b2, b3, bq + ks * 16);   // rows 0-7 (k lo, k hi), rows 8-15 (k lo, k hi)
-          ldmatrix_x4(a0, a1, a2, a3, aq + ks * 16);
-          ldmatrix_x4(c0, c1, c2, c3, aq + 16 * PA + ks * 16);
-          mma_bf16(acc[0][0], a0, a1, a2, a3, b0, b1);
-          mma_bf16(acc[1][0], a0, a1, a2, a3, b2, b3);
-          mma_bf16(acc[0][1], c0, c1, c2, c3, b0, b1);
-          mma_bf16(acc[1][1], c0, c1, c2, c3, b2, b3);
-        }
-      };
-      auto zero = [&](float (&acc)[2][2][4]) {
-#pragma unroll
-        for (int a_ = 0; a_ < 2; ++a_)
-#pragma unroll
-          for (int b_ = 0; b_ < 2; ++b_) acc[a_][b_][0] = acc[a_][b_][1] = acc[a_][b_][2] = acc[a_][b_][3] = 0.f;
-      };
-      // partial tiles -> owner ranks: utterances (q4, q4+8, q4+16, q4+24) x rows (2*i4, 2*i4+1), fp16
-      auto send = [&](const float (&acc)[2][2][4], uint4* recv, int buf, unsigned bar) {
-#pragma unroll
-        for (int a_ = 0; a_ < 2; ++a_) {
-          const int nt = 2 * ntp + a_;
-          uint4 pk = make_uint4(pack_h2(acc[a_][0][0], acc[a_][0][1]), pack_h2(acc[a_][0][2], acc[a_][0][3]),
-                                pack_h2(acc[a_][1][0], acc[a_][1][1]), pack_h2(acc[a_][1][2], acc[a_][1][3]));
-          const unsigned dst = smem_u32(recv + (buf * NPART + rank * 2 + kh) * 32 + lane);
-          st_async_v4(mapa(dst, nt), pk, mapa(bar, nt));
-        }
-      };
-      // sum of the 8 partial tiles of (utterance fu, rows 2*i4, 2*i4+1); false when the watchdog fired
-      auto gather = [&](const uint4* recv, int buf, unsigned bar, unsigned parity, float& s0, float& s1) -> bool {
-        if (!mbar_wait(bar, parity)) return false;
-        s0 = 0.f; s1 = 0.f;
-        const unsigned* rw = (const unsigned*)(recv + buf * NPART * 32 + lane) + warp;
-#pragma unroll
-        for (int srcr = 0; srcr < NPART; ++srcr) {
-          const float2 f = unpack_h2(rw[srcr * 32 * 4]);
-          s0 += f.x; s1 += f.y;
-        }
-        return true;
-      };
-      float acc[2][2][4];   // [owner of the pair][m tile][fragment]
-      zero(acc);
-      int bad = 0;
-
-      // ================================================= critical part
-      if (finisher) {
-        if (KIND == K_FUSED) {
-          kloop(acc, Az + aoff, Wtop + brow * PT + bcol + kh * KHALF);                 // G_j z_{j-1}
-          trace(t, tph, 3);
-          send(acc, sRecvG, ab, barG);
-          trace(t, tph, 4);
-          float s0, s1, e0 = 0.f, e1 = 0.f;
-          if (!gather(sRecvG, ab, barG, (gpar >> ab) & 1u, s0, s1)) bad = 1;
-          if (!bad && takes_e && !gather(sRecvE, eb_in, smem_u32(&sBars[4 + eb_in]), (epar >> eb_in) & 1u, e0, e1)) bad = 1;
-          trace(t, tph, 5);
-          if (!bad) {
-            if (j == 1) { e0 += tb1.x; e1 += tb1.y; }
-            if (j == 2) { e0 += tb2.x; e1 += tb2.y; }
-            publish_gate(j, s0 + e0 + a0_, s1 + e1 + a1_, tagn);
+            for (int m = 0; m < 4; ++m) {
+              const float4 q = pin[m * 32];
+              acce[0][m >> 1][(m & 1) * 2] = q.x; acce[0][m >> 1][(m & 1) * 2 + 1] = q.y;
+              acce[1][m >> 1][(m & 1) * 2] = q.z; acce[1][m >> 1][(m & 1) * 2 + 1] = q.w;
+            }
           }
-          trace(t, tph, 6);
-        } else if (KIND == K_HEAD1 || KIND == K_HEAD2) {
-          kloop(acc, Az + aoff, (const __nv_bfloat16*)slot + brow * PWH + bcol + kh * KHALF);
-          trace(t, tph, 3);
-          send(acc, sRecvR, ab, barR);
-          trace(t, tph, 4);
         }
-        // res / skip rows of block j-1 (the streaming warps' tiles), or the head rows
-        float s0 = 0.f, s1 = 0.f;
-        if (!bad && !gather(sRecvR, ab, barR, (unsigned)(rp >> 1) & 1u, s0, s1)) bad = 1;
-        if (bad) {
-          if (lane == 0) *sAbort = 1;
-        } else if (is512) {
+        if (need_x) {
+          const __nv_bfloat16* aq = sAx + lrow + kh * (KS / 2);
+          const __nv_bfloat16* be = Wc + brow * PS + bcol + kh * (KS / 2);   // Wc_{j+1}
+          const __nv_bfloat16* bq = Wp + brow * PS + bcol + kh * (KS / 2);   // Wp_{j-1}
+          const bool with_e = makes_e && fused;
+#pragma unroll
+          for (int ks = 0; ks < KS / 32; ++ks) {
+            unsigned b0, b1, b2, b3, a0, a1, a2, a3, c0, c1, c2, c3;
+            ldmatrix_x4(a0, a1, a2, a3, aq + ks * 16);
+            ldmatrix_x4(c0, c1, c2, c3, aq + 16 * PA + ks * 16);
+            ldmatrix_x4(b0, b1, b2, b3, bq + ks * 16);
+            mma_bf16(acc[0][0], a0, a1, a2, a3, b0, b1);
+            mma_bf16(acc[1][0], a0, a1, a2, a3, b2, b3);
+            mma_bf16(acc[0][1], c0, c1, c2, c3, b0, b1);
+            mma_bf16(acc[1][1], c0, c1, c2, c3, b2, b3);
+            if (with_e) {
+              ldmatrix_x4(b0, b1, b2, b3, be + ks * 16);
+              mma_bf16(acce[0][0], a0, a1, a2, a3, b0, b1);
+              mma_bf16(acce[1][0], a0, a1, a2, a3, b2, b3);
+              mma_bf16(acce[0][1], c0, c1, c2, c3, b0, b1);
+              mma_bf16(acce[1][1], c0, c1, c2, c3, b2, b3);
+            }
+          }
+        }
+        if (makes_e) { send(acce, sRecvE, eb, barE0 + 8 * eb); ++ep; }
+        trace(t, j, 9);
+        if (need_x) {
+          // ring rows kept un-reduced in fragment order for step t + k.  Priming passes write slot 0; the last one
+          // fills the whole ring.
+          float* ringf = p.ring[j - 1];
+          const int rs = p.ring_size[j - 1];
+          const size_t slot_f4 = (size_t)NOWN * (RINGF / 4);
+          float4* r0 = (float4*)(ringf + (size_t)s * RINGF + w4 * 512) + lane;
+          const int sl0 = prime ? 0 : (t & (rs - 1)), sl1 = prime ? (t == -1 ? rs : 1) : sl0 + 1;
+          for (int sl = sl0; sl < sl1; ++sl) {
+            float4* r1 = r0 + sl * slot_f4;
+#pragma unroll
+            for (int m = 0; m < 4; ++m)
+              r1[m * 32] = make_float4(acc[0][m >> 1][(m & 1) * 2], acc[0][m >> 1][(m & 1) * 2 + 1],
+                                       acc[1][m >> 1][(m & 1) * 2], acc[1][m >> 1][(m & 1) * 2 + 1]);
+          }
+        }
+        trace(t, j, 10);
+        // res / skip rows of block j-1 (the finishers' tiles): finish, publish x_j (consumed by phase j+1)
+        {
+          float s0, s1;
+          gather(sRecvR, rb, barR0 + 8 * rb, (rpar >> rb) & 1u, s0, s1);
+          rpar ^= 1u << rb;
           const int l = j - 1;
           const float v0 = s0 + sBr[l * 8 + 2 * i4], v1 = s1 + sBr[l * 8 + 2 * i4 + 1];
           if (i4 < 2) {
-            if (KIND == K_FUSED) {   // residual projection + current input (qpnet.py:669 / 639); dead after the last block (C7)
+            if (fused) {   // residual projection + current input (qpnet.py:669 / 639); dead after the last block (C7)
               xc0 += v0; xc1 += v1;
-              st_strong_u32(vx_word(j) + i4, pack_tagged(xc0, xc1, tagn));
+              st_strong_u32(p.vx + (((size_t)j * NOWN + s) * UB + fu) * 2 + i4, pack_tagged(xc0, xc1, tagn));
             }
           } else if (i4 == 2) {
             sk0 += v0; sk1 += v1;
-            if (KIND == K_FINAL && !prime)
+            if (!fused && !prime)
               st_strong_u32(p.v256 + (size_t)s * UB + fu, pack_tagged(fmaxf(sk0, 0.f), fmaxf(sk1, 0.f), (unsigned)t & 1u));
           }
-        } else if (KIND == K_HEAD1) {
-          if (i4 == 0)
-            st_strong_u32(p.v256 + (size_t)(NOWN + s) * UB + fu, pack_tagged(fmaxf(s0 + sBh[0], 0.f), fmaxf(s1 + sBh[1], 0.f), (unsigned)t & 1u));
-        } else {
-          if (i4 == 0) {
-            const unsigned par_t = (unsigned)t & 1u;
-            st_strong_v2(p.vlog + ((size_t)s * UB + fu) * 2, (__float_as_uint(s0 + sBh[8]) & ~1u) | par_t,
-                         (__float_as_uint(s1 + sBh[9]) & ~1u) | par_t);
-          }
         }
-        trace(t, tph, 7);
-      } else {
-        if (is512) {
-          kloop(acc, Az + aoff, Wbot + brow * PB + bcol + kh * KHALF);                 // [R ; K]_{j-1} z_{j-1}
-          send(acc, sRecvR, ab, barR);
-        }
-        trace_s(t, tph, 10);
-        issue_next_tile();   // into the other slot: last read in the late part of the previous phase, before barrier A
-        trace_s(t, tph, 11);
-      }
-
-      // ================================================= late part (fused / final phases)
-      if (is512) {
-        // x_{j-1} was published during phase j-1, after z_{j-1}; block 0's x_0 never travels (tables)
-        const bool need_x = j >= 2;
-        int fail2 = 0;
-        if (need_x) fail2 = poll512(p.vx, j - 1, tagn, sAx);
-        cp_async_wait<1>();   // streaming warps: the past tiles of THIS phase's slot have landed (the next tile may be in flight)
-        if (__syncthreads_or(fail2 | *sAbort)) return true;                // ---- barrier B
-        trace(t, tph, 8);
-        if (finisher) {
-          if (makes_e) {
-            // E for gate block gl: past-tap partial tiles seed the accumulators, then H_gl z_{j-1} + Wc_gl x_{j-1}
-            const int tt = KIND == K_FINAL ? t + 1 : t;
-            zero(acc);
-            if (tt > -L) {
-              const float4* pin = (const float4*)(slot + TILE_B) + w4 * 128 + lane;
-#pragma unroll
-              for (int m = 0; m < 4; ++m) {
-                const float4 q = pin[m * 32];
-                acc[0][m >> 1][(m & 1) * 2] = q.x; acc[0][m >> 1][(m & 1) * 2 + 1] = q.y;
-                acc[1][m >> 1][(m & 1) * 2] = q.z; acc[1][m >> 1][(m & 1) * 2 + 1] = q.w;
-              }
-            }
-            if (KIND == K_FUSED) {
-              kloop(acc, Az + aoff, Wtop + brow * PT + bcol + KS + kh * KHALF);                  // H_{j+1} z_{j-1}
-              if (need_x) kloop(acc, sAx + aoff, Wtop + brow * PT + bcol + 2 * KS + kh * KHALF);   // Wc_{j+1} x_{j-1}
-            }
-            send(acc, sRecvE, eb_out, smem_u32(&sBars[4 + eb_out]));
-          }
-          trace(t, tph, 9);
-        } else {
-          if (need_x) {
-            // ring rows: P_{j-1}(t) = Wp_{j-1} . x_{j-1}(t) over this CTA's K-share, kept un-reduced in fragment order
-            // for step t + k.  Priming passes write slot 0; the last one fills the whole ring.
-            zero(acc);
-            kloop(acc, sAx + aoff, Wbot + brow * PB + bcol + KS + kh * KHALF);
-            float* ringf = p.ring[j - 1];
-            const int rs = p.ring_size[j - 1];
-            const size_t slot_f4 = (size_t)NOWN * (RINGF / 4);
-            float4* r0 = (float4*)(ringf + (size_t)s * RINGF + w4 * 512) + lane;
-            const int sl0 = prime ? 0 : (t & (rs - 1)), sl1 = prime ? (t == -1 ? rs : 1) : sl0 + 1;
-            for (int sl = sl0; sl < sl1; ++sl) {
-              float4* r1 = r0 + sl * slot_f4;
-#pragma unroll
-              for (int m = 0; m < 4; ++m)
-                r1[m * 32] = make_float4(acc[0][m >> 1][(m & 1) * 2], acc[0][m >> 1][(m & 1) * 2 + 1],
-                                         acc[1][m >> 1][(m & 1) * 2], acc[1][m >> 1][(m & 1) * 2 + 1]);
-            }
-          }
-          if (KIND == K_FUSED && j == 1) {
-            // h_up[:, ta] = h[:, ta / U] * w[ta % U] + b (qpnet.py:143-158, 451) for the NEXT step
-            const int tn = t + 1;
-            if (tn < g.max_steps) {
-              const int ta = tn < 0 ? 0 : tn;
-              const int f = ta / U, jj = ta - f * U;
-              if (jj == 0 && tn > 0) {
-                for (int e = t128; e < UB * A; e += 128) {
-                  int u = e / A, a = e - u * A;
-                  sHraw[u * HR + a] = u < B ? g.h[((size_t)u * A + a) * p.F + f] : 0.f;
-                }
-                asm volatile("bar.sync 1, 128;\n" ::: "memory");
-              }
-              const float w = g.up_w[jj], bb = g.up_b[0];
+        trace(t, j, 11);
+        if (j == 1) {
+          // h_up[:, ta] = h[:, ta / U] * w[ta % U] + b (qpnet.py:143-158, 451) for the NEXT step
+          const int tn = t + 1;
+          if (tn < g.max_steps) {
+            const int ta = tn < 0 ? 0 : tn;
+            const int f = ta / U, jj = ta - f * U;
+            if (jj == 0 && tn > 0) {
               for (int e = t128; e < UB * A; e += 128) {
                 int u = e / A, a = e - u * A;
-                sHaux[((tn & 1) * UB + u) * PH + a] = __float2bfloat16(sHraw[u * HR + a] * w + bb);
+                sHraw[u * HR + a] = u < B ? g.h[((size_t)u * A + a) * p.F + f] : 0.f;
               }
+              asm volatile("bar.sync 1, 128;\n" ::: "memory");
+            }
+            const float w = g.up_w[jj], bb = g.up_b[0];
+            for (int e = t128; e < UB * A; e += 128) {
+              int u = e / A, a = e - u * A;
+              sHaux[((tn & 1) * UB + u) * PH + a] = __float2bfloat16(sHraw[u * HR + a] * w + bb);
             }
           }
-          trace_s(t, tph, 12);
         }
+        if (ms & 1) asm volatile("bar.arrive 7, 256;\n" ::: "memory"); else asm volatile("bar.arrive 6, 256;\n" ::: "memory");   // phase ms done
+        ++ms;
+        trace(t, j, 12);
       }
-      // bookkeeping shared by every thread
-      if (takes_e) { epar ^= 1u << eb_in; }
-      if (KIND == K_FUSED) { gpar ^= 1u << ab; have_e = false; }
-      if (makes_e) { ++ecnt; have_e = true; }
-      ++rp;
-      return false;
-    };
-    {
-      bool stop = false;
-      for (int j = 1; j < L && !stop; ++j) stop = phase(std::integral_constant<int, K_FUSED>(), j);
-      if (!stop) stop = phase(std::integral_constant<int, K_FINAL>(), L);
-      if (!stop && !prime) {
-        stop = phase(std::integral_constant<int, K_HEAD1>(), 0);
-        if (!stop) stop = phase(std::integral_constant<int, K_HEAD2>(), 0);
-      }
-      if (stop) goto done;
-    }
 
-    // ================================================================ sampling: one warp per utterance
-    if (!prime && warp == 7 && s < B) {
-      if (TRACE && s == 0 && lane == 0 && t >= p.trace_step0 && t < p.trace_step0 + p.trace_nsteps)
-        p.trace[((size_t)(t - p.trace_step0) * nphase + L + 3) * TRACE_EVENTS + 0] = clock64();
-      const int u = s;
-      const unsigned par_t = (unsigned)t & 1u;
-      float v[8];
-      int bad = 0;
-      {
-        unsigned pend = 0xF;
-        unsigned spins = 0; long long t0 = 0;
-        while (pend) {
-          uint2 w[4];
+      // ---------------------------------------------------------------- sampling: one warp per utterance
+      if (!prime && warp == 7 && s < B) {
+        const int u = s;
+        const unsigned par_t = (unsigned)t & 1u;
+        float v[8];
+        {
+          unsigned pend = 0xF;
+          unsigned spins = 0; long long t0 = 0;
+          while (pend) {
+            uint2 w[4];
 #pragma unroll
-          for (int j = 0; j < 4; ++j)
-            if (pend & (1u << j)) w[j] = ld_strong_v2(p.vlog + ((size_t)(4 * lane + j) * UB + u) * 2);
+            for (int j = 0; j < 4; ++j)
+              if (pend & (1u << j)) w[j] = ld_strong_v2(p.vlog + ((size_t)(4 * lane + j) * UB + u) * 2);
 #pragma unroll
-          for (int j = 0; j < 4; ++j)
-            if ((pend & (1u << j)) && (((w[j].x ^ par_t) | (w[j].y ^ par_t)) & 1u) == 0) {
-              v[2 * j] = __uint_as_float(w[j].x); v[2 * j + 1] = __uint_as_float(w[j].y); pend &= ~(1u << j);
-            }
-          if (pend && spin_check(spins, t0)) { bad = 1; break; }
+            for (int j = 0; j < 4; ++j)
+              if ((pend & (1u << j)) && (((w[j].x ^ par_t) | (w[j].y ^ par_t)) & 1u) == 0) {
+                v[2 * j] = __uint_as_float(w[j].x); v[2 * j + 1] = __uint_as_float(w[j].y); pend &= ~(1u << j);
+              }
+            if (pend) spin_check(spins, t0);
+          }
         }
-      }
-      if (__any_sync(0xffffffffu, bad)) {
-        if (lane == 0) *sAbort = 1;
-      } else {
         float mx = -INFINITY;
         int amax = 0;
 #pragma unroll
@@ -1006,12 +1097,9 @@ __global__ void __launch_bounds__(NT, 1) f2_gen_kernel(Plan p, GenArgsDev g) {
           st_strong_u32(p.vsym + u * 32, ((unsigned)fed & 0xFFFFu) | (par_t << 30));
         }
       }
-      if (TRACE && s == 0 && lane == 0 && t >= p.trace_step0 && t < p.trace_step0 + p.trace_nsteps)
-        p.trace[((size_t)(t - p.trace_step0) * nphase + L + 3) * TRACE_EVENTS + 7] = clock64();
     }
+    cp_async_wait<0>();
   }
-done:
-  cp_async_wait<0>();
   __syncthreads();
   cluster_sync();   // no CTA of the cluster leaves while a peer may still write into its shared memory
 }

@@ -17,8 +17,8 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 
 
 def fold2_trace(m, args, d64, L):
-    """two-level folded generator (qp_generate_fold2.cu): phases = block 0, fused 1..L-1, final skip, head-1, head-2,
-    sampling; 13 events each, see TRACE_EVENTS in the kernel"""
+    """role-split two-level folded generator (qp_generate_fold2.cu): phases = block 0, 512-phases 1..L (L = final skip),
+    head-1, head-2; 13 events each, see TRACE_EVENTS in the kernel (0-7 finisher thread 0, 8-12 streamer thread 128)"""
     from qpnet_b200 import _lib, ops
     nphase, nev = L + 4, 13
     n = 8 * nphase * nev
@@ -31,38 +31,40 @@ def fold2_trace(m, args, d64, L):
     M = ops.max_ceil(d64)
     fn(m._arch, args.utts, M, ws.data_ptr(), ws.numel(), buf, n, None)
     tr = np.array(buf, dtype=np.int64).reshape(8, nphase, nev)
-    names = ["blk0  "] + [f"fuse{j:02d}" for j in range(1, L)] + ["final ", "head1 ", "head2 ", "sample"]
-    labels = ["poll", "barrierA", "mma", "send", "dsmem", "pubZ", "pubX"]
+    names = ["blk0  "] + [f"fuse{j:02d}" for j in range(1, L)] + ["final ", "head1 ", "head2 "]
+    labels = ["poll", "bar", "gateMMA", "send", "res+H+wait", "pubZ", "rest"]
     for st in range(1, 3):
         print(f"--- step {args.step + st}: total {tr[st + 1, 0, 0] - tr[st, 0, 0]} cycles")
         for ph in range(nphase - 1):
             e = tr[st, ph]
-            nxt = tr[st, ph + 1, 0]
+            nxt = tr[st, ph + 1, 0] if ph + 1 < nphase - 1 else tr[st + 1, 0, 0]
             if ph == 0:
                 print(f"{names[ph]} symbols {e[1] - e[0]:6d}  pubZ {e[6] - e[1]:6d}  tables {e[7] - e[6]:5d}  gap {nxt - e[7]:5d}")
             elif ph < L:
-                print(names[ph] + " " + "  ".join(f"{lab} {e[i + 1] - e[i]:5d}" for i, lab in enumerate(labels))
-                      + f"  | late: barrierB {e[8] - e[7]:5d} E {e[9] - e[8]:5d} gap {nxt - e[9]:5d}"
-                      + f"  | streamer vs start: sentR {e[10] - e[0]:5d} issued {e[11] - e[0]:5d} [z pub {e[6] - e[0]:5d}] barrierB {e[8] - e[0]:5d} done {e[12] - e[0]:5d}")
+                print(names[ph] + " " + "  ".join(f"{lab} {e[i + 1] - e[i]:5d}" for i, lab in enumerate(labels)) + f"  gap {nxt - e[7]:5d}"
+                      + f"  | streamer vs finisher start: staged {e[8] - e[0]:6d} Esent {e[9] - e[0]:6d} ring {e[10] - e[0]:6d} xpub {e[11] - e[0]:6d} issued {e[12] - e[0]:6d}")
             elif ph == L:
-                print(f"{names[ph]} poll {e[1] - e[0]:5d}  barrierA {e[2] - e[1]:5d}  skip published {e[7] - e[2]:5d}  barrierB {e[8] - e[7]:5d}  E {e[9] - e[8]:5d} gap {nxt - e[9]:5d}")
+                print(f"{names[ph]} poll {e[1] - e[0]:5d}  bar {e[2] - e[1]:5d}  rest {e[7] - e[2]:5d}  gap {nxt - e[7]:5d}"
+                      + f"  | streamer: staged {e[8] - e[0]:6d} Esent {e[9] - e[0]:6d} ring {e[10] - e[0]:6d} skip pub {e[11] - e[0]:6d}")
             else:
-                print(f"{names[ph]} poll {e[1] - e[0]:5d}  barrier {e[2] - e[1]:5d}  mma {e[3] - e[2]:5d}  send {e[4] - e[3]:5d}  finish {e[7] - e[4]:5d}  gap {nxt - e[7]:5d}")
-    crit = np.zeros(7)
-    late = np.zeros(3)
+                print(f"{names[ph]} poll {e[1] - e[0]:5d}  bar {e[2] - e[1]:5d}  mma {e[3] - e[2]:5d}  send {e[4] - e[3]:5d}  finish {e[7] - e[4]:5d}  gap {nxt - e[7]:5d}")
+    crit = np.zeros(8)
+    strm = np.zeros(5)
     for st in range(1, 7):
         for ph in range(1, L):
             e = tr[st, ph]
-            crit += [e[i + 1] - e[i] for i in range(7)]
-            late += [e[8] - e[7], e[9] - e[8], tr[st, ph + 1, 0] - e[9]]
+            crit[:7] += [e[i + 1] - e[i] for i in range(7)]
+            crit[7] += tr[st, ph + 1, 0] - e[7]
+            strm += [e[9] - e[8], e[10] - e[9], e[11] - e[10], e[12] - e[11], (tr[st, ph + 1, 8] - e[12]) if ph + 1 <= L else 0]
     crit /= 6 * (L - 1)
-    late /= 6 * (L - 1)
-    print("fused phases, mean over 6 steps:", "  ".join(f"{lab} {crit[i]:.0f}" for i, lab in enumerate(labels)),
-          " | late: barrierB %.0f  E %.0f  gap %.0f" % tuple(late), " total/phase %.0f" % (crit.sum() + late.sum()))
+    strm /= 6 * (L - 1)
+    print("finisher, fused phases, mean over 6 steps:", "  ".join(f"{lab} {crit[i]:.0f}" for i, lab in enumerate(labels + ["gap"])),
+          " total/phase %.0f" % crit.sum())
+    print("streamer, fused phases: staged->Esent %.0f  ->ring stored %.0f  ->x published %.0f  ->tile requested %.0f  ->next staged %.0f" % tuple(strm))
     tot = [tr[st + 1, 0, 0] - tr[st, 0, 0] for st in range(1, 7)]
     tail = [tr[st + 1, 0, 0] - tr[st, L, 0] for st in range(1, 7)]
     head = [tr[st, 1, 0] - tr[st, 0, 0] for st in range(1, 7)]
-    print("step total (mean):", np.mean(tot), " block 0 incl. symbol wait:", np.mean(head), " final+head+sampling:", np.mean(tail))
+    print("step total (mean):", np.mean(tot), " block 0 incl. symbol wait:", np.mean(head), " final+heads:", np.mean(tail))
 
 
 def fold_trace(m, args, d64, L):
