@@ -66,7 +66,7 @@ constexpr int MAXL = 16;
 constexpr int RINGF = 4 * 512;               // floats per CTA per ring slot
 // trace events, CTA 0.  thread 0 (finisher): 0 start, 1 z pieces fresh, 2 finisher barrier passed, 3 gate MMA done, 4 gate
 // partials sent, 5 gate + E partials arrived, 6 z published, 7 phase done.  thread 128 (streamer): 8 x staged + tile landed,
-// 9 E sent, 10 ring stored, 11 x published, 12 next tile requested
+// 9 E sent, 10 x published, 11 next tile requested, 12 ring stored (phase done)
 constexpr int TRACE_EVENTS = 13;
 enum { K_FUSED = 0, K_FINAL = 1, K_HEAD1 = 2, K_HEAD2 = 3 };
 
@@ -99,7 +99,8 @@ static int pow2_above(int v) { int q = 1; while (q <= v) q <<= 1; return q; }
 
 bool supported(const QpArch* a, int B) {
   if (a->n_resch != C || a->n_skipch != S || a->n_quantize != Q || a->n_aux > AP) return false;
-  if (a->n_fixed + a->n_adaptive > MAXL || a->n_fixed + a->n_adaptive < 4 || a->n_fixed < 1 || a->dil_fixed[0] != 1) return false;
+  // n_fixed >= 3: blocks 1 and 2 (whose past-tap tiles are requested during the previous step) must have fixed look-backs
+  if (a->n_fixed + a->n_adaptive > MAXL || a->n_fixed + a->n_adaptive < 4 || a->n_fixed < 3 || a->dil_fixed[0] != 1) return false;
   return B >= 1 && B <= UB;
 }
 
@@ -726,13 +727,10 @@ __global__ void __launch_bounds__(NT, 1) f2_gen_kernel(Plan p, GenArgsDev g) {
           send(acc, sRecvG, gb, barG);
           trace(t, j, 4);
         }
-        // while the gate partial tiles travel: res / skip rows of block j-1 (finished by the streaming warps) ...
+        // while the gate partial tiles travel: res / skip rows of block j-1 (finished by the streaming warps)
         zero(acc);
         kloop(K4(), acc, aq, Wrk + brow * PS + bcol + kh * (KS / 2));
         send(acc, sRecvR, rb, barR0 + 8 * rb);
-        // ... and the part of the NEXT gate that z_{j-1} already determines
-        zero(carry);
-        if (j <= L - 2) kloop(K4(), carry, aq, Wtop + brow * PT2 + bcol + KS + kh * (KS / 2));
         if (fused) {
           float s0, s1, e0 = 0.f, e1 = 0.f;
           gather(sRecvG, gb, barG, (gpar >> gb) & 1u, s0, s1);
@@ -751,6 +749,9 @@ __global__ void __launch_bounds__(NT, 1) f2_gen_kernel(Plan p, GenArgsDev g) {
           trace(t, j, 6);
           have_e = false;
         }
+        // the part of the NEXT gate that z_{j-1} already determines, while z_j travels
+        zero(carry);
+        if (j <= L - 2) kloop(K4(), carry, aq, Wtop + brow * PT2 + bcol + KS + kh * (KS / 2));
         if (makes_e_of(t, j)) have_e = true;
         ++nf; ++mf;
         trace(t, j, 7);
@@ -832,6 +833,7 @@ __global__ void __launch_bounds__(NT, 1) f2_gen_kernel(Plan p, GenArgsDev g) {
     // The past-tap partial tiles are those the E part needs: block j+1 of the same step (j <= L-2), or block 1 of the
     // next step (j == L).
     int pf_t = -L, pf_i = 0, pf_slot = 0;   // cursor of the next tile to fetch
+    double dstep[4] = {1.0, 1.0, 1.0, 1.0};   // d[u][t] of this thread's four utterances (u = (lane >> 2) + 8m) for the current step
     auto issue_next_tile = [&]() {
       if (pf_t < g.max_steps) {
         unsigned char* dst = sWS + pf_slot * SSLOT;
@@ -856,21 +858,13 @@ __global__ void __launch_bounds__(NT, 1) f2_gen_kernel(Plan p, GenArgsDev g) {
             int k[4];
 #pragma unroll
             for (int m = 0; m < 4; ++m) k[m] = p.dil[gl];
-            if (gl >= p.nF) {   // pitch-dependent look-back of this step (qpnet.py:476-483, 613-624); loads batched
-              double dd[4];
-#pragma unroll
-              for (int m = 0; m < 4; ++m) {
-                const int u = (ln >> 2) + 8 * m;
-                dd[m] = 0.0;
-                if (u < B)
-                  dd[m] = g.d_is_f64 ? ((const double*)g.d)[(long long)u * ldd + tt]
-                                     : (double)((const float*)g.d)[(long long)u * ldd + tt];
-              }
+            if (gl >= p.nF) {   // pitch-dependent look-back of this step (qpnet.py:476-483, 613-624): d[u][tt] was loaded at the
+                                // start of step tt (every adaptive block of a step shares it; their tiles are requested inside it)
 #pragma unroll
               for (int m = 0; m < 4; ++m) {
                 const int u = (ln >> 2) + 8 * m;
                 int kk = 0;
-                if (u < B) kk = g.d_is_f64 ? -gen_index_f64(dd[m], p.dil[gl]) : -gen_index_f32((float)dd[m], p.dil[gl]);
+                if (u < B) kk = g.d_is_f64 ? -gen_index_f64(dstep[m], p.dil[gl]) : -gen_index_f32((float)dstep[m], p.dil[gl]);
                 if (kk <= 0 || kk > p.depth[gl]) kk = p.depth[gl];   // k == 0: python index 0 = oldest entry (C4)
                 k[m] = kk;
               }
@@ -896,6 +890,13 @@ __global__ void __launch_bounds__(NT, 1) f2_gen_kernel(Plan p, GenArgsDev g) {
       const unsigned tagn = (unsigned)(t + L) & 1u;
       // ---------------------------------------------------------------- block 0: the fp32 residual stream of the owned
       // channels restarts from the causal layer x_0; skip sums restart
+      if (t >= 0) {
+#pragma unroll
+        for (int m = 0; m < 4; ++m) {
+          const int u = (lane >> 2) + 8 * m;
+          if (u < B) dstep[m] = g.d_is_f64 ? ((const double*)g.d)[(long long)u * ldd + t] : (double)((const float*)g.d)[(long long)u * ldd + t];
+        }
+      }
       step_symbols(t);
       {
         const int c_ = __shfl_sync(0xffffffffu, sy_c, fu), a_ = __shfl_sync(0xffffffffu, sy_p1, fu);
@@ -915,79 +916,38 @@ __global__ void __launch_bounds__(NT, 1) f2_gen_kernel(Plan p, GenArgsDev g) {
           mbar_expect_tx(barR0 + 8 * rb, NPART * 512);
           if (makes_e) mbar_expect_tx(barE0 + 8 * eb, NPART * 512);
         }
-        // every streaming warp is done with the previous phase: its x tile and the other weight slot may be overwritten
+        // every streaming warp is done with the previous phase: its x tile may be overwritten
         asm volatile("bar.sync 4, 128;\n" ::: "memory");
-        issue_next_tile();   // next phase's tile into the other slot
         const bool need_x = j >= 2;   // x_{j-1} was published during phase j-1; block 0's x_0 never travels (tables)
         if (need_x) poll512(p.vx, j - 1, tagn, sAx);
-        cp_async_wait<1>();                                            // the past tiles of this phase's slot
+        cp_async_wait<0>();                                            // the past tiles of this phase's slot
         mbar_wait(barTS0 + 8 * slot_i, (unsigned)(ms >> 1) & 1u);      // and its weight tile have landed
         asm volatile("bar.sync 4, 128;\n" ::: "memory");
         trace(t, j, 8);
         const unsigned char* slot = sWS + slot_i * SSLOT;
         const __nv_bfloat16* Wc = (const __nv_bfloat16*)slot;
         const __nv_bfloat16* Wp = Wc + NR * PS;
-        // E for gate block gl (past-tap partial tiles + Wc_gl x_{j-1}) and the ring rows P_{j-1}(t) = Wp_{j-1} x_{j-1}(t)
-        // share the activation fragments
-        float acc[2][2][4], acce[2][2][4];
-        zero(acc);
-        zero(acce);
+        const __nv_bfloat16* aq = sAx + lrow + kh * (KS / 2);
+        float acc[2][2][4];
+        // ---- E for gate block gl: past-tap partial tiles + Wc_gl x_{j-1} -> owners (the finishers of the next phase wait for it)
         if (makes_e) {
+          zero(acc);
           const int tt = fused ? t : t + 1;
           if (tt > -L) {
             const float4* pin = (const float4*)(slot + ST_B) + w4 * 128 + lane;
 #pragma unroll
             for (int m = 0; m < 4; ++m) {
               const float4 q = pin[m * 32];
-              acce[0][m >> 1][(m & 1) * 2] = q.x; acce[0][m >> 1][(m & 1) * 2 + 1] = q.y;
-              acce[1][m >> 1][(m & 1) * 2] = q.z; acce[1][m >> 1][(m & 1) * 2 + 1] = q.w;
+              acc[0][m >> 1][(m & 1) * 2] = q.x; acc[0][m >> 1][(m & 1) * 2 + 1] = q.y;
+              acc[1][m >> 1][(m & 1) * 2] = q.z; acc[1][m >> 1][(m & 1) * 2 + 1] = q.w;
             }
           }
+          if (need_x && fused) kloop(K4(), acc, aq, Wc + brow * PS + bcol + kh * (KS / 2));   // Wc_{j+1} x_{j-1}
+          send(acc, sRecvE, eb, barE0 + 8 * eb);
+          ++ep;
         }
-        if (need_x) {
-          const __nv_bfloat16* aq = sAx + lrow + kh * (KS / 2);
-          const __nv_bfloat16* be = Wc + brow * PS + bcol + kh * (KS / 2);   // Wc_{j+1}
-          const __nv_bfloat16* bq = Wp + brow * PS + bcol + kh * (KS / 2);   // Wp_{j-1}
-          const bool with_e = makes_e && fused;
-#pragma unroll
-          for (int ks = 0; ks < KS / 32; ++ks) {
-            unsigned b0, b1, b2, b3, a0, a1, a2, a3, c0, c1, c2, c3;
-            ldmatrix_x4(a0, a1, a2, a3, aq + ks * 16);
-            ldmatrix_x4(c0, c1, c2, c3, aq + 16 * PA + ks * 16);
-            ldmatrix_x4(b0, b1, b2, b3, bq + ks * 16);
-            mma_bf16(acc[0][0], a0, a1, a2, a3, b0, b1);
-            mma_bf16(acc[1][0], a0, a1, a2, a3, b2, b3);
-            mma_bf16(acc[0][1], c0, c1, c2, c3, b0, b1);
-            mma_bf16(acc[1][1], c0, c1, c2, c3, b2, b3);
-            if (with_e) {
-              ldmatrix_x4(b0, b1, b2, b3, be + ks * 16);
-              mma_bf16(acce[0][0], a0, a1, a2, a3, b0, b1);
-              mma_bf16(acce[1][0], a0, a1, a2, a3, b2, b3);
-              mma_bf16(acce[0][1], c0, c1, c2, c3, b0, b1);
-              mma_bf16(acce[1][1], c0, c1, c2, c3, b2, b3);
-            }
-          }
-        }
-        if (makes_e) { send(acce, sRecvE, eb, barE0 + 8 * eb); ++ep; }
         trace(t, j, 9);
-        if (need_x) {
-          // ring rows kept un-reduced in fragment order for step t + k.  Priming passes write slot 0; the last one
-          // fills the whole ring.
-          float* ringf = p.ring[j - 1];
-          const int rs = p.ring_size[j - 1];
-          const size_t slot_f4 = (size_t)NOWN * (RINGF / 4);
-          float4* r0 = (float4*)(ringf + (size_t)s * RINGF + w4 * 512) + lane;
-          const int sl0 = prime ? 0 : (t & (rs - 1)), sl1 = prime ? (t == -1 ? rs : 1) : sl0 + 1;
-          for (int sl = sl0; sl < sl1; ++sl) {
-            float4* r1 = r0 + sl * slot_f4;
-#pragma unroll
-            for (int m = 0; m < 4; ++m)
-              r1[m * 32] = make_float4(acc[0][m >> 1][(m & 1) * 2], acc[0][m >> 1][(m & 1) * 2 + 1],
-                                       acc[1][m >> 1][(m & 1) * 2], acc[1][m >> 1][(m & 1) * 2 + 1]);
-          }
-        }
-        trace(t, j, 10);
-        // res / skip rows of block j-1 (the finishers' tiles): finish, publish x_j (consumed by phase j+1)
+        // ---- res / skip rows of block j-1 (the finishers' tiles): finish, publish x_j (consumed by phase j+1)
         {
           float s0, s1;
           gather(sRecvR, rb, barR0 + 8 * rb, (rpar >> rb) & 1u, s0, s1);
@@ -1005,7 +965,28 @@ __global__ void __launch_bounds__(NT, 1) f2_gen_kernel(Plan p, GenArgsDev g) {
               st_strong_u32(p.v256 + (size_t)s * UB + fu, pack_tagged(fmaxf(sk0, 0.f), fmaxf(sk1, 0.f), (unsigned)t & 1u));
           }
         }
+        trace(t, j, 10);
+        // ---- next phase's tile into the other slot (last read in the previous phase; every warp is past this phase's barrier)
+        issue_next_tile();
         trace(t, j, 11);
+        // ---- ring rows P_{j-1}(t) = Wp_{j-1} . x_{j-1}(t) over this CTA's K-share, kept un-reduced in fragment order for
+        // step t + k.  Priming passes write slot 0; the last one fills the whole ring.
+        if (need_x) {
+          zero(acc);
+          kloop(K4(), acc, aq, Wp + brow * PS + bcol + kh * (KS / 2));
+          float* ringf = p.ring[j - 1];
+          const int rs = p.ring_size[j - 1];
+          const size_t slot_f4 = (size_t)NOWN * (RINGF / 4);
+          float4* r0 = (float4*)(ringf + (size_t)s * RINGF + w4 * 512) + lane;
+          const int sl0 = prime ? 0 : (t & (rs - 1)), sl1 = prime ? (t == -1 ? rs : 1) : sl0 + 1;
+          for (int sl = sl0; sl < sl1; ++sl) {
+            float4* r1 = r0 + sl * slot_f4;
+#pragma unroll
+            for (int m = 0; m < 4; ++m)
+              r1[m * 32] = make_float4(acc[0][m >> 1][(m & 1) * 2], acc[0][m >> 1][(m & 1) * 2 + 1],
+                                       acc[1][m >> 1][(m & 1) * 2], acc[1][m >> 1][(m & 1) * 2 + 1]);
+          }
+        }
         if (j == 1) {
           // h_up[:, ta] = h[:, ta / U] * w[ta % U] + b (qpnet.py:143-158, 451) for the NEXT step
           const int tn = t + 1;

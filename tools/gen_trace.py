@@ -42,10 +42,10 @@ def fold2_trace(m, args, d64, L):
                 print(f"{names[ph]} symbols {e[1] - e[0]:6d}  pubZ {e[6] - e[1]:6d}  tables {e[7] - e[6]:5d}  gap {nxt - e[7]:5d}")
             elif ph < L:
                 print(names[ph] + " " + "  ".join(f"{lab} {e[i + 1] - e[i]:5d}" for i, lab in enumerate(labels)) + f"  gap {nxt - e[7]:5d}"
-                      + f"  | streamer vs finisher start: staged {e[8] - e[0]:6d} Esent {e[9] - e[0]:6d} ring {e[10] - e[0]:6d} xpub {e[11] - e[0]:6d} issued {e[12] - e[0]:6d}")
+                      + f"  | streamer vs finisher start: staged {e[8] - e[0]:6d} Esent {e[9] - e[0]:6d} xpub {e[10] - e[0]:6d} issued {e[11] - e[0]:6d} done {e[12] - e[0]:6d}")
             elif ph == L:
                 print(f"{names[ph]} poll {e[1] - e[0]:5d}  bar {e[2] - e[1]:5d}  rest {e[7] - e[2]:5d}  gap {nxt - e[7]:5d}"
-                      + f"  | streamer: staged {e[8] - e[0]:6d} Esent {e[9] - e[0]:6d} ring {e[10] - e[0]:6d} skip pub {e[11] - e[0]:6d}")
+                      + f"  | streamer: staged {e[8] - e[0]:6d} Esent {e[9] - e[0]:6d} skip pub {e[10] - e[0]:6d} done {e[12] - e[0]:6d}")
             else:
                 print(f"{names[ph]} poll {e[1] - e[0]:5d}  bar {e[2] - e[1]:5d}  mma {e[3] - e[2]:5d}  send {e[4] - e[3]:5d}  finish {e[7] - e[4]:5d}  gap {nxt - e[7]:5d}")
     crit = np.zeros(8)
@@ -60,7 +60,7 @@ def fold2_trace(m, args, d64, L):
     strm /= 6 * (L - 1)
     print("finisher, fused phases, mean over 6 steps:", "  ".join(f"{lab} {crit[i]:.0f}" for i, lab in enumerate(labels + ["gap"])),
           " total/phase %.0f" % crit.sum())
-    print("streamer, fused phases: staged->Esent %.0f  ->ring stored %.0f  ->x published %.0f  ->tile requested %.0f  ->next staged %.0f" % tuple(strm))
+    print("streamer, fused phases: staged->Esent %.0f  ->x published %.0f  ->tile requested %.0f  ->ring stored %.0f  ->next staged %.0f" % tuple(strm))
     tot = [tr[st + 1, 0, 0] - tr[st, 0, 0] for st in range(1, 7)]
     tail = [tr[st + 1, 0, 0] - tr[st, L, 0] for st in range(1, 7)]
     head = [tr[st, 1, 0] - tr[st, 0, 0] for st in range(1, 7)]
