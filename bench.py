@@ -299,17 +299,19 @@ def main():
 
     # ---------------- roofline of the dominant kernel (persistent generator) ----------------
     peak, peak_src = peaks()
-    steps_per_launch = max_n + 1                       # + the priming step
+    steps_per_launch = max_n + 16                      # + the 16 priming passes of the folded generator
     bytes_per_launch = steps_per_launch * (ALG_WEIGHT_BYTES + n_utts * ALG_STATE_BYTES)
     kernel_s = (sum(dev_ms) / len(dev_ms)) / 1e3       # events bracket pack + generator; generator is > 99.9 %
     achieved = bytes_per_launch / kernel_s / 1e9
     tps = ncu_traffic_per_step()
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": (tps * steps_per_launch if tps is not None else None), "peak_source": peak_src,
-                "kernel": "qp::cl::cl_gen_kernel (cluster generator)" if n_utts <= 32 else "qp::gen_kernel (generic)",
+                "kernel": ("qp::f2::f2_gen_kernel (two-level folded cluster generator)" if n_utts <= 32
+                           else "qp::gen_kernel (generic)"),
                 "us_per_sample_step": kernel_s / steps_per_launch * 1e6,
-                "note": "SURVEY.md 8(d) models the step as weight-bandwidth bound; ncu shows the weights L2-resident and the "
-                        "step bound by the chain of 35 cross-SM exchanges (profiles/r01e_*), so frac is small by construction",
+                "note": "SURVEY.md 8(d) models the step as weight-bandwidth bound (47.25 MB of bf16 weights per step); ncu "
+                        "shows the packed weights L2-resident and the step bound by the chain of 20 cross-SM exchanges "
+                        "(16 blocks + skip + 2 head layers + sampling, profiles/r01h_*), so frac is small by construction",
                 "algorithmic_bytes_per_step": ALG_WEIGHT_BYTES + n_utts * ALG_STATE_BYTES}
 
     cpu = None

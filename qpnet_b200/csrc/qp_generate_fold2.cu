@@ -371,10 +371,30 @@ __global__ void table_kernel(TensorMap tm, Plan p, const float* const* __restric
   }
 }
 
+// L2 eviction policies: the 88 MB of packed weights are re-read every step and should stay in the 126 MB L2
+// (evict_last); the past-tap rings stream through once per look-back (evict_first)
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;\n" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;\n" : "=l"(pol));
+  return pol;
+}
 // global -> shared bulk copy (bytes % 16 == 0), completes on an mbarrier of this CTA
-__device__ __forceinline__ void bulk_g2s(unsigned dst, const void* src, unsigned bytes, unsigned bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n"
-               ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+__device__ __forceinline__ void bulk_g2s(unsigned dst, const void* src, unsigned bytes, unsigned bar, uint64_t pol) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;\n"
+               ::"r"(dst), "l"(src), "r"(bytes), "r"(bar), "l"(pol) : "memory");
+}
+__device__ __forceinline__ void cp_async16_hint(void* smem, const void* gmem, uint64_t pol) {
+  unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;\n" ::"r"(sa), "l"(gmem), "l"(pol) : "memory");
+}
+__device__ __forceinline__ void st_v4_hint(float4* p, float4 v, uint64_t pol) {
+  asm volatile("st.global.L2::cache_hint.v4.f32 [%0], {%1,%2,%3,%4}, %5;\n"
+               ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w), "l"(pol) : "memory");
 }
 
 struct SmemMap {   // byte offsets into the dynamic shared memory
@@ -447,6 +467,7 @@ __global__ void __launch_bounds__(NT, 1) f2_gen_kernel(Plan p, GenArgsDev g) {
   const int w4 = warp & 3, ntp = w4 & 1, kh = w4 >> 1;   // tile of this warp: rows 16*ntp.., K-half kh of the 128-share
   const int fu = q4 + 8 * w4;                   // utterance this thread finishes (gate rows: finishers, res / skip rows: streamers)
   const int t128 = tid & 127;                   // index inside the role
+  const uint64_t pol_keep = l2_policy_evict_last(), pol_stream = l2_policy_evict_first();
 
   // ---- one-time staging ---------------------------------------------------------------
   for (int e = tid; e < sm.total / 16; e += NT) ((uint4*)smem)[e] = make_uint4(0, 0, 0, 0);
@@ -616,7 +637,7 @@ __global__ void __launch_bounds__(NT, 1) f2_gen_kernel(Plan p, GenArgsDev g) {
 
   if (finisher) {
     // ======================================================================================= finishers
-    float2 tb1 = make_float2(0.f, 0.f), tb2 = make_float2(0.f, 0.f);   // Wc_1 . x_0 and Wc_2 . x_0 of (fu, rows 2*i4, +1)
+    float2 tu1 = make_float2(0.f, 0.f), tv1 = tu1, tu2 = tu1, tv2 = tu1;   // Wc_1 . x_0 = tu1 + tv1 and Wc_2 . x_0 = tu2 + tv2 of (fu, rows 2*i4, +1)
     float carry[2][2][4];                // H_{j+1} z_{j-1} of this warp's tile, added to the next gate tile
     zero(carry);
     int nf = 0;                          // finisher phases so far: z tile = nf & 1
@@ -635,7 +656,7 @@ __global__ void __launch_bounds__(NT, 1) f2_gen_kernel(Plan p, GenArgsDev g) {
       if (tid == 0 && pf_t < g.max_steps) {
         const unsigned bar = barTF0 + 8 * pf_slot;
         mbar_expect_tx(bar, FT_B);
-        bulk_g2s(smem_u32(sWF + pf_slot * FT_B), p.Wf + ((size_t)pf_i * NOWN + s) * FT_E, FT_B, bar);
+        bulk_g2s(smem_u32(sWF + pf_slot * FT_B), p.Wf + ((size_t)pf_i * NOWN + s) * FT_E, FT_B, bar, pol_keep);
         if (++pf_i == L) { pf_i = 0; ++pf_t; }
       }
       pf_slot ^= 1;
@@ -683,10 +704,8 @@ __global__ void __launch_bounds__(NT, 1) f2_gen_kernel(Plan p, GenArgsDev g) {
         trace(t, 0, 6);
         // off the critical path: the x_0 terms of blocks 1 and 2
         const float* T = p.T12 + (size_t)s * 4 * Q * 8 + 2 * i4;
-        const float2 u1 = __ldg((const float2*)(T + (0 * Q + c_) * 8)), v1 = __ldg((const float2*)(T + (1 * Q + a_) * 8));
-        const float2 u2 = __ldg((const float2*)(T + (2 * Q + c_) * 8)), v2 = __ldg((const float2*)(T + (3 * Q + a_) * 8));
-        tb1 = make_float2(u1.x + v1.x, u1.y + v1.y);
-        tb2 = make_float2(u2.x + v2.x, u2.y + v2.y);
+        tu1 = __ldg((const float2*)(T + (0 * Q + c_) * 8)); tv1 = __ldg((const float2*)(T + (1 * Q + a_) * 8));   // summed at their first
+        tu2 = __ldg((const float2*)(T + (2 * Q + c_) * 8)); tv2 = __ldg((const float2*)(T + (3 * Q + a_) * 8));   // use: the loads stay in flight
       }
       trace(t, 0, 7);
 
@@ -743,8 +762,8 @@ __global__ void __launch_bounds__(NT, 1) f2_gen_kernel(Plan p, GenArgsDev g) {
             ++ec;
           }
           trace(t, j, 5);
-          if (j == 1) { e0 += tb1.x; e1 += tb1.y; }
-          if (j == 2) { e0 += tb2.x; e1 += tb2.y; }
+          if (j == 1) { e0 += tu1.x + tv1.x; e1 += tu1.y + tv1.y; }
+          if (j == 2) { e0 += tu2.x + tv2.x; e1 += tu2.y + tv2.y; }
           publish_gate(j, s0 + e0 + a0_, s1 + e1 + a1_, tagn);
           trace(t, j, 6);
           have_e = false;
@@ -841,7 +860,7 @@ __global__ void __launch_bounds__(NT, 1) f2_gen_kernel(Plan p, GenArgsDev g) {
         const int j = pf_i + 1;
         if (t128 == 0) {
           mbar_expect_tx(bar, ST_B);
-          bulk_g2s(smem_u32(dst), p.Ws + ((size_t)pf_i * NOWN + s) * ST_E, ST_B, bar);
+          bulk_g2s(smem_u32(dst), p.Ws + ((size_t)pf_i * NOWN + s) * ST_E, ST_B, bar, pol_keep);
         }
         const int gl = j == L ? 1 : j + 1;          // gate block whose past tap the E part of phase j seeds
         const int tt = j == L ? pf_t + 1 : pf_t;    // its step
@@ -874,8 +893,8 @@ __global__ void __launch_bounds__(NT, 1) f2_gen_kernel(Plan p, GenArgsDev g) {
           }
 #pragma unroll
           for (int m = 0; m < 4; ++m)
-            cp_async16(dst + ST_B + ((w * 4 + m) * 32 + ln) * 16,
-                       ringf + ((size_t)slot[m] * NOWN + s) * RINGF + w * 512 + (m * 32 + ln) * 4);
+            cp_async16_hint(dst + ST_B + ((w * 4 + m) * 32 + ln) * 16,
+                            ringf + ((size_t)slot[m] * NOWN + s) * RINGF + w * 512 + (m * 32 + ln) * 4, pol_stream);
         }
         ++pf_i;
         if (pf_i == L) { pf_i = 0; ++pf_t; }
@@ -983,8 +1002,8 @@ __global__ void __launch_bounds__(NT, 1) f2_gen_kernel(Plan p, GenArgsDev g) {
             float4* r1 = r0 + sl * slot_f4;
 #pragma unroll
             for (int m = 0; m < 4; ++m)
-              r1[m * 32] = make_float4(acc[0][m >> 1][(m & 1) * 2], acc[0][m >> 1][(m & 1) * 2 + 1],
-                                       acc[1][m >> 1][(m & 1) * 2], acc[1][m >> 1][(m & 1) * 2 + 1]);
+              st_v4_hint(r1 + m * 32, make_float4(acc[0][m >> 1][(m & 1) * 2], acc[0][m >> 1][(m & 1) * 2 + 1],
+                                                  acc[1][m >> 1][(m & 1) * 2], acc[1][m >> 1][(m & 1) * 2 + 1]), pol_stream);
           }
         }
         if (j == 1) {

@@ -413,6 +413,39 @@ def test_generator_utterance_groups_vs_oracle(dev, monkeypatch, kw, B, groups):
     assert float(err.max()) < 0.06, err
 
 
+@pytest.mark.parametrize("fac", [1.0, 0.5, 1.5])
+def test_generator_full_model_every_kernel_vs_oracle(dev, monkeypatch, fac):
+    """SI default architecture on every generator kernel (QPNET_GEN_KERNEL = fold2 | fold | cluster | generic), with the
+    F0 contour scaled x0.5 / x1.5 (BASELINE configs[2]: longest and shortest pitch-dependent look-backs, ring depth up to
+    8 * ceil(max d)).  Teacher-forced per-step logits against the CPU oracle, 0.06 absolute; the steps run past the
+    look-back of the first adaptive blocks so the rings are read back, not only primed."""
+    a = orc.Arch()
+    p = orc.init_params(a, 33, 0.05)
+    B, frames, steps = 3, 3, 300
+    h = np.zeros((B, a.A, frames), np.float32)
+    d = np.zeros((B, frames * a.U), np.float64)
+    for b in range(B):
+        hs, f0, _ = synth.utterance(frames, 700 + b, fac, a.A)
+        h[b] = hs.T
+        d[b] = cases.d_from_f0(f0)
+    x = torch.full((B, 1), a.Q // 2, dtype=torch.long)
+    forced = torch.from_numpy(np.random.RandomState(11).randint(0, a.Q, size=(B, steps))).long()
+    lg = []
+    with torch.no_grad():
+        orc.generate(a, p, x, torch.from_numpy(h), [steps] * B, d, mode="argmax", force=forced, logits_out=lg,
+                     max_steps=steps)
+    want = torch.stack(lg, dim=1)
+    m = _model({}, p, dev)
+    for kernel in ("fold2", "fold", "cluster", "generic"):
+        monkeypatch.setenv("QPNET_GEN_KERNEL", kernel)
+        res, got = m.batch_fast_generate(x, torch.from_numpy(h), [steps] * B, d, None, "argmax", False, force=forced,
+                                         return_logits=True)
+        err = float((got.cpu() - want).abs().max())
+        print(f"f0 x{fac} kernel {kernel}: max |dlogit| = {err:.4f} (min d {d.min():.2f}, max d {d.max():.2f})")
+        assert err < 0.06, (kernel, err)
+        assert all(len(r) == steps for r in res)
+
+
 # ------------------------------------------------------------------ training step (qpnet_train.py:517-531)
 def test_training_step_matches_reference_adam_update(dev):
     """One Trainer.step against the reference's recipe run on the CPU oracle: CE on the last bl logits,
