@@ -34,6 +34,12 @@ def max_ceil(d: torch.Tensor) -> int:
     return int(out.item())
 
 
+def _ld(t: torch.Tensor) -> int:
+    """Leading stride of a contiguous 2-D tensor.  (For a single row torch keeps whatever stride the tensor was
+    created with -- possibly 0 -- so do not trust ``stride(0)`` there.)"""
+    return t.shape[1] if t.shape[0] <= 1 else t.stride(0)
+
+
 def dilated_index(d: torch.Tensor, dilation: int, flavour: str) -> torch.Tensor:
     """Bit-exact index builders of qpnet.py:592-624.
 
@@ -51,7 +57,7 @@ def dilated_index(d: torch.Tensor, dilation: int, flavour: str) -> torch.Tensor:
         raise ValueError(flavour)
     fn = getattr(lib, "qp_index_" + flavour)
     empty = d.numel() == 0                      # empty / ragged edge case: still goes through the C ABI
-    check(fn(None if empty else d.data_ptr(), B, n, n if empty else d.stride(0), dilation,
+    check(fn(None if empty else d.data_ptr(), B, n, n if empty else _ld(d), dilation,
              None if empty else out.data_ptr(), _stream()))
     return out
 

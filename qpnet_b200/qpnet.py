@@ -222,13 +222,13 @@ class QPNet(nn.Module):
         if uniforms is not None:
             uniforms = uniforms.to(dev).contiguous().float()
             assert uniforms.shape[0] == B and uniforms.shape[1] >= max_n
-            a.uniforms, a.ld_uniforms = uniforms.data_ptr(), uniforms.stride(0)
+            a.uniforms, a.ld_uniforms = uniforms.data_ptr(), ops._ld(uniforms)
         a.philox_seed = int(self.philox_seed)
         if force is not None:
             force = force.to(dev).contiguous().to(torch.int32)
             assert force.shape[0] == B and force.shape[1] >= max_n
-            a.force, a.ld_force = force.data_ptr(), force.stride(0)
-        a.out, a.ld_out = out.data_ptr(), out.stride(0)
+            a.force, a.ld_force = force.data_ptr(), ops._ld(force)
+        a.out, a.ld_out = out.data_ptr(), ops._ld(out)
         logits = None
         if return_logits:
             logits = torch.zeros((B, max_n, self.n_quantize), dtype=torch.float32, device=dev)
