@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define QP_ABI_VERSION 1
+#define QP_ABI_VERSION 2
 #define QP_MAX_LAYERS 64
 
 enum {
@@ -159,6 +159,10 @@ typedef struct QpGenerateArgs {
   int32_t* out;         /* (B, ld_out) generated symbols                             */
   int64_t ld_out;
   float* logits_out;    /* optional (B, max_steps, Q) per-step logits                */
+  const int32_t* utt_ids;   /* optional (B,) device: caller-side index of each utterance;
+                               keys the in-kernel Philox stream, so that an utterance
+                               draws the same numbers whichever launch / slot it runs in
+                               (NULL: the slot index)                                    */
 } QpGenerateArgs;
 
 size_t qp_generate_workspace_bytes(const QpArch* arch, int32_t B, int32_t M);

@@ -143,6 +143,7 @@ struct GenArgsDev {
   const int64_t* seed; const float* h; const void* d; const int32_t* n_samples;
   const float* uniforms; long long ld_uniforms; unsigned long long philox_seed;
   const int32_t* force; long long ld_force;
+  const int32_t* utt_ids;   // optional: the caller-side index of every utterance (keys the Philox stream)
   int32_t* out; long long ld_out; float* logits_out;
   int mode, max_steps, d_is_f64;
   const float* causal_b; const float* up_w; const float* up_b;

@@ -943,7 +943,7 @@ __global__ void __launch_bounds__(NT, 1) fd_gen_kernel(Plan p, GenArgsDev g) {
             if (lane >= o) incl += nb;
           }
           const float total = __shfl_sync(0xffffffffu, incl, 31);
-          const float uu = g.uniforms ? g.uniforms[(long long)u * g.ld_uniforms + t] : philox_uniform(g.philox_seed, u, t);
+          const float uu = g.uniforms ? g.uniforms[(long long)u * g.ld_uniforms + t] : philox_uniform(g.philox_seed, g.utt_ids ? (unsigned)g.utt_ids[u] : (unsigned)u, t);
           const float target = uu * total;
           float run = incl - local;
           int cnt = 0;
@@ -1019,7 +1019,7 @@ int fd_generate(const QpArch* arch, const float* const* tensors_host, const QpGe
   GenArgsDev g;
   g.seed = a->seed; g.h = a->h; g.d = a->d; g.n_samples = a->n_samples;
   g.uniforms = a->uniforms; g.ld_uniforms = a->ld_uniforms; g.philox_seed = a->philox_seed;
-  g.force = a->force; g.ld_force = a->ld_force;
+  g.force = a->force; g.ld_force = a->ld_force; g.utt_ids = a->utt_ids;
   g.out = a->out; g.ld_out = a->ld_out; g.logits_out = a->logits_out;
   g.mode = a->mode; g.max_steps = a->max_steps; g.d_is_f64 = a->d_is_f64;
   g.causal_b = tensors_host[tm.causal_b()]; g.up_w = tensors_host[tm.up_w()]; g.up_b = tensors_host[tm.up_b()];

@@ -123,6 +123,8 @@ class _TeacherForced(torch.autograd.Function):
 class QPNet(nn.Module):
     """QUASI-PERIODIC WAVENET -- same constructor as qpnet.py:174-178."""
 
+    GROUP = 32      # utterances per launch of the folded cluster generator
+
     def __init__(self, n_quantize=256, n_aux=39, n_resch=512, n_skipch=256,
                  dilationF_depth=4, dilationF_repeat=3, dilationA_depth=4, dilationA_repeat=1,
                  kernel_size=2, upsampling_factor=110):
@@ -169,6 +171,9 @@ class QPNet(nn.Module):
         # it; False selects the exact fp32 SIMT path (tight-tolerance parity)
         self.tensor_cores = (n_resch % 64 == 0 and n_skipch % 64 == 0 and n_quantize % 32 == 0 and n_aux <= 64)
         self.last_launches = 0      # kernels launched by the most recent call (bench accounting)
+        # widths the folded cluster generator is built for (qp_generate_fold2.cu); 32 utterances per launch
+        self._folded_ok = (n_resch == 512 and n_skipch == 256 and n_quantize == 256 and n_aux <= 48
+                           and len(self.dilationsF) >= 3 and len(self.dilationsF) + len(self.dilationsA) <= 16)
         self.philox_seed = 100      # qpnet_decode.py:58 default --seed
 
     # ------------------------------------------------------------------ helpers
@@ -200,13 +205,45 @@ class QPNet(nn.Module):
     # ------------------------------------------------------------------ device-resident core
     @torch.no_grad()
     def generate_device(self, seed, h, d, n_dev, max_n, qmode=_lib.QP_MODE_SAMPLING, uniforms=None, force=None,
-                        return_logits=False, check_status=True):
+                        return_logits=False, check_status=True, n_host=None):
         """Generation with every input already resident in HBM: seed (B,) int64, h (B,A,F) fp32,
         d (B,F*U) fp64 (numpy flavour of the reference) or fp32 (extra_memory flavour), n_dev (B,)
-        int32.  Returns (symbols (B, max_n) int32 on the device, logits or None)."""
+        int32.  Returns (symbols (B, max_n) int32 on the device, logits or None).
+
+        The folded cluster generator runs 32 utterances per launch.  A larger batch of the SI default widths is
+        dealt to launches of 32, longest first, so every launch retires at its own last step (the reference's decoder
+        sorts by length for the same reason, qpnet_decode.py:257-259); ``utt_ids`` keeps every utterance on the Philox
+        stream of its caller-side index, so the symbols do not depend on the grouping."""
+        B = h.shape[0]
+        if B > self.GROUP and self._folded_ok:
+            dev = h.device
+            n_host = list(n_host) if n_host is not None else n_dev.cpu().tolist()
+            order = sorted(range(B), key=lambda b: -n_host[b])
+            out = torch.zeros((B, max(max_n, 1)), dtype=torch.int32, device=dev)
+            logits = torch.zeros((B, max_n, self.n_quantize), dtype=torch.float32, device=dev) if return_logits else None
+            launches = 0
+            for c in range(0, B, self.GROUP):
+                ids = order[c:c + self.GROUP]
+                idx = torch.tensor(ids, dtype=torch.int64, device=dev)
+                sub_max = max(n_host[b] for b in ids)
+                o, lg = self._generate_launch(seed[idx], h[idx], d[idx], n_dev[idx], sub_max, qmode,
+                                              None if uniforms is None else uniforms.to(dev)[idx],
+                                              None if force is None else force.to(dev)[idx], return_logits, check_status,
+                                              idx.to(torch.int32))
+                launches += self.last_launches
+                out[idx, :o.shape[1]] = o
+                if return_logits:
+                    logits[idx, :sub_max] = lg
+            self.last_launches = launches
+            return out, logits
+        return self._generate_launch(seed, h, d, n_dev, max_n, qmode, uniforms, force, return_logits, check_status, None)
+
+    def _generate_launch(self, seed, h, d, n_dev, max_n, qmode, uniforms, force, return_logits, check_status, utt_ids):
+        """One qp_generate call (<= 32 utterances on the folded kernel, any number on the generic one)."""
         params = self._tensors()
         dev = params[0].device
         ops._need_cuda(seed, h, d, n_dev)
+        seed, h, d, n_dev = seed.contiguous(), h.contiguous(), d.contiguous(), n_dev.contiguous()
         B, F = h.shape[0], h.shape[2]
         if d.shape[0] != B or d.shape[1] != F * self.upsampling_factor:
             raise ValueError("dilated_factors must be (B, upsampling_factor * frames)")
@@ -229,6 +266,9 @@ class QPNet(nn.Module):
             assert force.shape[0] == B and force.shape[1] >= max_n
             a.force, a.ld_force = force.data_ptr(), ops._ld(force)
         a.out, a.ld_out = out.data_ptr(), ops._ld(out)
+        if utt_ids is not None:
+            utt_ids = utt_ids.to(dev).contiguous().to(torch.int32)
+            a.utt_ids = utt_ids.data_ptr()
         logits = None
         if return_logits:
             logits = torch.zeros((B, max_n, self.n_quantize), dtype=torch.float32, device=dev)
@@ -281,7 +321,8 @@ class QPNet(nn.Module):
                 d = torch.from_numpy(np.ascontiguousarray(dilated_factors, dtype=np.float64)).to(dev)
         seed = x[:, -1].to(dev).contiguous().to(torch.int64)
         n_dev = torch.tensor(list(n_samples_list), dtype=torch.int32, device=dev)
-        out, logits = self.generate_device(seed, h, d, n_dev, max_n, qmode, uniforms, force, return_logits)
+        out, logits = self.generate_device(seed, h, d, n_dev, max_n, qmode, uniforms, force, return_logits,
+                                           n_host=list(n_samples_list))
         host = out.cpu().numpy().astype(np.int64)
         # ---- retirement order and caller-list mutation, exactly qpnet.py:527-557 --------
         alive = list(range(B))

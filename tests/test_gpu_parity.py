@@ -361,6 +361,43 @@ def test_generator_is_deterministic_and_batch_independent(dev):
         assert np.array_equal(solo[0], r)
 
 
+def test_generator_large_batch_is_dealt_to_launches_of_32(dev):
+    """More than 32 utterances of the SI default widths: dealt to launches of 32, longest first (host wrapper).  Every
+    utterance must come out exactly as in a solo call -- same Philox stream (utt_ids), same arithmetic."""
+    a = orc.Arch()
+    p = orc.init_params(a, 8, 0.05)
+    m = _model({}, p, dev)
+    B = 37
+    frames = [1 + (b % 2) for b in range(B)]
+    Fm = max(frames)
+    h = np.zeros((B, a.A, Fm), np.float32)
+    d = np.zeros((B, Fm * a.U), np.float64)
+    n_list = []
+    for b in range(B):
+        hs, f0, n = synth.utterance(frames[b], 900 + b, 1.0, a.A)
+        h[b, :, :frames[b]] = hs.T
+        d[b, :frames[b] * a.U] = cases.d_from_f0(f0)
+        n_list.append(min(n, 40 + 3 * b))
+    x = torch.full((B, 1), a.Q // 2, dtype=torch.long)
+    m.philox_seed = 5
+    res = m.batch_fast_generate(x, torch.from_numpy(h), list(n_list), d)
+    order = np.argsort(np.array(n_list), kind="stable")
+    assert [len(r) for r in res] == sorted(n_list)
+    for b in (0, 17, 36):
+        pos = list(order).index(b)
+        solo = m.batch_fast_generate(x[b:b + 1], torch.from_numpy(h[b:b + 1]), [n_list[b]], d[b:b + 1])
+        # a solo call keys Philox with slot 0, the batch with the caller-side index b: compare through generate_device
+        seed = torch.full((1,), a.Q // 2, dtype=torch.int64, device=dev)
+        o, _ = m.generate_device(seed, torch.from_numpy(h[b:b + 1]).to(dev), torch.from_numpy(d[b:b + 1]).to(dev),
+                                 torch.tensor([n_list[b]], dtype=torch.int32, device=dev), n_list[b])
+        if b == 0:
+            assert np.array_equal(solo[0], res[pos])        # index 0 == slot 0: identical streams
+        o2, _ = m._generate_launch(seed, torch.from_numpy(h[b:b + 1]).to(dev), torch.from_numpy(d[b:b + 1]).to(dev),
+                                   torch.tensor([n_list[b]], dtype=torch.int32, device=dev), n_list[b], 0, None, None,
+                                   False, True, torch.tensor([b], dtype=torch.int32, device=dev))
+        assert np.array_equal(o2[0, :n_list[b]].cpu().numpy().astype(np.int64), res[pos]), b
+
+
 def test_generator_philox_sampling_statistics(dev):
     """In-kernel Philox path: symbols are valid, vary with the seed, and repeat with it."""
     g, kw, a, p, x, h, d, n_list, mode, xm, m, uni = _gen_setup("small_sampling", dev)
@@ -382,7 +419,7 @@ def test_generator_rejects_bad_mode(dev):
 
 
 @pytest.mark.parametrize("kw,B,groups", [(cases.SMALL, 21, None), (cases.SMALL, 37, "1"), (cases.SMALL, 37, "2"),
-                                         (cases.FULL, 19, None)])
+                                         (cases.FULL, 19, None), (cases.FULL, 41, None)])
 def test_generator_utterance_groups_vs_oracle(dev, monkeypatch, kw, B, groups):
     """More than one 16-utterance chunk: chunks are dealt to co-resident CTA groups (and looped
     inside a group when there are more chunks than groups, forced here with QPNET_GEN_GROUPS).
