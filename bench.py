@@ -192,6 +192,7 @@ def main():
     ap.add_argument("--ref-sample-steps", type=int, default=120)
     ap.add_argument("--cpu-sample-steps", type=int, default=200)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-train", action="store_true", help="skip the train seg/s probe")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -292,6 +293,17 @@ def main():
     e2e_value = total_samples_rank * world * args.steps / float(t_e2e.item())
     assert len(res) == n_utts and all(len(r) == n for r, n in zip(res, sorted(n_list)))
 
+    # ---------------- the metric's second half: train seg/s (BASELINE configs[4]), a few data-parallel steps ----------------
+    train = None
+    if not args.no_train:
+        del flush
+        torch.cuda.empty_cache()
+        import importlib.util
+        spec = importlib.util.spec_from_file_location("bench_train", os.path.join(ROOT, "tools", "bench_train.py"))
+        bench_train = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(bench_train)
+        train = bench_train.measure(dev, rank, world, steps=3, warmup=3)
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -332,7 +344,8 @@ def main():
             "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "real_time_factor": e2e_value / FS},
             "gpu_launches": launches,
-            "roofline": roofline, "cpu_baseline": cpu, "wall_s_timed_region": t_wall}
+            "roofline": roofline, "cpu_baseline": cpu, "wall_s_timed_region": t_wall,
+            "train": train}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
