@@ -1,5 +1,6 @@
 // Backward of the teacher-forced stack (what autograd does for the reference around
-// qpnet_train.py:526-531), fp32 exact path.  Consumes the workspace a QP_F_SAVE forward
+// qpnet_train.py:526-531): exact fp32 SIMT contractions, or TF32 tensor-core contractions (fp32 accumulate) when the
+// forward ran on the bf16 tensor-core path (QP_F_BF16).  Consumes the workspace a QP_F_SAVE forward
 // filled.  All contractions reuse the segmented GEMM / weight-gradient kernels.
 #include "qp_gemm_f32.cuh"
 #include "qp_tf_plan.cuh"
@@ -73,8 +74,9 @@ __global__ void upsample_grad_kernel(const float* __restrict__ dHup, const float
   if (threadIdx.x == 0) { dw[j] = r0[0]; atomicAdd(db, r1[0]); }
 }
 
+// tc: TF32 tensor-core contractions (the backward of the bf16 training path); false: exact fp32 SIMT
 int tf_backward_f32(const QpArch* arch, const float* const* tensors, const int64_t* x, const float* h,
-                    const TfPlan& p, const float* dlogits, float* const* grads, cudaStream_t st) {
+                    const TfPlan& p, const float* dlogits, float* const* grads, bool tc, cudaStream_t st) {
   const PackedDims& pd = p.pd;
   const TensorMap tm = tensor_map(arch);
   const int C = pd.C, S = pd.S, Q = pd.Q, A = pd.A, B = p.B, L0 = p.L0, bl = p.bl, L = pd.L;
@@ -89,24 +91,24 @@ int tf_backward_f32(const QpArch* arch, const float* const* tensors, const int64
     w.p[0] = mk(dlogits, (int64_t)bl * Q, Q, nullptr, 0, bl, Q); w.np = 1;
     w.q[0] = mk(p.H1, (int64_t)bl * S, S, nullptr, 0, bl, S, 1); w.nq = 1;
     w.B = B; w.n_rows = bl; w.I = Q; w.J = S; w.out = grads[tm.post2_w()]; w.ldo = S; w.colsum = grads[tm.post2_b()];
-    if (int e = launch_wgrad(w, st)) return e;
+    if (int e = launch_wgrad(w, st, tc)) return e;
     GemmArgs g = {};
     g.seg[0] = mk(dlogits, (int64_t)bl * Q, Q, nullptr, 0, bl, Q); g.nseg = 1;
     g.W = tensors[tm.post2_w()]; g.ldw = S; g.w_kn = 1;
     g.B = B; g.n_rows = bl; g.N = S; g.out = p.dH1; g.out_bstride = (int64_t)bl * S; g.ldo = S;
     g.mask = p.H1; g.mask_bstride = (int64_t)bl * S; g.ldmask = S;
-    if (int e = launch_gemm<EPI_PLAIN>(g, st)) return e;
+    if (int e = launch_gemm<EPI_PLAIN>(g, st, tc)) return e;
     WgradArgs w1 = {};
     w1.p[0] = mk(p.dH1, (int64_t)bl * S, S, nullptr, 0, bl, S); w1.np = 1;
     w1.q[0] = mk(p.skipsum, (int64_t)bl * S, S, nullptr, 0, bl, S, 1); w1.nq = 1;
     w1.B = B; w1.n_rows = bl; w1.I = S; w1.J = S; w1.out = grads[tm.post1_w()]; w1.ldo = S; w1.colsum = grads[tm.post1_b()];
-    if (int e = launch_wgrad(w1, st)) return e;
+    if (int e = launch_wgrad(w1, st, tc)) return e;
     GemmArgs g1 = {};
     g1.seg[0] = mk(p.dH1, (int64_t)bl * S, S, nullptr, 0, bl, S); g1.nseg = 1;
     g1.W = tensors[tm.post1_w()]; g1.ldw = S; g1.w_kn = 1;
     g1.B = B; g1.n_rows = bl; g1.N = S; g1.out = p.dskip; g1.out_bstride = (int64_t)bl * S; g1.ldo = S;
     g1.mask = p.skipsum; g1.mask_bstride = (int64_t)bl * S; g1.ldmask = S;
-    if (int e = launch_gemm<EPI_PLAIN>(g1, st)) return e;
+    if (int e = launch_gemm<EPI_PLAIN>(g1, st, tc)) return e;
   }
   QP_CUDA(cudaMemsetAsync(p.dHup, 0, sizeof(float) * (size_t)B * L0 * A, st));
 
@@ -128,7 +130,7 @@ int tf_backward_f32(const QpArch* arch, const float* const* tensors, const int64
       g.B = B; g.n_rows = n; g.N = C;
       g.gsave = p.G[l]; g.gsave_bstride = (int64_t)n * 2 * C;
       g.out = p.dgate; g.out_bstride = (int64_t)n * 2 * C; g.ldo = 2 * C;
-      if (int e = launch_gemm<EPI_DGATE>(g, st)) return e;
+      if (int e = launch_gemm<EPI_DGATE>(g, st, tc)) return e;
     }
     // d[res | skip] weights and biases
     {
@@ -138,7 +140,7 @@ int tf_backward_f32(const QpArch* arch, const float* const* tensors, const int64
       w.q[0] = mk(p.Z[l], (int64_t)n * C, C, nullptr, 0, n, C); w.nq = 1;
       w.B = B; w.n_rows = n; w.I = C + S; w.J = C;
       w.out = p.dW.Wrs + pd.wrs_elems() * l; w.ldo = C; w.colsum = p.dW.brs + (size_t)(C + S) * l;
-      if (int e = launch_wgrad(w, st)) return e;
+      if (int e = launch_wgrad(w, st, tc)) return e;
     }
     // d gate weights / biases:  dgate^T * [x_past | x_cur | h_up]
     {
@@ -149,7 +151,7 @@ int tf_backward_f32(const QpArch* arch, const float* const* tensors, const int64
       w.q[2] = mk(p.Hup, (int64_t)L0 * A, A, nullptr, L0 - n, L0, A); w.nq = 3;
       w.B = B; w.n_rows = n; w.I = 2 * C; w.J = pd.Kg;
       w.out = p.dW.Wg + pd.wg_elems() * l; w.ldo = pd.Kg; w.colsum = p.dW.bg + (size_t)2 * C * l;
-      if (int e = launch_wgrad(w, st)) return e;
+      if (int e = launch_wgrad(w, st, tc)) return e;
     }
     // dX[l] (scatter: past rows, current rows + residual) and dHup
     {
@@ -162,7 +164,7 @@ int tf_backward_f32(const QpArch* arch, const float* const* tensors, const int64
       g.dx = dX; g.dx_bstride = (int64_t)Lin * C; g.dx_rowmap = rowmap; g.dx_past_off = 0; g.dx_cur_off = sh; g.dx_rows = Lin;
       g.resid = dXnext; g.resid_bstride = (int64_t)n * C; g.ldresid = C;
       g.dh = p.dHup; g.dh_bstride = (int64_t)L0 * A; g.dh_off = L0 - n;
-      if (int e = launch_gemm<EPI_DX>(g, st)) return e;
+      if (int e = launch_gemm<EPI_DX>(g, st, tc)) return e;
       dXnext = dX;
     }
   }
@@ -196,7 +198,7 @@ int qp_backward(const QpArch* arch, const float* const* tensors_host, const int6
   TfPlan p;
   size_t need = make_tf_plan(arch, B, T, F, bl, M, flags, ws, ws_bytes, &p);
   if (need > ws_bytes) return set_error(QP_EWORKSPACE, "backward: workspace %zu < %zu bytes", ws_bytes, need);
-  return tf_backward_f32(arch, tensors_host, x, h, p, dlogits, grads_host, (cudaStream_t)stream);
+  return tf_backward_f32(arch, tensors_host, x, h, p, dlogits, grads_host, (flags & QP_F_BF16) != 0, (cudaStream_t)stream);
 }
 
 }  // extern "C"

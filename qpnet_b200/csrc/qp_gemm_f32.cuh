@@ -7,6 +7,8 @@
 // (past tap rows, current tap rows, aux rows): the 2-tap causal / pitch-adaptive conv is
 // a GEMM whose A rows are *gathered*, never materialised (qpnet.py:295-298,657-666).
 #pragma once
+#include <algorithm>
+
 #include "qp_common.cuh"
 
 namespace qp {
@@ -44,13 +46,66 @@ struct GemmArgs {
 };
 
 constexpr int GM = 64, GN = 64, GK = 16;
+constexpr int GPAD = 8;   // tile pitch GM + 8: the TF32 fragment loads (k = lane % 4, m = lane / 4) hit 32 distinct banks
+
+// ---- TF32 tensor-core inner product (backward of the bf16 training path): the same 64 x 64 x 16 shared tiles,
+// mma.sync.m16n8k8 with fp32 accumulation; warp w owns rows 16 (w & 3).., columns 32 (w >> 2)...  The accumulators
+// go through a shared 64 x 64 tile back into the (ty, tx) 4 x 4 register layout, so every epilogue is shared with the
+// exact fp32 SIMT path.
+__device__ __forceinline__ unsigned to_tf32(float x) {
+  unsigned r;
+  asm("cvt.rna.tf32.f32 %0, %1;\n" : "=r"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ void mma_tf32(float (&c)[4], unsigned a0, unsigned a1, unsigned a2, unsigned a3, unsigned b0, unsigned b1) {
+  asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3]) : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ void tile_mma_tf32(const float (*As)[GM + GPAD], const float (*Ws)[GN + GPAD], float (&c)[4][4]) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int g = lane >> 2, t = lane & 3, m0 = 16 * (warp & 3), n0 = 32 * (warp >> 2);
+#pragma unroll
+  for (int ks = 0; ks < GK; ks += 8) {
+    const unsigned a0 = to_tf32(As[ks + t][m0 + g]), a1 = to_tf32(As[ks + t][m0 + g + 8]);
+    const unsigned a2 = to_tf32(As[ks + t + 4][m0 + g]), a3 = to_tf32(As[ks + t + 4][m0 + g + 8]);
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt) {
+      const unsigned b0 = to_tf32(Ws[ks + t][n0 + nt * 8 + g]), b1 = to_tf32(Ws[ks + t + 4][n0 + nt * 8 + g]);
+      mma_tf32(c[nt], a0, a1, a2, a3, b0, b1);
+    }
+  }
+}
+// fragment layout -> (ty, tx) 4 x 4 layout through shared memory (call from all 256 threads)
+__device__ __forceinline__ void frag_to_blocked(float (*Cs)[GN + 4], const float (&c)[4][4], float (&acc)[4][4]) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int g = lane >> 2, t = lane & 3, m0 = 16 * (warp & 3), n0 = 32 * (warp >> 2);
+#pragma unroll
+  for (int nt = 0; nt < 4; ++nt) {
+    Cs[m0 + g][n0 + nt * 8 + 2 * t] = c[nt][0];
+    Cs[m0 + g][n0 + nt * 8 + 2 * t + 1] = c[nt][1];
+    Cs[m0 + g + 8][n0 + nt * 8 + 2 * t] = c[nt][2];
+    Cs[m0 + g + 8][n0 + nt * 8 + 2 * t + 1] = c[nt][3];
+  }
+  __syncthreads();
+  const int tx = threadIdx.x % 16, ty = threadIdx.x / 16;
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = Cs[ty * 4 + i][tx * 4 + j];
+}
 
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + __expf(-x)); }
 
-template <int EPI>
+template <int EPI, bool TC>
 __global__ void __launch_bounds__(256) gemm_f32_kernel(GemmArgs a) {
-  __shared__ float As[GK][GM + 4];
-  __shared__ float Ws[GK][GN + 4];
+  __shared__ float As[GK][GM + GPAD];
+  __shared__ float Ws[GK][GN + GPAD];
+  __shared__ float Cs[TC ? GM : 1][GN + 4];
+  float cfr[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) cfr[i][j] = 0.f;
   const int b = blockIdx.z;
   const int r0 = blockIdx.x * GM;
   const int n0 = a.n_begin + blockIdx.y * GN;
@@ -95,22 +150,27 @@ __global__ void __launch_bounds__(256) gemm_f32_kernel(GemmArgs a) {
         Ws[kk][nn] = v;
       }
       __syncthreads();
+      if (TC) {
+        tile_mma_tf32(As, Ws, cfr);
+      } else {
 #pragma unroll
-      for (int kk = 0; kk < GK; ++kk) {
-        float av[4], wv[4];
+        for (int kk = 0; kk < GK; ++kk) {
+          float av[4], wv[4];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) av[i] = As[kk][ty * 4 + i];
+          for (int i = 0; i < 4; ++i) av[i] = As[kk][ty * 4 + i];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) wv[j] = Ws[kk][tx * 4 + j];
+          for (int j = 0; j < 4; ++j) wv[j] = Ws[kk][tx * 4 + j];
 #pragma unroll
-        for (int i = 0; i < 4; ++i)
+          for (int i = 0; i < 4; ++i)
 #pragma unroll
-          for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], wv[j], acc[i][j]);
+            for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], wv[j], acc[i][j]);
+        }
       }
       __syncthreads();
     }
     koff += sg.K;
   }
+  if (TC) frag_to_blocked(Cs, cfr, acc);
 
   // ------------------------------------------------------------------ epilogue
 #pragma unroll
@@ -193,10 +253,11 @@ __global__ void __launch_bounds__(256) gemm_f32_kernel(GemmArgs a) {
 }
 
 template <int EPI>
-inline int launch_gemm(const GemmArgs& a, cudaStream_t stream) {
+inline int launch_gemm(const GemmArgs& a, cudaStream_t stream, bool tc = false) {
   if (a.n_rows <= 0 || a.B <= 0 || a.N - a.n_begin <= 0) return QP_OK;
   dim3 grid((a.n_rows + GM - 1) / GM, (a.N - a.n_begin + GN - 1) / GN, a.B);
-  gemm_f32_kernel<EPI><<<grid, 256, 0, stream>>>(a);
+  if (tc) gemm_f32_kernel<EPI, true><<<grid, 256, 0, stream>>>(a);
+  else gemm_f32_kernel<EPI, false><<<grid, 256, 0, stream>>>(a);
   QP_LAUNCH_CHECK();
   return QP_OK;
 }
@@ -212,6 +273,8 @@ struct WgradArgs {
   int I, J;             // output dims
   float* out; int ldo;  // out[i*ldo + j], overwritten
   float* colsum;        // optional [I]: sum_r P[r][i]  (bias gradient), overwritten
+  int chunk;            // rows per split (set by launch_wgrad): blockIdx.z contracts rows [z*chunk, (z+1)*chunk) and, when
+                        // there is more than one split, accumulates into the zeroed output with atomics
 };
 
 __device__ __forceinline__ float seg_load(const Seg& sg, int b, int r, int k, int n_rows) {
@@ -221,9 +284,16 @@ __device__ __forceinline__ float seg_load(const Seg& sg, int b, int r, int k, in
   return sg.relu ? fmaxf(v, 0.f) : v;
 }
 
+template <bool TC>
 static __global__ void __launch_bounds__(256) wgrad_f32_kernel(WgradArgs a) {
-  __shared__ float Ps[GK][GM + 4];
-  __shared__ float Qs[GK][GN + 4];
+  __shared__ float Ps[GK][GM + GPAD];
+  __shared__ float Qs[GK][GN + GPAD];
+  __shared__ float Cs[TC ? GM : 1][GN + 4];
+  float cfr[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) cfr[i][j] = 0.f;
   const int i0 = blockIdx.x * GM, j0 = blockIdx.y * GN;
   const int tid = threadIdx.x, tx = tid % 16, ty = tid / 16;
   float acc[4][4];
@@ -232,16 +302,17 @@ static __global__ void __launch_bounds__(256) wgrad_f32_kernel(WgradArgs a) {
   for (int i = 0; i < 4; ++i)
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
-  // resolve which P / Q segment each of this thread's load slots belongs to (fixed per thread)
+  const int row_begin = blockIdx.z * a.chunk, row_end = min(a.n_rows, row_begin + a.chunk);
+  const bool split = gridDim.z > 1;
   for (int b = 0; b < a.B; ++b) {
-    for (int r0 = 0; r0 < a.n_rows; r0 += GK) {
+    for (int r0 = row_begin; r0 < row_end; r0 += GK) {
 #pragma unroll
       for (int e4 = 0; e4 < 4; ++e4) {
         int e = tid + e4 * 256;
         int ii = e % GM, rr = e / GM;  // coalesced along i
         int i = i0 + ii, r = r0 + rr;
         float v = 0.f;
-        if (i < a.I && r < a.n_rows) {
+        if (i < a.I && r < row_end) {
           int off = 0;
           for (int s = 0; s < a.np; ++s) {
             if (i - off < a.p[s].K) { v = seg_load(a.p[s], b, r, i - off, a.n_rows); break; }
@@ -252,7 +323,7 @@ static __global__ void __launch_bounds__(256) wgrad_f32_kernel(WgradArgs a) {
         int jj = e % GN;
         int j = j0 + jj;
         float w = 0.f;
-        if (j < a.J && r < a.n_rows) {
+        if (j < a.J && r < row_end) {
           int off = 0;
           for (int s = 0; s < a.nq; ++s) {
             if (j - off < a.q[s].K) { w = seg_load(a.q[s], b, r, j - off, a.n_rows); break; }
@@ -262,17 +333,21 @@ static __global__ void __launch_bounds__(256) wgrad_f32_kernel(WgradArgs a) {
         Qs[rr][jj] = w;
       }
       __syncthreads();
+      if (TC) {
+        tile_mma_tf32(Ps, Qs, cfr);
+      } else {
 #pragma unroll
-      for (int kk = 0; kk < GK; ++kk) {
-        float pv[4], qv[4];
+        for (int kk = 0; kk < GK; ++kk) {
+          float pv[4], qv[4];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) pv[i] = Ps[kk][ty * 4 + i];
+          for (int i = 0; i < 4; ++i) pv[i] = Ps[kk][ty * 4 + i];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) qv[j] = Qs[kk][tx * 4 + j];
+          for (int j = 0; j < 4; ++j) qv[j] = Qs[kk][tx * 4 + j];
 #pragma unroll
-        for (int i = 0; i < 4; ++i)
+          for (int i = 0; i < 4; ++i)
 #pragma unroll
-          for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(pv[i], qv[j], acc[i][j]);
+            for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(pv[i], qv[j], acc[i][j]);
+        }
       }
       if (a.colsum && blockIdx.y == 0 && tid < GM) {
 #pragma unroll
@@ -281,19 +356,45 @@ static __global__ void __launch_bounds__(256) wgrad_f32_kernel(WgradArgs a) {
       __syncthreads();
     }
   }
+  if (TC) frag_to_blocked(Cs, cfr, acc);
 #pragma unroll
   for (int i = 0; i < 4; ++i)
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       int ii = i0 + ty * 4 + i, jj = j0 + tx * 4 + j;
-      if (ii < a.I && jj < a.J) a.out[(int64_t)ii * a.ldo + jj] = acc[i][j];
+      if (ii < a.I && jj < a.J) {
+        if (split) atomicAdd(a.out + (int64_t)ii * a.ldo + jj, acc[i][j]);
+        else a.out[(int64_t)ii * a.ldo + jj] = acc[i][j];
+      }
     }
-  if (a.colsum && blockIdx.y == 0 && tid < GM && i0 + tid < a.I) a.colsum[i0 + tid] = csum;
+  if (a.colsum && blockIdx.y == 0 && tid < GM && i0 + tid < a.I) {
+    if (split) atomicAdd(a.colsum + i0 + tid, csum);
+    else a.colsum[i0 + tid] = csum;
+  }
 }
 
-inline int launch_wgrad(const WgradArgs& a, cudaStream_t stream) {
+// The contraction runs over the rows of a segment (~20 000 in training) while the output is small, so the rows are
+// split over blockIdx.z until the grid holds a few thousand blocks; partial products meet in the zeroed output
+// through fp32 atomics (the output must be dense: ldo == J).
+inline int launch_wgrad(const WgradArgs& a0, cudaStream_t stream, bool tc = false) {
+  WgradArgs a = a0;
   dim3 grid((a.I + GM - 1) / GM, (a.J + GN - 1) / GN);
-  wgrad_f32_kernel<<<grid, 256, 0, stream>>>(a);
+  int nsplit = 1;
+  if (a.ldo == a.J) {
+    const int tiles = (int)(grid.x * grid.y);
+    nsplit = std::max(1, std::min(std::min(64, 4096 / std::max(tiles, 1)), a.n_rows / 256));
+  }
+  a.chunk = ((a.n_rows + nsplit - 1) / nsplit + GK - 1) / GK * GK;
+  nsplit = (a.n_rows + a.chunk - 1) / std::max(a.chunk, 1);
+  if (nsplit < 1) nsplit = 1;
+  grid.z = nsplit;
+  if (nsplit > 1) {
+    cudaError_t e_ = cudaMemsetAsync(a.out, 0, sizeof(float) * (size_t)a.I * a.ldo, stream);
+    if (e_ == cudaSuccess && a.colsum) e_ = cudaMemsetAsync(a.colsum, 0, sizeof(float) * (size_t)a.I, stream);
+    if (e_ != cudaSuccess) return set_error(QP_ECUDA, "wgrad memset failed: %s", cudaGetErrorString(e_));
+  }
+  if (tc) wgrad_f32_kernel<true><<<grid, 256, 0, stream>>>(a);
+  else wgrad_f32_kernel<false><<<grid, 256, 0, stream>>>(a);
   QP_LAUNCH_CHECK();
   return QP_OK;
 }
