@@ -45,7 +45,8 @@ struct GemmArgs {
   float* dh; int64_t dh_bstride; int dh_off; int A;
 };
 
-constexpr int GM = 64, GN = 64, GK = 16;
+constexpr int GM = 64, GN = 64, GK = 16;   // (GK = 32 was measured slower: 36 KB of tiles per block halve the residency)
+constexpr int LD_IT = GM * GK / 256;   // elements of a 64 x GK tile each of the 256 threads loads
 constexpr int GPAD = 8;   // tile pitch GM + 8: the TF32 fragment loads (k = lane % 4, m = lane / 4) hit 32 distinct banks
 
 // ---- TF32 tensor-core inner product (backward of the bf16 training path): the same 64 x 64 x 16 shared tiles,
@@ -123,7 +124,7 @@ __global__ void __launch_bounds__(256) gemm_f32_kernel(GemmArgs a) {
     for (int k0 = 0; k0 < sg.K; k0 += GK) {
       // A tile: 64 rows x 16 k
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
+      for (int i = 0; i < LD_IT; ++i) {
         int e = tid + i * 256;
         int rr = e / GK, kk = e % GK;
         int r = r0 + rr, k = k0 + kk;
@@ -139,7 +140,7 @@ __global__ void __launch_bounds__(256) gemm_f32_kernel(GemmArgs a) {
       }
       // W tile: 64 n x 16 k
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
+      for (int i = 0; i < LD_IT; ++i) {
         int e = tid + i * 256;
         int nn, kk;
         if (a.w_kn) { kk = e / GN; nn = e % GN; } else { nn = e / GK; kk = e % GK; }
@@ -307,7 +308,7 @@ static __global__ void __launch_bounds__(256) wgrad_f32_kernel(WgradArgs a) {
   for (int b = 0; b < a.B; ++b) {
     for (int r0 = row_begin; r0 < row_end; r0 += GK) {
 #pragma unroll
-      for (int e4 = 0; e4 < 4; ++e4) {
+      for (int e4 = 0; e4 < LD_IT; ++e4) {
         int e = tid + e4 * 256;
         int ii = e % GM, rr = e / GM;  // coalesced along i
         int i = i0 + ii, r = r0 + rr;
