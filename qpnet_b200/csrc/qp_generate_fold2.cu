@@ -746,10 +746,6 @@ __global__ void __launch_bounds__(NT, 1) f2_gen_kernel(Plan p, GenArgsDev g) {
           send(acc, sRecvG, gb, barG);
           trace(t, j, 4);
         }
-        // while the gate partial tiles travel: res / skip rows of block j-1 (finished by the streaming warps)
-        zero(acc);
-        kloop(K4(), acc, aq, Wrk + brow * PS + bcol + kh * (KS / 2));
-        send(acc, sRecvR, rb, barR0 + 8 * rb);
         if (fused) {
           float s0, s1, e0 = 0.f, e1 = 0.f;
           gather(sRecvG, gb, barG, (gpar >> gb) & 1u, s0, s1);
@@ -768,7 +764,11 @@ __global__ void __launch_bounds__(NT, 1) f2_gen_kernel(Plan p, GenArgsDev g) {
           trace(t, j, 6);
           have_e = false;
         }
-        // the part of the NEXT gate that z_{j-1} already determines, while z_j travels
+        // while z_j travels: the res / skip rows of block j-1 (finished by the streaming warps; x_j has a phase of slack) ...
+        zero(acc);
+        kloop(K4(), acc, aq, Wrk + brow * PS + bcol + kh * (KS / 2));
+        send(acc, sRecvR, rb, barR0 + 8 * rb);
+        // ... and the part of the NEXT gate that z_{j-1} already determines
         zero(carry);
         if (j <= L - 2) kloop(K4(), carry, aq, Wtop + brow * PT2 + bcol + KS + kh * (KS / 2));
         if (makes_e_of(t, j)) have_e = true;
