@@ -83,6 +83,19 @@ int qp_mulaw_decode(const int64_t* y, int64_t n, int32_t mu, double* x, void* st
 int qp_f0_to_dilated(const double* f0, int32_t B, int32_t F, double fs, double dense,
                      int32_t U, double f0_floor, double* d64, float* d32, void* stream);
 
+/* ---- decode front end (qpnet_decode.py:163-200, 268-269), one launch for a padded batch ------------
+ * raw: (B, Fmax, D) fp64 unscaled acoustic features, zero padded past n_frames[b] (device, (B,) int32).
+ * Per live frame: f0' = raw[f0_dim] * f0_factor (172-173); d = ((1.0*fs)/(f0' == 0 ? fs/dense : f0'))/dense
+ * repeated U times (174-175, 90-108, utils.py:216-235); h = float((x - mean)/scale) with x[f0_dim] = f0'
+ * (StandardScaler.transform), written transposed as (B, D, Fmax) fp32 (190).  Padding frames: h = 0, d = 0
+ * (pad_list, 73-88).  d64 / d32: (B, Fmax*U); either may be NULL. */
+int qp_feat_prepare(const double* raw, const int32_t* n_frames, int32_t B, int32_t Fmax, int32_t D,
+                    const double* mean, const double* scale, double f0_factor, int32_t f0_dim,
+                    double fs, double dense, int32_t U, float* h, double* d64, float* d32, void* stream);
+
+/* ---- decode back end (qpnet_decode.py:315-318): symbols -> decode_mu_law (fp64) -> *32768 -> clip -> int16 */
+int qp_mulaw_decode_pcm16(const int32_t* y, int64_t n, int32_t mu, int16_t* pcm, void* stream);
+
 /* max over all elements of ceil(d)  (qpnet.py:255 / 347-350); result to *out (device). */
 int qp_max_ceil_f32(const float* d, int64_t n, int32_t* out, void* stream);
 int qp_max_ceil_f64(const double* d, int64_t n, int32_t* out, void* stream);

@@ -388,3 +388,38 @@ def generate(a: Arch, p, seed_x, h, n_samples_list, d, mode="sampling", uniforms
         prev = new
         new = s if force is None else torch.as_tensor(force[:, i], dtype=torch.int64)
     return [out[b, : min(n_samples_list[b], T)].numpy() for b in range(B)]
+
+
+# ------------------------------------------------------------------ decode front / back end (next row (f)1)
+def decode_pad_list(batch_list, pad_value=0.0):
+    """qpnet_decode.py:73-88."""
+    maxlen = max(b.shape[0] for b in batch_list)
+    out = np.zeros((len(batch_list), maxlen, batch_list[0].shape[-1]))
+    for i, b in enumerate(batch_list):
+        out[i, : b.shape[0]] = b
+    return out
+
+
+def decode_frontend(feats, mean, scale, fs, dense_factor, upsampling_factor, f0_factor, f0_dim_index):
+    """What decode_generator yields for one batch of raw (T_i, D) matrices (qpnet_decode.py:158-200, 268-269):
+    h (B, D, Fmax) float32, d (B, Fmax*U) float64, n_samples_list."""
+    hs, ds, ns = [], [], []
+    for f in feats:
+        h = np.array(f, dtype=np.float64, copy=True)
+        h[:, f0_dim_index] = h[:, f0_dim_index] * f0_factor                       # 172-173
+        d = dilated_factor(h[:, f0_dim_index].copy(order="C"), fs, dense_factor)  # 174, 90-108
+        d = extend_time(d, upsampling_factor)                                     # 175
+        h = (h - np.asarray(mean, np.float64)) / np.asarray(scale, np.float64)    # StandardScaler.transform (268-269)
+        hs.append(h)
+        ds.append(d[:, None])
+        ns.append(f.shape[0] * upsampling_factor - 1)                             # 184
+    h_pad = np.transpose(decode_pad_list(hs).astype(np.float32), (0, 2, 1))       # 187, 190
+    d_pad = decode_pad_list(ds)[:, :, 0]                                          # 188, 194
+    return h_pad, d_pad, ns
+
+
+def decode_pcm16(samples, mu=256):
+    """qpnet_decode.py:315-318: decode_mu_law -> * 32768 -> clip -> int16."""
+    wav = decode_mu_law(np.asarray(samples), mu)
+    return np.clip(wav * 32768, -32768, 32767).astype(np.int16)
+

@@ -44,6 +44,8 @@ SIGNATURES = {
     "qp_mulaw_encode": (C.c_int, [_P, _I64, _I32, _P, _P]),
     "qp_mulaw_decode": (C.c_int, [_P, _I64, _I32, _P, _P]),
     "qp_f0_to_dilated": (C.c_int, [_P, _I32, _I32, _F64, _F64, _I32, _F64, _P, _P, _P]),
+    "qp_feat_prepare": (C.c_int, [_P, _P, _I32, _I32, _I32, _P, _P, _F64, _I32, _F64, _F64, _I32, _P, _P, _P, _P]),
+    "qp_mulaw_decode_pcm16": (C.c_int, [_P, _I64, _I32, _P, _P]),
     "qp_max_ceil_f32": (C.c_int, [_P, _I64, _P, _P]),
     "qp_max_ceil_f64": (C.c_int, [_P, _I64, _P, _P]),
     "qp_index_tf_f32": (C.c_int, [_P, _I32, _I32, _I64, _I32, _P, _P]),

@@ -82,6 +82,52 @@ __global__ void f0_to_dilated_kernel(const double* __restrict__ f0, int B, int F
   if (d32) d32[i] = (float)d;
 }
 
+// ------------------------------------------------------------------ decode front end (qpnet_decode.py:163-200)
+// raw features (B, Fmax, D) fp64, zero padded past n_frames[b] -> per frame f < n_frames[b]:
+//   f0' = raw[f0_dim] * f0_factor (172-173); d = ((1.0*fs)/(f0' == 0 ? fs/dense : f0'))/dense, repeated U times (174-175, 90-108);
+//   h[k] = float((x_k - mean_k) / scale_k) with x_f0dim = f0' (StandardScaler.transform, 268-269), transposed to (B, D, Fmax) (190).
+// Padding frames give h = 0 and d = 0 (pad_list, 73-88).  One thread per (b, f, k).
+__global__ void feat_prepare_kernel(const double* __restrict__ raw, const int32_t* __restrict__ n_frames, int B, int Fmax,
+                                    int D, const double* __restrict__ mean, const double* __restrict__ scale,
+                                    double f0_factor, int f0_dim, double fs, double dense, int U,
+                                    float* __restrict__ h, double* __restrict__ d64, float* __restrict__ d32) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (int64_t)B * Fmax * D) return;
+  const int k = (int)(i % D);
+  const int64_t bf = i / D;
+  const int f = (int)(bf % Fmax), b = (int)(bf / Fmax);
+  const bool live = f < n_frames[b];
+  double x = live ? raw[i] : 0.0;
+  if (k == f0_dim && live) x = __dmul_rn(x, f0_factor);
+  float hv = 0.f;
+  if (live) hv = (float)__ddiv_rn(__dsub_rn(x, mean[k]), scale[k]);
+  h[((int64_t)b * D + k) * Fmax + f] = hv;
+  if (k == f0_dim) {
+    double dv = 0.0;
+    if (live) {
+      double f0 = x == 0.0 ? fs / dense : x;
+      dv = __ddiv_rn(__ddiv_rn(1.0 * fs, f0), dense);
+    }
+    const int64_t o = ((int64_t)b * Fmax + f) * U;
+    for (int u = 0; u < U; ++u) {
+      if (d64) d64[o + u] = dv;
+      if (d32) d32[o + u] = (float)dv;
+    }
+  }
+}
+
+// ------------------------------------------------------------------ decode back end (qpnet_decode.py:315-318)
+// symbol -> decode_mu_law (qpnet.py:34-45, fp64) -> * 32768 -> clip [-32768, 32767] -> int16 (numpy astype: truncation)
+__global__ void mulaw_pcm16_kernel(const int32_t* __restrict__ y, int64_t n, double mu, int16_t* __restrict__ out) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double fx = ((double)y[i] - 0.5) / mu * 2.0 - 1.0;
+  double sgn = (fx > 0.0) - (fx < 0.0);
+  double w = sgn / mu * (pow(1.0 + mu, fabs(fx)) - 1.0) * 32768.0;
+  w = fmin(fmax(w, -32768.0), 32767.0);
+  out[i] = (int16_t)w;   // C conversion truncates toward zero, like ndarray.astype(np.int16)
+}
+
 template <typename T>
 __global__ void max_ceil_kernel(const T* __restrict__ d, int64_t n, int32_t* __restrict__ out) {
   int best = INT32_MIN;
@@ -207,6 +253,31 @@ int qp_index_gen_f32(const float* d, int32_t B, int32_t n, int64_t ld, int32_t d
 }
 int qp_index_gen_f64(const double* d, int32_t B, int32_t n, int64_t ld, int32_t dil, int32_t* idx, void* s) {
   return index_impl<3>(d, B, n, ld, dil, idx, s);
+}
+
+int qp_feat_prepare(const double* raw, const int32_t* n_frames, int32_t B, int32_t Fmax, int32_t D, const double* mean,
+                    const double* scale, double f0_factor, int32_t f0_dim, double fs, double dense, int32_t U, float* h,
+                    double* d64, float* d32, void* stream) {
+  if (int e = check_device()) return e;
+  QP_REQUIRE(B >= 0 && Fmax >= 0 && D >= 1 && U >= 1 && f0_dim >= 0 && f0_dim < D, "feat_prepare: bad shape");
+  QP_REQUIRE(fs > 0 && dense > 0, "feat_prepare: fs and dense_factor must be positive");
+  if ((int64_t)B * Fmax == 0) return QP_OK;
+  QP_REQUIRE(raw && n_frames && mean && scale && h && (d64 || d32), "feat_prepare: NULL pointer");
+  int64_t n = (int64_t)B * Fmax * D;
+  feat_prepare_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(raw, n_frames, B, Fmax, D, mean, scale,
+                                                                                  f0_factor, f0_dim, fs, dense, U, h, d64, d32);
+  QP_LAUNCH_CHECK();
+  return QP_OK;
+}
+
+int qp_mulaw_decode_pcm16(const int32_t* y, int64_t n, int32_t mu, int16_t* pcm, void* stream) {
+  if (int e = check_device()) return e;
+  QP_REQUIRE(n >= 0 && mu >= 2, "mulaw_decode_pcm16: bad size");
+  if (n == 0) return QP_OK;
+  QP_REQUIRE(y && pcm, "mulaw_decode_pcm16: NULL pointer");
+  mulaw_pcm16_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(y, n, (double)(mu - 1), pcm);   // qpnet.py:41: mu = mu - 1
+  QP_LAUNCH_CHECK();
+  return QP_OK;
 }
 
 }  // extern "C"

@@ -104,6 +104,33 @@ def decode_mu_law(y, mu=256):
     return mulaw_decode_t(torch.from_numpy(np.ascontiguousarray(y)).cuda(), mu).cpu().numpy()
 
 
+def feat_prepare(raw: torch.Tensor, n_frames: torch.Tensor, mean: torch.Tensor, scale: torch.Tensor, f0_factor: float,
+                 f0_dim: int, fs: float, dense_factor: float, upsampling: int, want_f64: bool = True, want_f32: bool = False):
+    """Decode front end on the device (qpnet_decode.py:163-200, 268-269): raw (B, Fmax, D) fp64 zero padded,
+    n_frames (B,) -> (h (B, D, Fmax) fp32, d64 (B, Fmax*U) fp64 or None, d32 or None)."""
+    _need_cuda(raw, n_frames, mean, scale)
+    raw = raw.to(torch.float64).contiguous()
+    B, Fmax, D = raw.shape
+    n_frames = n_frames.to(torch.int32).contiguous()
+    mean, scale = mean.to(torch.float64).contiguous(), scale.to(torch.float64).contiguous()
+    h = torch.empty((B, D, Fmax), dtype=torch.float32, device=raw.device)
+    d64 = torch.empty((B, Fmax * upsampling), dtype=torch.float64, device=raw.device) if want_f64 else None
+    d32 = torch.empty((B, Fmax * upsampling), dtype=torch.float32, device=raw.device) if want_f32 else None
+    check(lib.qp_feat_prepare(raw.data_ptr(), n_frames.data_ptr(), B, Fmax, D, mean.data_ptr(), scale.data_ptr(),
+                              float(f0_factor), int(f0_dim), float(fs), float(dense_factor), int(upsampling), h.data_ptr(),
+                              d64.data_ptr() if want_f64 else None, d32.data_ptr() if want_f32 else None, _stream()))
+    return h, d64, d32
+
+
+def mulaw_decode_pcm16(sym: torch.Tensor, mu: int = 256) -> torch.Tensor:
+    """Decode back end (qpnet_decode.py:315-318): int32 symbols -> int16 PCM, on the device."""
+    _need_cuda(sym)
+    sym = sym.to(torch.int32).contiguous()
+    out = torch.empty(sym.shape, dtype=torch.int16, device=sym.device)
+    check(lib.qp_mulaw_decode_pcm16(sym.data_ptr(), sym.numel(), mu, out.data_ptr(), _stream()))
+    return out
+
+
 def cross_entropy(logits: torch.Tensor, target: torch.Tensor, want_grad: bool = True):
     """Mean softmax cross-entropy over all rows (qpnet_train.py:430,526) and its gradient."""
     _need_cuda(logits, target)

@@ -215,8 +215,76 @@ def golden_mulaw():
     print("mulaw enc known:", ref.encode_mu_law(xs))
 
 
+# ---------------------------------------------------------------- G7: decode front / back end
+def _reference_functions(path, names, namespace):
+    """Compile the named top-level functions of a reference script WITHOUT importing the script (its module-level
+    imports need h5py / docopt, which are not installed): the function bodies are the reference's, unmodified."""
+    import ast
+    tree = ast.parse(open(path).read())
+    for node in tree.body:
+        if isinstance(node, ast.FunctionDef) and node.name in names:
+            code = compile(ast.Module(body=[node], type_ignores=[]), path, "exec")
+            exec(code, namespace)
+    missing = [n for n in names if n not in namespace]
+    assert not missing, missing
+    return namespace
+
+
+def golden_decode():
+    """decode_generator's per-utterance arithmetic (qpnet_decode.py:158-200) and the write-out (315-318), driven with
+    the reference's own pad_list / _dilated_factor / _batch_f0 / extend_time / decode_mu_law and sklearn's
+    StandardScaler (268-269) on seeded synthetic WORLD-style features."""
+    import copy
+    from numpy.matlib import repmat
+    from sklearn.preprocessing import StandardScaler
+    ns = {"np": np, "copy": copy, "repmat": repmat}
+    _reference_functions("/root/reference/src/bin/qpnet_decode.py", ["pad_list", "_dilated_factor", "_batch_f0"], ns)
+    _reference_functions("/root/reference/src/utils/utils.py", ["extend_time"], ns)
+    out = {}
+    rs = np.random.RandomState(5)
+    D = 39
+    mean = rs.randn(D) * 2.0
+    scale = rs.rand(D) * 3.0 + 0.5
+    mean[0], scale[0] = 0.0, 1.0                     # calc_stats.py:29-33 leaves the U/V flag unscaled
+    scaler = StandardScaler()
+    scaler.mean_, scaler.scale_, scaler.n_features_in_ = mean, scale, D
+    out["mean"], out["scale"] = mean, scale
+    for factor in (1.0, 0.5, 1.5):
+        feats = []
+        for u, frames in enumerate((7, 4, 9)):
+            hs, f0, _ = synth.utterance(frames, 300 + u, 1.0, D)
+            raw = rs.randn(frames, D)
+            raw[:, 0] = (rs.rand(frames) > 0.3)
+            raw[:, 1] = f0
+            if u == 1:
+                raw[2, 1] = 0.0                      # an unvoiced hole: f0 == 0 -> fs / dense_factor (101)
+            feats.append(raw)
+        batch_h, batch_d = [], []
+        for raw in feats:                            # the loop body of decode_generator, 163-183
+            h = raw.copy()
+            h[:, 1] = h[:, 1] * factor
+            d = ns["_dilated_factor"](ns["_batch_f0"](h), synth.FS, synth.DENSE_FACTOR)
+            d = ns["extend_time"](np.expand_dims(d, -1), synth.UPSAMPLING)
+            h = scaler.transform(h)
+            batch_h += [h]
+            batch_d += [d]
+        bh = torch.from_numpy(ns["pad_list"](batch_h)).float().transpose(1, 2).numpy()   # 187, 190
+        bd = ns["pad_list"](batch_d).squeeze(-1)                                          # 188, 194
+        for u, raw in enumerate(feats):
+            out[f"f{factor}/raw{u}"] = raw
+        out[f"f{factor}/h"] = bh
+        out[f"f{factor}/d"] = bd
+    sym = np.arange(256, dtype=np.int64)
+    wav = ref.decode_mu_law(sym, 256)
+    out["pcm_all_symbols"] = np.clip(wav * 32768, -32768, 32767).astype(np.int16)        # 317-319
+    np.savez_compressed(os.path.join(HERE, "decode.npz"), **out)
+    print("decode.npz:", len(out), "arrays")
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["indices", "forward", "generate", "mulaw"]
+    which = sys.argv[1:] or ["indices", "forward", "generate", "mulaw", "decode"]
+    if "decode" in which:
+        golden_decode()
     if "indices" in which:
         golden_indices()
     if "forward" in which:

@@ -515,3 +515,44 @@ def test_training_step_matches_reference_adam_update(dev):
     for _ in range(5):
         loss = tr.step(x.to(dev), h.to(dev), d.to(dev), t.to(dev), bl)
     assert float(loss) < l0
+
+
+# ------------------------------------------------------------------ decode front / back end
+@pytest.mark.gpu
+@pytest.mark.parametrize("fac", [1.0, 0.5, 1.5])
+def test_decode_frontend_device_is_bit_exact(dev, fac):
+    """qp_feat_prepare against the reference-generated fixtures: scaled features (fp32) and dilated factors (fp64) equal
+    bit for bit, padding zeros included; both d flavours."""
+    from qpnet_b200 import decode as qdec
+    g = cases.load("decode")
+    feats = [g[f"f{fac}/raw{u}"] for u in range(3)]
+    x, h, n_list, d = qdec.prepare_batch(feats, g["mean"], g["scale"], synth.FS, synth.DENSE_FACTOR, synth.UPSAMPLING, fac, 1,
+                                         extra_memory=False, device=dev)
+    assert np.array_equal(h.cpu().numpy(), g[f"f{fac}/h"])
+    assert d.dtype == torch.float64 and np.array_equal(d.cpu().numpy(), g[f"f{fac}/d"])
+    assert n_list == [f.shape[0] * synth.UPSAMPLING - 1 for f in feats] and x.tolist() == [[128]] * 3
+    _, _, _, d32 = qdec.prepare_batch(feats, g["mean"], g["scale"], synth.FS, synth.DENSE_FACTOR, synth.UPSAMPLING, fac, 1,
+                                      extra_memory=True, device=dev)
+    assert np.array_equal(d32.cpu().numpy(), g[f"f{fac}/d"].astype(np.float32))          # qpnet_decode.py:191-192
+
+
+@pytest.mark.gpu
+def test_decode_backend_pcm16_and_pipeline(dev, tmp_path):
+    """qp_mulaw_decode_pcm16 on every symbol, and the whole decode() pipeline on a small model: every utterance comes back
+    as int16 PCM of the reference's length, equal to the oracle's write-out of the symbols the generator produced."""
+    from qpnet_b200 import decode as qdec, ops
+    g = cases.load("decode")
+    pcm = ops.mulaw_decode_pcm16(torch.arange(256, dtype=torch.int32, device=dev))
+    assert np.array_equal(pcm.cpu().numpy(), g["pcm_all_symbols"])
+    a = orc.Arch(**cases.SMALL)
+    m = _model(cases.SMALL, orc.init_params(a, 4, 0.1), dev)
+    feats = [g[f"f1.0/raw{u}"] for u in range(3)]
+    m.philox_seed = 9
+    out = qdec.decode(m, feats, g["mean"], g["scale"], fs=synth.FS, batch_size=2, ids=["a", "b", "c"])
+    assert sorted(out) == ["a", "b", "c"]
+    for name, f in zip(["a", "b", "c"], feats):
+        assert out[name].dtype == np.int16 and len(out[name]) == f.shape[0] * synth.UPSAMPLING - 1
+    qdec.write_wav(str(tmp_path / "a.wav"), synth.FS, out["a"])
+    import wave
+    with wave.open(str(tmp_path / "a.wav")) as w:
+        assert w.getframerate() == synth.FS and w.getnframes() == len(out["a"]) and w.getsampwidth() == 2

@@ -155,3 +155,26 @@ def _forward_rows(a, p, x, hup, d, bl, M):
         cur = res + xc
         skips = skips + skip[-bl:]
     return orc._head(p, skips)
+
+
+# ------------------------------------------------------------------ decode front / back end
+def test_decode_frontend_and_pcm_match_reference_functions():
+    """oracle.decode_frontend / decode_pcm16 against fixtures produced by the reference's own pad_list,
+    _dilated_factor, _batch_f0, extend_time, decode_mu_law and sklearn's StandardScaler (make_golden.py: golden_decode)."""
+    g = cases.load("decode")
+    for fac in (1.0, 0.5, 1.5):
+        feats = [g[f"f{fac}/raw{u}"] for u in range(3)]
+        h, d, ns = orc.decode_frontend(feats, g["mean"], g["scale"], synth.FS, synth.DENSE_FACTOR, synth.UPSAMPLING, fac, 1)
+        assert h.dtype == np.float32 and np.array_equal(h, g[f"f{fac}/h"])
+        assert np.array_equal(d, g[f"f{fac}/d"])
+        assert ns == [f.shape[0] * synth.UPSAMPLING - 1 for f in feats]
+    assert np.array_equal(orc.decode_pcm16(np.arange(256)), g["pcm_all_symbols"])
+
+
+def test_decode_batch_lists_follow_the_reference_split():
+    """qpnet_decode.py:149-156: argsort by length, then np.array_split into ceil(N / batch_size) batches."""
+    from qpnet_b200.decode import batch_lists          # host logic only (no CUDA call)
+    lengths = [50, 10, 30, 20, 40, 60, 5]
+    got = batch_lists(lengths, 3)
+    assert got == [[6, 1, 3], [2, 4], [0, 5]]
+    assert batch_lists([], 4) == []
