@@ -281,8 +281,35 @@ def golden_decode():
     print("decode.npz:", len(out), "arrays")
 
 
+# ---------------------------------------------------------------- G8: checkpoint written the reference's way
+def golden_checkpoint():
+    """A small reference model + Adam state after one step, saved exactly like qpnet_train.py:336-352 / 389."""
+    import argparse
+    arch = dict(n_resch=8, n_skipch=8)
+    a = orc.Arch(**arch)
+    m = ref_model(arch, orc.init_params(a, 12, 0.1))
+    m.train()
+    opt = torch.optim.Adam(m.parameters(), lr=1e-4)
+    T = 6 * a.U
+    hs, f0, _ = synth.utterance(6, 77, 1.0, a.A)
+    x = torch.from_numpy(np.random.RandomState(3).randint(0, a.Q, size=(1, T))).long()
+    h = torch.from_numpy(hs.T.copy())[None]
+    d = torch.from_numpy(d_from_f0(f0)).float()[None, :T]
+    out = m(x, h, d, torch.tensor([100]))
+    torch.nn.functional.cross_entropy(out.reshape(-1, a.Q), x[0, -100:]).backward()
+    opt.step()
+    checkpoint = {"model": m.state_dict(), "optimizer": opt.state_dict(), "iterations": 7}
+    torch.save(checkpoint, os.path.join(HERE, "checkpoint-7.pkl"))
+    ns = argparse.Namespace(n_quantize=256, n_aux=39, n_resch=8, n_skipch=8, dilationF_depth=4, dilationF_repeat=3,
+                            dilationA_depth=4, dilationA_repeat=1, kernel_size=2, upsampling_factor=110, lr=1e-4, seed=1)
+    torch.save(ns, os.path.join(HERE, "model.conf"))
+    print("checkpoint-7.pkl", os.path.getsize(os.path.join(HERE, "checkpoint-7.pkl")), "bytes")
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["indices", "forward", "generate", "mulaw", "decode"]
+    which = sys.argv[1:] or ["indices", "forward", "generate", "mulaw", "decode", "checkpoint"]
+    if "checkpoint" in which:
+        golden_checkpoint()
     if "decode" in which:
         golden_decode()
     if "indices" in which:

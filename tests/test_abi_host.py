@@ -84,3 +84,30 @@ def test_synth_is_deterministic_and_in_range():
     assert np.array_equal(a, b) and np.array_equal(f0a, f0b) and n == 20 * 110 - 1
     f0 = synth.f0_contour(500, 7)
     assert f0.min() >= 45.0 and f0.max() <= 450.0
+
+
+def test_reference_checkpoint_round_trip(tmp_path):
+    """a checkpoint and model.conf written by the reference's trainer (fixtures produced by the
+    unmodified reference class + torch.optim.Adam, make_golden.py: golden_checkpoint) load into the new class, resume the
+    optimizer, and save back in the same format."""
+    from qpnet_b200 import checkpoint as ck
+    from qpnet_b200.qpnet import QPNet
+    gold = os.path.join(ROOT, "tests", "golden")
+    kw = ck.load_config(os.path.join(gold, "model.conf"))
+    assert kw["n_resch"] == 8 and kw["upsampling_factor"] == 110
+    m = QPNet(**kw)
+    opt = torch.optim.Adam(m.parameters(), lr=1e-4)
+    it = ck.load_checkpoint(os.path.join(gold, "checkpoint-7.pkl"), m, opt)
+    assert it == 7
+    ref = torch.load(os.path.join(gold, "checkpoint-7.pkl"), weights_only=False)
+    sd = m.state_dict()
+    assert list(sd) == list(ref["model"])
+    assert all(torch.equal(sd[k], ref["model"][k]) for k in sd)
+    assert opt.state_dict()["state"][0]["step"] == ref["optimizer"]["state"][0]["step"]
+    path = ck.save_checkpoint(str(tmp_path), m, opt, it + 1)
+    assert os.path.basename(path) == "checkpoint-8.pkl"
+    again = torch.load(path, weights_only=False)
+    assert set(again) == {"model", "optimizer", "iterations"} and again["iterations"] == 8
+    # a DataParallel checkpoint ("module." prefix, qpnet_train.py:416-423) loads too
+    torch.save({"model": {"module." + k: v for k, v in ref["model"].items()}, "iterations": 3}, str(tmp_path / "dp.pkl"))
+    assert ck.load_checkpoint(str(tmp_path / "dp.pkl"), QPNet(**kw)) == 3
