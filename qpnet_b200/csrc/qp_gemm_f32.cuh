@@ -98,7 +98,7 @@ __device__ __forceinline__ void frag_to_blocked(float (*Cs)[GN + 4], const float
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + __expf(-x)); }
 
 template <int EPI, bool TC>
-__global__ void __launch_bounds__(256) gemm_f32_kernel(GemmArgs a) {
+__global__ void __launch_bounds__(256, TC ? 4 : 2) gemm_f32_kernel(GemmArgs a) {
   __shared__ float As[GK][GM + GPAD];
   __shared__ float Ws[GK][GN + GPAD];
   __shared__ float Cs[TC ? GM : 1][GN + 4];
