@@ -285,8 +285,37 @@ __device__ __forceinline__ float seg_load(const Seg& sg, int b, int r, int k, in
   return sg.relu ? fmaxf(v, 0.f) : v;
 }
 
+// one load slot of a thread: a fixed output row / column, i.e. a fixed column of one segment of P or Q
+struct WSlot {
+  const float* base;   // segment base + column (nullptr: outside the output, loads zero)
+  const int* rowmap;
+  int64_t bstride;
+  int ld, row_off, src_rows, relu;
+};
+__device__ __forceinline__ WSlot wslot_resolve(const Seg* segs, int nseg, int col, int limit) {
+  WSlot w; w.base = nullptr; w.rowmap = nullptr; w.bstride = 0; w.ld = 0; w.row_off = 0; w.src_rows = 0; w.relu = 0;
+  if (col >= limit) return w;
+  int off = 0;
+  for (int s = 0; s < nseg; ++s) {
+    if (col - off < segs[s].K) {
+      w.base = segs[s].base + (col - off); w.rowmap = segs[s].rowmap; w.bstride = segs[s].bstride; w.ld = segs[s].ld;
+      w.row_off = segs[s].row_off; w.src_rows = segs[s].src_rows; w.relu = segs[s].relu;
+      return w;
+    }
+    off += segs[s].K;
+  }
+  return w;
+}
+__device__ __forceinline__ float wslot_load(const WSlot& w, int b, int r, int n_rows, int row_end) {
+  if (!w.base || r >= row_end) return 0.f;
+  const int src = w.rowmap ? w.rowmap[(int64_t)b * n_rows + r] : r + w.row_off;
+  if (src < 0 || src >= w.src_rows) return 0.f;
+  const float v = w.base[(int64_t)b * w.bstride + (int64_t)src * w.ld];
+  return w.relu ? fmaxf(v, 0.f) : v;
+}
+
 template <bool TC>
-static __global__ void __launch_bounds__(256) wgrad_f32_kernel(WgradArgs a) {
+static __global__ void __launch_bounds__(256, 4) wgrad_f32_kernel(WgradArgs a) {
   __shared__ float Ps[GK][GM + GPAD];
   __shared__ float Qs[GK][GN + GPAD];
   __shared__ float Cs[TC ? GM : 1][GN + 4];
@@ -298,56 +327,53 @@ static __global__ void __launch_bounds__(256) wgrad_f32_kernel(WgradArgs a) {
   const int i0 = blockIdx.x * GM, j0 = blockIdx.y * GN;
   const int tid = threadIdx.x, tx = tid % 16, ty = tid / 16;
   float acc[4][4];
-  float csum = 0.f;  // threads with tx == 0 (first 64 rows mapping below) accumulate colsum
+  float csum = 0.f;  // threads with tid < GM accumulate the column sum of P (bias gradient)
 #pragma unroll
   for (int i = 0; i < 4; ++i)
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  // every load slot of this thread reads a fixed column: element e = tid + 256 k -> column e % 64, tile row e / 64
+  const int cc = tid % GM, rr0 = tid / GM;
+  const WSlot ps = wslot_resolve(a.p, a.np, i0 + cc, a.I);
+  const WSlot qs = wslot_resolve(a.q, a.nq, j0 + cc, a.J);
   const int row_begin = blockIdx.z * a.chunk, row_end = min(a.n_rows, row_begin + a.chunk);
   const bool split = gridDim.z > 1;
   for (int b = 0; b < a.B; ++b) {
+    // software pipeline: the next 16-row tile is in registers while the tensor cores work on the current one
+    float pv[LD_IT], qv[LD_IT];
+#pragma unroll
+    for (int k = 0; k < LD_IT; ++k) {
+      pv[k] = wslot_load(ps, b, row_begin + rr0 + 4 * k, a.n_rows, row_end);
+      qv[k] = wslot_load(qs, b, row_begin + rr0 + 4 * k, a.n_rows, row_end);
+    }
     for (int r0 = row_begin; r0 < row_end; r0 += GK) {
 #pragma unroll
-      for (int e4 = 0; e4 < LD_IT; ++e4) {
-        int e = tid + e4 * 256;
-        int ii = e % GM, rr = e / GM;  // coalesced along i
-        int i = i0 + ii, r = r0 + rr;
-        float v = 0.f;
-        if (i < a.I && r < row_end) {
-          int off = 0;
-          for (int s = 0; s < a.np; ++s) {
-            if (i - off < a.p[s].K) { v = seg_load(a.p[s], b, r, i - off, a.n_rows); break; }
-            off += a.p[s].K;
-          }
-        }
-        Ps[rr][ii] = v;
-        int jj = e % GN;
-        int j = j0 + jj;
-        float w = 0.f;
-        if (j < a.J && r < row_end) {
-          int off = 0;
-          for (int s = 0; s < a.nq; ++s) {
-            if (j - off < a.q[s].K) { w = seg_load(a.q[s], b, r, j - off, a.n_rows); break; }
-            off += a.q[s].K;
-          }
-        }
-        Qs[rr][jj] = w;
+      for (int k = 0; k < LD_IT; ++k) {
+        Ps[rr0 + 4 * k][cc] = pv[k];
+        Qs[rr0 + 4 * k][cc] = qv[k];
       }
       __syncthreads();
+      if (r0 + GK < row_end) {
+#pragma unroll
+        for (int k = 0; k < LD_IT; ++k) {
+          pv[k] = wslot_load(ps, b, r0 + GK + rr0 + 4 * k, a.n_rows, row_end);
+          qv[k] = wslot_load(qs, b, r0 + GK + rr0 + 4 * k, a.n_rows, row_end);
+        }
+      }
       if (TC) {
         tile_mma_tf32(Ps, Qs, cfr);
       } else {
 #pragma unroll
         for (int kk = 0; kk < GK; ++kk) {
-          float pv[4], qv[4];
+          float pw[4], qw[4];
 #pragma unroll
-          for (int i = 0; i < 4; ++i) pv[i] = Ps[kk][ty * 4 + i];
+          for (int i = 0; i < 4; ++i) pw[i] = Ps[kk][ty * 4 + i];
 #pragma unroll
-          for (int j = 0; j < 4; ++j) qv[j] = Qs[kk][tx * 4 + j];
+          for (int j = 0; j < 4; ++j) qw[j] = Qs[kk][tx * 4 + j];
 #pragma unroll
           for (int i = 0; i < 4; ++i)
 #pragma unroll
-            for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(pv[i], qv[j], acc[i][j]);
+            for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(pw[i], qw[j], acc[i][j]);
         }
       }
       if (a.colsum && blockIdx.y == 0 && tid < GM) {
