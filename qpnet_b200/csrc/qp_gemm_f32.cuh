@@ -118,53 +118,70 @@ __global__ void __launch_bounds__(256, TC ? 4 : 2) gemm_f32_kernel(GemmArgs a) {
     for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
 
   int koff = 0;
+  // load slots of this thread: A element e = tid + 256 i -> tile row e / GK, k e % GK; W element -> (k, n) by layout
+  const int akk = tid % GK, arr0 = tid / GK;                 // A rows arr0 + (256 / GK) i
   for (int s = 0; s < a.nseg; ++s) {
     const Seg sg = a.seg[s];
     const float* abase = sg.base + (int64_t)b * sg.bstride;
-    for (int k0 = 0; k0 < sg.K; k0 += GK) {
-      // A tile: 64 rows x 16 k
+    // the source row of each of this thread's tile rows is fixed for the whole segment (gathered past tap: one lookup)
+    const float* arow[LD_IT];
 #pragma unroll
-      for (int i = 0; i < LD_IT; ++i) {
-        int e = tid + i * 256;
-        int rr = e / GK, kk = e % GK;
-        int r = r0 + rr, k = k0 + kk;
-        float v = 0.f;
-        if (r < a.n_rows && k < sg.K) {
-          int src = sg.rowmap ? sg.rowmap[(int64_t)b * a.n_rows + r] : r + sg.row_off;
-          if (src >= 0 && src < sg.src_rows) {
-            v = abase[(int64_t)src * sg.ld + k];
-            if (sg.relu) v = fmaxf(v, 0.f);
-          }
-        }
-        As[kk][rr] = v;
+    for (int i = 0; i < LD_IT; ++i) {
+      const int r = r0 + arr0 + (256 / GK) * i;
+      arow[i] = nullptr;
+      if (r < a.n_rows) {
+        const int src = sg.rowmap ? sg.rowmap[(int64_t)b * a.n_rows + r] : r + sg.row_off;
+        if (src >= 0 && src < sg.src_rows) arow[i] = abase + (int64_t)src * sg.ld;
       }
-      // W tile: 64 n x 16 k
+    }
+    auto load_a = [&](int k0, float (&av)[LD_IT]) {
+      const int k = k0 + akk;
 #pragma unroll
       for (int i = 0; i < LD_IT; ++i) {
-        int e = tid + i * 256;
+        float v = (arow[i] && k < sg.K) ? arow[i][k] : 0.f;
+        av[i] = sg.relu ? fmaxf(v, 0.f) : v;
+      }
+    };
+    auto load_w = [&](int k0, float (&wv)[LD_IT]) {
+#pragma unroll
+      for (int i = 0; i < LD_IT; ++i) {
+        const int e = tid + i * 256;
         int nn, kk;
         if (a.w_kn) { kk = e / GN; nn = e % GN; } else { nn = e / GK; kk = e % GK; }
-        int n = n0 + nn, k = k0 + kk;
+        const int n = n0 + nn, k = k0 + kk;
         float v = 0.f;
         if (n < a.N && k < sg.K)
           v = a.w_kn ? a.W[(int64_t)(koff + k) * a.ldw + n] : a.W[(int64_t)n * a.ldw + koff + k];
-        Ws[kk][nn] = v;
+        wv[i] = v;
+      }
+    };
+    // software pipeline inside a segment: the next K-slice is in registers while the current one is contracted
+    float av[LD_IT], wv[LD_IT];
+    load_a(0, av);
+    load_w(0, wv);
+    for (int k0 = 0; k0 < sg.K; k0 += GK) {
+#pragma unroll
+      for (int i = 0; i < LD_IT; ++i) {
+        As[akk][arr0 + (256 / GK) * i] = av[i];
+        const int e = tid + i * 256;
+        if (a.w_kn) Ws[e / GN][e % GN] = wv[i]; else Ws[e % GK][e / GK] = wv[i];
       }
       __syncthreads();
+      if (k0 + GK < sg.K) { load_a(k0 + GK, av); load_w(k0 + GK, wv); }
       if (TC) {
         tile_mma_tf32(As, Ws, cfr);
       } else {
 #pragma unroll
         for (int kk = 0; kk < GK; ++kk) {
-          float av[4], wv[4];
+          float pa[4], pw[4];
 #pragma unroll
-          for (int i = 0; i < 4; ++i) av[i] = As[kk][ty * 4 + i];
+          for (int i = 0; i < 4; ++i) pa[i] = As[kk][ty * 4 + i];
 #pragma unroll
-          for (int j = 0; j < 4; ++j) wv[j] = Ws[kk][tx * 4 + j];
+          for (int j = 0; j < 4; ++j) pw[j] = Ws[kk][tx * 4 + j];
 #pragma unroll
           for (int i = 0; i < 4; ++i)
 #pragma unroll
-            for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], wv[j], acc[i][j]);
+            for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(pa[i], pw[j], acc[i][j]);
         }
       }
       __syncthreads();
