@@ -302,39 +302,57 @@ __device__ __forceinline__ float seg_load(const Seg& sg, int b, int r, int k, in
   return sg.relu ? fmaxf(v, 0.f) : v;
 }
 
-// one load slot of a thread: a fixed output row / column, i.e. a fixed column of one segment of P or Q
+// One load slot of a thread: four consecutive output rows / columns, i.e. four consecutive columns of ONE segment of P
+// or Q (segment widths are multiples of 4 except the aux segment, which takes the scalar path), one tile row.
 struct WSlot {
-  const float* base;   // segment base + column (nullptr: outside the output, loads zero)
+  const float* base;   // segment base + first column (nullptr: outside the output, loads zero)
   const int* rowmap;
   int64_t bstride;
   int ld, row_off, src_rows, relu;
+  int valid;           // columns of the four that exist in the segment
+  int vec;             // 16-byte aligned rows: one float4 load
 };
 __device__ __forceinline__ WSlot wslot_resolve(const Seg* segs, int nseg, int col, int limit) {
   WSlot w; w.base = nullptr; w.rowmap = nullptr; w.bstride = 0; w.ld = 0; w.row_off = 0; w.src_rows = 0; w.relu = 0;
+  w.valid = 0; w.vec = 0;
   if (col >= limit) return w;
   int off = 0;
   for (int s = 0; s < nseg; ++s) {
     if (col - off < segs[s].K) {
       w.base = segs[s].base + (col - off); w.rowmap = segs[s].rowmap; w.bstride = segs[s].bstride; w.ld = segs[s].ld;
       w.row_off = segs[s].row_off; w.src_rows = segs[s].src_rows; w.relu = segs[s].relu;
+      w.valid = min(4, segs[s].K - (col - off));
+      w.vec = w.valid == 4 && (segs[s].ld & 3) == 0 && (segs[s].bstride & 3) == 0 && ((col - off) & 3) == 0 &&
+              (((size_t)segs[s].base) & 15) == 0;
       return w;
     }
     off += segs[s].K;
   }
   return w;
 }
-__device__ __forceinline__ float wslot_load(const WSlot& w, int b, int r, int n_rows, int row_end) {
-  if (!w.base || r >= row_end) return 0.f;
+__device__ __forceinline__ float4 wslot_load(const WSlot& w, int b, int r, int n_rows, int row_end) {
+  float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (!w.base || r >= row_end) return v;
   const int src = w.rowmap ? w.rowmap[(int64_t)b * n_rows + r] : r + w.row_off;
-  if (src < 0 || src >= w.src_rows) return 0.f;
-  const float v = w.base[(int64_t)b * w.bstride + (int64_t)src * w.ld];
-  return w.relu ? fmaxf(v, 0.f) : v;
+  if (src < 0 || src >= w.src_rows) return v;
+  const float* q = w.base + (int64_t)b * w.bstride + (int64_t)src * w.ld;
+  if (w.vec) {
+    v = *(const float4*)q;
+  } else {
+    v.x = q[0];
+    if (w.valid > 1) v.y = q[1];
+    if (w.valid > 2) v.z = q[2];
+    if (w.valid > 3) v.w = q[3];
+  }
+  if (w.relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+  return v;
 }
 
 template <bool TC>
 static __global__ void __launch_bounds__(256, 4) wgrad_f32_kernel(WgradArgs a) {
-  __shared__ float Ps[GK][GM + GPAD];
-  __shared__ float Qs[GK][GN + GPAD];
+  static_assert(GK == 16 && GM == 64 && GN == 64, "one float4 per thread per tile: 16 rows x 16 column quads");
+  __shared__ __align__(16) float Ps[GK][GM + GPAD];
+  __shared__ __align__(16) float Qs[GK][GN + GPAD];
   __shared__ float Cs[TC ? GM : 1][GN + 4];
   float cfr[4][4];
 #pragma unroll
@@ -349,33 +367,23 @@ static __global__ void __launch_bounds__(256, 4) wgrad_f32_kernel(WgradArgs a) {
   for (int i = 0; i < 4; ++i)
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
-  // every load slot of this thread reads a fixed column: element e = tid + 256 k -> column e % 64, tile row e / 64
-  const int cc = tid % GM, rr0 = tid / GM;
-  const WSlot ps = wslot_resolve(a.p, a.np, i0 + cc, a.I);
-  const WSlot qs = wslot_resolve(a.q, a.nq, j0 + cc, a.J);
+  // this thread's slot: tile row tid / 16, columns 4 (tid % 16) .. +3 of the P tile and of the Q tile
+  const int c4 = 4 * (tid % 16), rr = tid / 16;
+  const WSlot ps = wslot_resolve(a.p, a.np, i0 + c4, a.I);
+  const WSlot qs = wslot_resolve(a.q, a.nq, j0 + c4, a.J);
   const int row_begin = blockIdx.z * a.chunk, row_end = min(a.n_rows, row_begin + a.chunk);
   const bool split = gridDim.z > 1;
   for (int b = 0; b < a.B; ++b) {
     // software pipeline: the next 16-row tile is in registers while the tensor cores work on the current one
-    float pv[LD_IT], qv[LD_IT];
-#pragma unroll
-    for (int k = 0; k < LD_IT; ++k) {
-      pv[k] = wslot_load(ps, b, row_begin + rr0 + 4 * k, a.n_rows, row_end);
-      qv[k] = wslot_load(qs, b, row_begin + rr0 + 4 * k, a.n_rows, row_end);
-    }
+    float4 pv = wslot_load(ps, b, row_begin + rr, a.n_rows, row_end);
+    float4 qv = wslot_load(qs, b, row_begin + rr, a.n_rows, row_end);
     for (int r0 = row_begin; r0 < row_end; r0 += GK) {
-#pragma unroll
-      for (int k = 0; k < LD_IT; ++k) {
-        Ps[rr0 + 4 * k][cc] = pv[k];
-        Qs[rr0 + 4 * k][cc] = qv[k];
-      }
+      *(float4*)&Ps[rr][c4] = pv;
+      *(float4*)&Qs[rr][c4] = qv;
       __syncthreads();
       if (r0 + GK < row_end) {
-#pragma unroll
-        for (int k = 0; k < LD_IT; ++k) {
-          pv[k] = wslot_load(ps, b, r0 + GK + rr0 + 4 * k, a.n_rows, row_end);
-          qv[k] = wslot_load(qs, b, r0 + GK + rr0 + 4 * k, a.n_rows, row_end);
-        }
+        pv = wslot_load(ps, b, r0 + GK + rr, a.n_rows, row_end);
+        qv = wslot_load(qs, b, r0 + GK + rr, a.n_rows, row_end);
       }
       if (TC) {
         tile_mma_tf32(Ps, Qs, cfr);
