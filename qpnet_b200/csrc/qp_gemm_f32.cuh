@@ -99,8 +99,8 @@ __device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + __expf
 
 template <int EPI, bool TC>
 __global__ void __launch_bounds__(256, TC ? 4 : 2) gemm_f32_kernel(GemmArgs a) {
-  __shared__ float As[GK][GM + GPAD];
-  __shared__ float Ws[GK][GN + GPAD];
+  __shared__ __align__(16) float As[GK][GM + GPAD];
+  __shared__ __align__(16) float Ws[GK][GN + GPAD];
   __shared__ float Cs[TC ? GM : 1][GN + 4];
   float cfr[4][4];
 #pragma unroll
@@ -118,56 +118,66 @@ __global__ void __launch_bounds__(256, TC ? 4 : 2) gemm_f32_kernel(GemmArgs a) {
     for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
 
   int koff = 0;
-  // load slots of this thread: A element e = tid + 256 i -> tile row e / GK, k e % GK; W element -> (k, n) by layout
-  const int akk = tid % GK, arr0 = tid / GK;                 // A rows arr0 + (256 / GK) i
+  // load slots of this thread, one float4 each per K-slice: A tile row tid / 4, k (tid % 4) * 4 .. +3; W tile: k tid / 16,
+  // n (tid % 16) * 4 .. +3 when n is contiguous (w_kn), else n tid / 4, k (tid % 4) * 4 .. +3
+  static_assert(GK == 16 && GM == 64 && GN == 64, "one float4 per thread per tile");
+  const int ar = tid / 4, ak4 = (tid % 4) * 4;
+  const int wk = a.w_kn ? tid / 16 : (tid % 4) * 4, wn = a.w_kn ? (tid % 16) * 4 : tid / 4;
+  const bool w_vec = (a.ldw & 3) == 0 && (((size_t)a.W) & 15) == 0;
   for (int s = 0; s < a.nseg; ++s) {
     const Seg sg = a.seg[s];
-    const float* abase = sg.base + (int64_t)b * sg.bstride;
-    // the source row of each of this thread's tile rows is fixed for the whole segment (gathered past tap: one lookup)
-    const float* arow[LD_IT];
-#pragma unroll
-    for (int i = 0; i < LD_IT; ++i) {
-      const int r = r0 + arr0 + (256 / GK) * i;
-      arow[i] = nullptr;
+    // the source row of this thread's tile row is fixed for the whole segment (gathered past tap: one lookup)
+    const float* arow = nullptr;
+    {
+      const int r = r0 + ar;
       if (r < a.n_rows) {
         const int src = sg.rowmap ? sg.rowmap[(int64_t)b * a.n_rows + r] : r + sg.row_off;
-        if (src >= 0 && src < sg.src_rows) arow[i] = abase + (int64_t)src * sg.ld;
+        if (src >= 0 && src < sg.src_rows) arow = sg.base + (int64_t)b * sg.bstride + (int64_t)src * sg.ld;
       }
     }
-    auto load_a = [&](int k0, float (&av)[LD_IT]) {
-      const int k = k0 + akk;
-#pragma unroll
-      for (int i = 0; i < LD_IT; ++i) {
-        float v = (arow[i] && k < sg.K) ? arow[i][k] : 0.f;
-        av[i] = sg.relu ? fmaxf(v, 0.f) : v;
+    const bool a_vec = (sg.ld & 3) == 0 && (sg.bstride & 3) == 0 && (((size_t)sg.base) & 15) == 0;
+    auto load_a = [&](int k0) -> float4 {
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      const int k = k0 + ak4;
+      if (arow && k < sg.K) {
+        if (a_vec && k + 3 < sg.K) v = *(const float4*)(arow + k);
+        else {
+          v.x = arow[k];
+          if (k + 1 < sg.K) v.y = arow[k + 1];
+          if (k + 2 < sg.K) v.z = arow[k + 2];
+          if (k + 3 < sg.K) v.w = arow[k + 3];
+        }
+        if (sg.relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
       }
+      return v;
     };
-    auto load_w = [&](int k0, float (&wv)[LD_IT]) {
-#pragma unroll
-      for (int i = 0; i < LD_IT; ++i) {
-        const int e = tid + i * 256;
-        int nn, kk;
-        if (a.w_kn) { kk = e / GN; nn = e % GN; } else { nn = e / GK; kk = e % GK; }
-        const int n = n0 + nn, k = k0 + kk;
-        float v = 0.f;
-        if (n < a.N && k < sg.K)
-          v = a.w_kn ? a.W[(int64_t)(koff + k) * a.ldw + n] : a.W[(int64_t)n * a.ldw + koff + k];
-        wv[i] = v;
+    auto load_w = [&](int k0) -> float4 {
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (a.w_kn) {      // W[k][n]: four consecutive n
+        const int k = k0 + wk, n = n0 + wn;
+        if (k < sg.K && n < a.N) {
+          const float* q = a.W + (int64_t)(koff + k) * a.ldw + n;
+          if (w_vec && n + 3 < a.N && (n & 3) == 0) v = *(const float4*)q;
+          else { v.x = q[0]; if (n + 1 < a.N) v.y = q[1]; if (n + 2 < a.N) v.z = q[2]; if (n + 3 < a.N) v.w = q[3]; }
+        }
+      } else {           // W[n][k]: four consecutive k
+        const int k = k0 + wk, n = n0 + wn;
+        if (k < sg.K && n < a.N) {
+          const float* q = a.W + (int64_t)n * a.ldw + koff + k;
+          if (w_vec && k + 3 < sg.K && ((koff + k) & 3) == 0) v = *(const float4*)q;
+          else { v.x = q[0]; if (k + 1 < sg.K) v.y = q[1]; if (k + 2 < sg.K) v.z = q[2]; if (k + 3 < sg.K) v.w = q[3]; }
+        }
       }
+      return v;
     };
     // software pipeline inside a segment: the next K-slice is in registers while the current one is contracted
-    float av[LD_IT], wv[LD_IT];
-    load_a(0, av);
-    load_w(0, wv);
+    float4 av = load_a(0), wv = load_w(0);
     for (int k0 = 0; k0 < sg.K; k0 += GK) {
-#pragma unroll
-      for (int i = 0; i < LD_IT; ++i) {
-        As[akk][arr0 + (256 / GK) * i] = av[i];
-        const int e = tid + i * 256;
-        if (a.w_kn) Ws[e / GN][e % GN] = wv[i]; else Ws[e % GK][e / GK] = wv[i];
-      }
+      As[ak4][ar] = av.x; As[ak4 + 1][ar] = av.y; As[ak4 + 2][ar] = av.z; As[ak4 + 3][ar] = av.w;
+      if (a.w_kn) *(float4*)&Ws[wk][wn] = wv;
+      else { Ws[wk][wn] = wv.x; Ws[wk + 1][wn] = wv.y; Ws[wk + 2][wn] = wv.z; Ws[wk + 3][wn] = wv.w; }
       __syncthreads();
-      if (k0 + GK < sg.K) { load_a(k0 + GK, av); load_w(k0 + GK, wv); }
+      if (k0 + GK < sg.K) { av = load_a(k0 + GK); wv = load_w(k0 + GK); }
       if (TC) {
         tile_mma_tf32(As, Ws, cfr);
       } else {
