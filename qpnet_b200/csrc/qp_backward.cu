@@ -2,7 +2,10 @@
 // qpnet_train.py:526-531): exact fp32 SIMT contractions, or TF32 tensor-core contractions (fp32 accumulate) when the
 // forward ran on the bf16 tensor-core path (QP_F_BF16).  Consumes the workspace a QP_F_SAVE forward
 // filled.  All contractions reuse the segmented GEMM / weight-gradient kernels.
+#include <stdlib.h>
+
 #include "qp_gemm_f32.cuh"
+#include "qp_tc.cuh"
 #include "qp_tf_plan.cuh"
 
 namespace qp {
@@ -74,6 +77,14 @@ __global__ void upsample_grad_kernel(const float* __restrict__ dHup, const float
   if (threadIdx.x == 0) { dw[j] = r0[0]; atomicAdd(db, r1[0]); }
 }
 
+// Which contractions of the bf16 training path's backward run on tcgen05 (qp_tc.cu), bit mask, default all:
+// 1 weight gradients, 2 dz -> dgate GEMM, 4 dX GEMM.  QPNET_BWD_TC=0 is the TF32 mma.sync backward (A/B timing, bring-up).
+static int bwd_tc_mask() {
+  static int m = -1;
+  if (m < 0) { const char* e = getenv("QPNET_BWD_TC"); m = e ? atoi(e) & 7 : 7; }
+  return m;
+}
+
 // tc: TF32 tensor-core contractions (the backward of the bf16 training path); false: exact fp32 SIMT
 int tf_backward_f32(const QpArch* arch, const float* const* tensors, const int64_t* x, const float* h,
                     const TfPlan& p, const float* dlogits, float* const* grads, bool tc, cudaStream_t st) {
@@ -84,6 +95,10 @@ int tf_backward_f32(const QpArch* arch, const float* const* tensors, const int64
   for (int i = 0; i < ntens; ++i)
     if (!grads[i]) return set_error(QP_EINVAL, "backward: gradient tensor %d is NULL", i);
   QP_CUDA(cudaMemcpyAsync((void*)p.gtab, grads, sizeof(float*) * ntens, cudaMemcpyHostToDevice, st));
+  // bf16 operands on tcgen05 for the residual blocks (the head stays on the TF32 kernels: 2 % of the work)
+  const int mask = (tc && p.ones_col >= 0) ? bwd_tc_mask() : 0;
+  const bool tc_w = mask & 1, tc_dz = mask & 2, tc_dx = mask & 4;
+  const int Kgp = p.Kgp;
 
   // ---- head -------------------------------------------------------------------------
   {
@@ -111,6 +126,16 @@ int tf_backward_f32(const QpArch* arch, const float* const* tensors, const int64
     if (int e = launch_gemm<EPI_PLAIN>(g1, st, tc)) return e;
   }
   QP_CUDA(cudaMemsetAsync(p.dHup, 0, sizeof(float) * (size_t)B * L0 * A, st));
+  if (mask) {
+    QP_CUDA(cudaMemsetAsync(p.dbskip, 0, sizeof(float) * S, st));
+    if (int e = tc::f32_to_bf16_colsum(p.dskip, (long long)B * bl, S, p.dskip_bf, p.dbskip, st)) return e;
+  }
+  if (tc_w) {   // the tcgen05 weight-gradient kernel accumulates its row splits into zeroed outputs
+    QP_CUDA(cudaMemsetAsync(p.dW.Wg, 0, sizeof(float) * pd.wg_elems() * L, st));
+    QP_CUDA(cudaMemsetAsync(p.dW.bg, 0, sizeof(float) * (size_t)2 * C * L, st));
+    QP_CUDA(cudaMemsetAsync(p.dW.Wrs, 0, sizeof(float) * pd.wrs_elems() * L, st));
+    QP_CUDA(cudaMemsetAsync(p.dW.brs, 0, sizeof(float) * (size_t)(C + S) * L, st));
+  }
 
   // ---- residual blocks, last to first -----------------------------------------------
   const float* dXnext = nullptr;
@@ -119,8 +144,21 @@ int tf_backward_f32(const QpArch* arch, const float* const* tensors, const int64
     const int Lin = p.Lin[l], sh = p.shift[l], n = Lin - sh;
     const int* rowmap = l >= pd.nF ? p.pastrow[l - pd.nF] : nullptr;
     float* Wrs = p.W.Wrs + pd.wrs_elems() * l;
+    // bf16 copy of dXnext (+ its column sums = the residual-projection bias gradient)
+    if (mask && dXnext)
+      if (int e = tc::f32_to_bf16_colsum(dXnext, (long long)B * n, C, p.dX_bf, tc_w ? p.dW.brs + (size_t)(C + S) * l : nullptr, st)) return e;
     // dz = dXnext * R + dskip * K   ->  dgate (through the gate non-linearity)
-    {
+    if (tc_dz) {
+      tc::Args g = {};
+      int s = 0;
+      if (dXnext) g.seg[s++] = tc::Seg{p.dX_bf, (long long)n * C, C, nullptr, 0, n, C};
+      g.seg[s++] = tc::Seg{p.dskip_bf, (long long)bl * S, S, nullptr, -(n - bl), bl, S};
+      g.nseg = s;
+      g.W = p.Wrs_bf + (size_t)l * (C + S) * C + (dXnext ? 0 : (size_t)C * C); g.ldw = C; g.w_mn = 1;
+      g.B = B; g.n_rows = n; g.N = C; g.BN = C < 256 ? C : 256;
+      g.gin = p.G[l]; g.dgate_bf = p.dgate_bf; g.dgate_f32 = (tc_w && tc_dx) ? nullptr : p.dgate;
+      if (int e = tc::gemm_dgate(g, st)) return e;
+    } else {
       GemmArgs g = {};
       int s = 0;
       if (dXnext) g.seg[s++] = mk(dXnext, (int64_t)n * C, C, nullptr, 0, n, C);
@@ -131,9 +169,20 @@ int tf_backward_f32(const QpArch* arch, const float* const* tensors, const int64
       g.gsave = p.G[l]; g.gsave_bstride = (int64_t)n * 2 * C;
       g.out = p.dgate; g.out_bstride = (int64_t)n * 2 * C; g.ldo = 2 * C;
       if (int e = launch_gemm<EPI_DGATE>(g, st, tc)) return e;
+      if (mask)
+        if (int e = tc::f32_to_bf16_pad(p.dgate, (long long)B * n, 2 * C, 2 * C, p.dgate_bf, 0, st)) return e;
     }
     // d[res | skip] weights and biases
-    {
+    if (tc_w) {
+      tc::WgradArgs w = {};
+      w.p[0] = tc::Seg{dXnext ? p.dX_bf : nullptr, (long long)n * C, C, nullptr, 0, n, C};   // all-zero for the last block
+      w.p[1] = tc::Seg{p.dskip_bf, (long long)bl * S, S, nullptr, -(n - bl), bl, S}; w.np = 2;
+      w.q[0] = tc::Seg{p.Zbf[l], (long long)n * C, C, nullptr, 0, n, C}; w.nq = 1;
+      w.B = B; w.n_rows = n; w.I = C + S; w.J = C;
+      w.out = p.dW.Wrs + pd.wrs_elems() * l; w.ldo = C;
+      if (int e = tc::wgrad(w, st)) return e;
+      QP_CUDA(cudaMemcpyAsync(p.dW.brs + (size_t)(C + S) * l + C, p.dbskip, sizeof(float) * S, cudaMemcpyDeviceToDevice, st));
+    } else {
       WgradArgs w = {};
       w.p[0] = mk(dXnext, (int64_t)n * C, C, nullptr, 0, dXnext ? n : 0, C);   // dead (all-zero) for the last block
       w.p[1] = mk(p.dskip, (int64_t)bl * S, S, nullptr, -(n - bl), bl, S); w.np = 2;
@@ -142,8 +191,18 @@ int tf_backward_f32(const QpArch* arch, const float* const* tensors, const int64
       w.out = p.dW.Wrs + pd.wrs_elems() * l; w.ldo = C; w.colsum = p.dW.brs + (size_t)(C + S) * l;
       if (int e = launch_wgrad(w, st, tc)) return e;
     }
-    // d gate weights / biases:  dgate^T * [x_past | x_cur | h_up]
-    {
+    // d gate weights / biases:  dgate^T * [x_past | x_cur | h_up | 1]
+    if (tc_w) {
+      tc::WgradArgs w = {};
+      w.p[0] = tc::Seg{p.dgate_bf, (long long)n * 2 * C, 2 * C, nullptr, 0, n, 2 * C}; w.np = 1;
+      w.q[0] = tc::Seg{p.Xbf[l], (long long)Lin * C, C, rowmap, 0, Lin, C};
+      w.q[1] = tc::Seg{p.Xbf[l], (long long)Lin * C, C, nullptr, sh, Lin, C};
+      w.q[2] = tc::Seg{p.Hup_bf, (long long)L0 * 64, 64, nullptr, L0 - n, L0, 64}; w.nq = 3;
+      w.B = B; w.n_rows = n; w.I = 2 * C; w.J = pd.Kg;
+      w.out = p.dW.Wg + pd.wg_elems() * l; w.ldo = pd.Kg;
+      w.ones_out = p.dW.bg + (size_t)2 * C * l; w.ones_col = 2 * C + p.ones_col;
+      if (int e = tc::wgrad(w, st)) return e;
+    } else {
       WgradArgs w = {};
       w.p[0] = mk(p.dgate, (int64_t)n * 2 * C, 2 * C, nullptr, 0, n, 2 * C); w.np = 1;
       w.q[0] = mk(p.X[l], (int64_t)Lin * C, C, rowmap, 0, Lin, C);
@@ -157,6 +216,18 @@ int tf_backward_f32(const QpArch* arch, const float* const* tensors, const int64
     {
       float* dX = pong[l & 1];
       QP_CUDA(cudaMemsetAsync(dX, 0, sizeof(float) * (size_t)B * Lin * C, st));
+      if (tc_dx) {
+        tc::Args g = {};
+        g.seg[0] = tc::Seg{p.dgate_bf, (long long)n * 2 * C, 2 * C, nullptr, 0, n, 2 * C}; g.nseg = 1;
+        g.W = p.Wg_bf + (size_t)l * 2 * C * Kgp; g.ldw = Kgp; g.w_mn = 1;
+        g.B = B; g.n_rows = n; g.N = Kgp; g.BN = Kgp < 256 ? Kgp : 256; g.C = C; g.A = A;
+        g.dx = dX; g.dx_bstride = (long long)Lin * C; g.dx_rowmap = rowmap; g.dx_past_off = 0; g.dx_cur_off = sh; g.dx_rows = Lin;
+        g.resid = dXnext; g.resid_bstride = (long long)n * C;
+        g.dh = p.dHup; g.dh_bstride = (long long)L0 * A; g.dh_off = L0 - n;
+        if (int e = tc::gemm_dx(g, st)) return e;
+        dXnext = dX;
+        continue;
+      }
       GemmArgs g = {};
       g.seg[0] = mk(p.dgate, (int64_t)n * 2 * C, 2 * C, nullptr, 0, n, 2 * C); g.nseg = 1;
       g.W = p.W.Wg + pd.wg_elems() * l; g.ldw = pd.Kg; g.w_kn = 1;

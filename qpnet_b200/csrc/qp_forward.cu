@@ -137,7 +137,7 @@ int tf_forward_bf16(const QpArch* arch, const float* const* tensors, const int64
   upsample_kernel<<<dim3((unsigned)(((int64_t)L0 * A + 255) / 256), B), 256, 0, st>>>(
       h, A, p.F, pd.U, L0, tensors[tm.up_w()], tensors[tm.up_b()], p.Hup);
   QP_LAUNCH_CHECK();
-  if (int e = tc::f32_to_bf16_pad(p.Hup, (long long)B * L0, A, 64, p.Hup_bf, 0, st)) return e;
+  if (int e = tc::f32_to_bf16_pad(p.Hup, (long long)B * L0, A, 64, p.Hup_bf, 0, st, p.ones_col)) return e;
   for (int l = 0; l < pd.L; ++l) {
     const int Lin = p.Lin[l], sh = p.shift[l], n = Lin - sh;
     const int* rowmap = nullptr;
@@ -147,7 +147,7 @@ int tf_forward_bf16(const QpArch* arch, const float* const* tensors, const int64
       QP_LAUNCH_CHECK();
       rowmap = pr;
     }
-    const __nv_bfloat16* Xin = p.Xbf[l & 1];
+    const __nv_bfloat16* Xin = p.Xbf[l];
     tc::Args g = {};
     g.seg[0] = tc::Seg{Xin, (long long)Lin * C, C, rowmap, 0, Lin, C};
     g.seg[1] = tc::Seg{Xin, (long long)Lin * C, C, nullptr, sh, Lin, C};
@@ -156,11 +156,11 @@ int tf_forward_bf16(const QpArch* arch, const float* const* tensors, const int64
     g.W = p.Wg_bf + (size_t)l * 2 * C * Kgp; g.ldw = Kgp;
     g.bias = p.W.bg + (size_t)2 * C * l;
     g.B = B; g.n_rows = n; g.N = 2 * C; g.n_begin = 0; g.BN = 2 * C < 256 ? 2 * C : 256;
-    g.z_bf = p.Zbf; g.z_f32 = save ? p.Z[l] : nullptr; g.gsave = save ? p.G[l] : nullptr;
+    g.z_bf = p.Zbf[l]; g.z_f32 = save ? p.Z[l] : nullptr; g.gsave = save ? p.G[l] : nullptr;
     if (int e = tc::gemm_gate(g, st)) return e;
 
     tc::Args r = {};
-    r.seg[0] = tc::Seg{p.Zbf, (long long)n * C, C, nullptr, 0, n, C};
+    r.seg[0] = tc::Seg{p.Zbf[l], (long long)n * C, C, nullptr, 0, n, C};
     r.nseg = 1;
     r.W = p.Wrs_bf + (size_t)l * (C + S) * C; r.ldw = C;
     r.bias = p.W.brs + (size_t)(C + S) * l;
@@ -169,7 +169,7 @@ int tf_forward_bf16(const QpArch* arch, const float* const* tensors, const int64
     r.BN = (r.N - r.n_begin) < 256 ? (r.N - r.n_begin) : 256;
     r.C = C; r.S = S;
     r.xcur = p.X[l]; r.xcur_bstride = (long long)Lin * C; r.xcur_off = sh;
-    r.xnext = (l + 1 < pd.L) ? p.X[l + 1] : nullptr; r.xnext_bf = p.Xbf[(l + 1) & 1];
+    r.xnext = (l + 1 < pd.L) ? p.X[l + 1] : nullptr; r.xnext_bf = p.Xbf[l + 1];
     r.skip = p.skipsum; r.skip_bstride = (long long)bl * S; r.skip_row0 = n - bl; r.skip_accum = l > 0;
     if (int e = tc::gemm_resskip(r, st)) return e;
   }

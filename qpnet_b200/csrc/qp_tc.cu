@@ -14,6 +14,10 @@
 // * one output tile per CTA; grid = (row tiles, column tiles, batch).
 #include "qp_tc.cuh"
 
+#include <stdlib.h>
+
+#include <algorithm>
+
 namespace qp {
 namespace tc {
 
@@ -29,6 +33,10 @@ constexpr long long WAIT_TIMEOUT_CYCLES = 4000000000LL;   // ~2 s: a lost barrie
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(dst), "l"(src) : "memory");
+}
+// src_bytes = 0: the 16 destination bytes are zero-filled (rows outside a segment's source range)
+__device__ __forceinline__ void cp_async16z(uint32_t dst, const void* src, uint32_t src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
 template <int N>
@@ -64,9 +72,24 @@ __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::
 __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
   return (uint64_t)((saddr & 0x3FFFFu) >> 4) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
 }
-// kind::f16 instruction descriptor (cute::UMMA::InstrDescriptor): D fp32, A/B bf16, both K-major.
-__device__ __forceinline__ uint32_t umma_idesc(int M, int N) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+// MN-major SWIZZLE_128B descriptor (cute: Swizzle<3,4,3> o ((8,n),(8,k)):((1,LBO),(8,SBO)) in 16-byte units): a tile
+// is stored as 64-element (128-byte) MN rows, one per K index, eight K rows to a 1024-byte swizzle atom; SBO = bytes
+// between consecutive 8-row K groups, LBO = bytes between consecutive 64-wide MN blocks.
+constexpr uint32_t MN_SBO = 1024, MN_LBO = 8192;   // a 64 (MN) x 64 (K) block is 8 consecutive atoms
+__device__ __forceinline__ uint64_t umma_desc_mn(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
+  return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)(lbo >> 4) << 16) | ((uint64_t)(sbo >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
+// byte offset of the 16-byte piece c (8 MN elements) of K row k inside a 64 x 64 MN-major block
+__device__ __forceinline__ uint32_t mn_piece(int k, int c) {
+  return (uint32_t)((k >> 3) * 1024 + (k & 7) * 128 + ((c ^ (k & 7)) << 4));
+}
+// kind::f16 instruction descriptor (cute::UMMA::InstrDescriptor): D fp32, A/B bf16; bit 15 / 16: A / B operand MN-major.
+__device__ __forceinline__ uint32_t umma_idesc(int M, int N, int a_mn = 0, int b_mn = 0) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_mn << 15) | ((uint32_t)b_mn << 16) | ((uint32_t)(N >> 3) << 17) |
+         ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ void red_add4(float* p, float x, float y, float z, float w) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};\n" ::"l"(p), "f"(x), "f"(y), "f"(z), "f"(w) : "memory");
 }
 __device__ __forceinline__ void umma(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
   asm volatile("{\n .reg .pred p;\n setp.ne.b32 p, %4, 0;\n tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}\n"
@@ -132,12 +155,15 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(Args a) {
     const int w0 = min(n0 + tid, a.N - 1), w1 = min(n0 + 128 + tid, a.N - 1);
     // a thread only copies the weight rows that exist in this tile (BN may be 32..256 in steps of 32)
     const bool ldb0 = tid < a.BN, ldb1 = 128 + tid < a.BN;
+    // MN-major weights (w_mn): thread -> 16-byte piece tid & 7 of K rows (tid >> 3) + 16 g, every 64-column block
+    const int wc = tid & 7, wkr = tid >> 3, wblk = ncols >> 6;
     int kc = 0, koff = 0;
     for (int s = 0; s < a.nseg; ++s) {
       const Seg sg = a.seg[s];
       int src = sg.rowmap ? sg.rowmap[(long long)b * a.n_rows + rr] : rr + sg.row_off;
+      const uint32_t abytes = (sg.base != nullptr && src >= 0 && src < sg.src_rows) ? 16u : 0u;   // else the row reads zero
       src = max(0, min(src, sg.src_rows - 1));
-      const __nv_bfloat16* arow = sg.base + (long long)b * sg.bstride + (long long)src * sg.ld;
+      const __nv_bfloat16* arow = abytes ? sg.base + (long long)b * sg.bstride + (long long)src * sg.ld : a.W;
       const __nv_bfloat16* wrow0 = a.W + (long long)w0 * a.ldw + koff;
       const __nv_bfloat16* wrow1 = a.W + (long long)w1 * a.ldw + koff;
       for (int k0 = 0; k0 < sg.K; k0 += BK, ++kc) {
@@ -146,12 +172,21 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(Args a) {
         const uint32_t sA = sbase + stage * stage_bytes + row_off;
         const uint32_t sB = sA + BM * 128;
 #pragma unroll
-        for (int c = 0; c < 8; ++c) cp_async16(sA + ((c ^ sw) << 4), arow + k0 + c * 8);
-        if (ldb0) {
+        for (int c = 0; c < 8; ++c) cp_async16z(sA + ((c ^ sw) << 4), abytes ? arow + k0 + c * 8 : arow, abytes);
+        if (a.w_mn) {
+          const uint32_t sBm = sbase + stage * stage_bytes + BM * 128;
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            const int k = wkr + 16 * g;
+            const __nv_bfloat16* wr = a.W + (long long)(koff + k0 + k) * a.ldw + n0 + wc * 8;
+            const uint32_t dst = sBm + mn_piece(k, wc);
+            for (int q = 0; q < wblk; ++q) cp_async16(dst + q * MN_LBO, wr + q * 64);
+          }
+        } else if (ldb0) {
 #pragma unroll
           for (int c = 0; c < 8; ++c) cp_async16(sB + ((c ^ sw) << 4), wrow0 + k0 + c * 8);
         }
-        if (ldb1) {
+        if (!a.w_mn && ldb1) {
 #pragma unroll
           for (int c = 0; c < 8; ++c) cp_async16(sB + 16 * 1024 + ((c ^ sw) << 4), wrow1 + k0 + c * 8);
         }
@@ -240,6 +275,62 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(Args a) {
             }
           }
         }
+      } else if (EPI == EPI_DGATE) {
+        // acc = dz[r][c], c = n .. n + 31 -> dgate columns 2c, 2c + 1 through the saved sigmoid / tanh values
+        if (rv) {
+          const long long row = (long long)b * a.n_rows + r;
+          const float4* gp = (const float4*)(a.gin + row * (2 * a.N) + 2 * n);
+          float o[64];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const float4 gv = gp[j];   // (sg, th) of channels n + 2j, n + 2j + 1
+            const float dz0 = __uint_as_float(v[2 * j]), dz1 = __uint_as_float(v[2 * j + 1]);
+            o[4 * j] = dz0 * gv.y * gv.x * (1.f - gv.x);
+            o[4 * j + 1] = dz0 * gv.x * (1.f - gv.y * gv.y);
+            o[4 * j + 2] = dz1 * gv.w * gv.z * (1.f - gv.z);
+            o[4 * j + 3] = dz1 * gv.z * (1.f - gv.w * gv.w);
+          }
+          uint4* ob = (uint4*)(a.dgate_bf + row * (2 * a.N) + 2 * n);
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            ob[j] = make_uint4(pack_bf16(o[8 * j], o[8 * j + 1]), pack_bf16(o[8 * j + 2], o[8 * j + 3]),
+                               pack_bf16(o[8 * j + 4], o[8 * j + 5]), pack_bf16(o[8 * j + 6], o[8 * j + 7]));
+          if (a.dgate_f32) {
+            float4* of = (float4*)(a.dgate_f32 + row * (2 * a.N) + 2 * n);
+#pragma unroll
+            for (int j = 0; j < 16; ++j) of[j] = make_float4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
+          }
+        }
+      } else if (EPI == EPI_DX) {
+        // acc = (dgate * Wg)[r][k], k = n .. n + 31 inside one of [past C | current C | aux]
+        if (rv) {
+          if (n < a.C) {
+            const int src = a.dx_rowmap ? a.dx_rowmap[(long long)b * a.n_rows + r] : r + a.dx_past_off;
+            if (src >= 0 && src < a.dx_rows) {
+              float* q = a.dx + (long long)b * a.dx_bstride + (long long)src * a.C + n;
+#pragma unroll
+              for (int j = 0; j < 8; ++j)
+                red_add4(q + 4 * j, __uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]),
+                         __uint_as_float(v[4 * j + 3]));
+            }
+          } else if (n < 2 * a.C) {
+            const int c = n - a.C;
+            float* q = a.dx + (long long)b * a.dx_bstride + (long long)(r + a.dx_cur_off) * a.C + c;
+            const float4* rs = a.resid ? (const float4*)(a.resid + (long long)b * a.resid_bstride + (long long)r * a.C + c) : nullptr;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              float4 x4 = rs ? rs[j] : make_float4(0.f, 0.f, 0.f, 0.f);
+              red_add4(q + 4 * j, __uint_as_float(v[4 * j]) + x4.x, __uint_as_float(v[4 * j + 1]) + x4.y,
+                       __uint_as_float(v[4 * j + 2]) + x4.z, __uint_as_float(v[4 * j + 3]) + x4.w);
+            }
+          } else {
+            const int ka = n - 2 * a.C;
+            float* q = a.dh + (long long)b * a.dh_bstride + (long long)(r + a.dh_off) * a.A;
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (ka + j < a.A) q[ka + j] += __uint_as_float(v[j]);
+          }
+        }
       } else {  // EPI_HEAD: out = acc + bias (fp32, pre-activation) and optionally relu(out) as the next bf16 operand
         if (rv) {
           float o[32];
@@ -263,16 +354,18 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(Args a) {
   } else {
     // ================================================================== MMA issuer (one thread)
     if (lane == 0) {
-      const uint32_t idesc = umma_idesc(BM, ncols);
+      const uint32_t idesc = umma_idesc(BM, ncols, 0, a.w_mn);
+      const uint32_t bstep = a.w_mn ? (2 * MN_SBO) >> 4 : 2;   // MN-major: K = 16 is two 8-row groups; K-major: 32 bytes
       for (int kc = 0; kc < nk; ++kc) {
         const int stage = kc % STAGES, it = kc / STAGES;
         mbar_wait(bar0 + 8 * stage, (uint32_t)it & 1u);
         tc_fence_after();
         const uint64_t ad = umma_desc(sbase + stage * stage_bytes);
-        const uint64_t bd = umma_desc(sbase + stage * stage_bytes + BM * 128);
+        const uint32_t sb = sbase + stage * stage_bytes + BM * 128;
+        const uint64_t bd = a.w_mn ? umma_desc_mn(sb, a.mn_lbo, a.mn_sbo) : umma_desc(sb);
 #pragma unroll
         for (int k = 0; k < BK / 16; ++k)          // +32 bytes per K = 16 step inside the 128-byte swizzle row
-          umma(tmem, ad + 2 * k, bd + 2 * k, idesc, (uint32_t)(kc | k));
+          umma(tmem, ad + 2 * k, bd + bstep * k, idesc, (uint32_t)(kc | k));
         umma_commit(bar0 + 8 * (STAGES + stage));  // slot free once these MMAs retire
       }
       umma_commit(bar0 + 8 * 2 * STAGES);           // accumulator complete
@@ -284,18 +377,31 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(Args a) {
   if (warp == 4) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem), "r"(TMEM_COLS) : "memory");
 }
 
+// QPNET_MN_SWAP=1 exchanges the two MN-major descriptor strides (bring-up aid; the default is the cute convention)
+static void mn_strides(uint32_t* lbo, uint32_t* sbo) {
+  static int swap = -1;
+  if (swap < 0) { const char* e = getenv("QPNET_MN_SWAP"); swap = (e && e[0] == '1') ? 1 : 0; }
+  *lbo = swap ? MN_SBO : MN_LBO;
+  *sbo = swap ? MN_LBO : MN_SBO;
+}
+
 template <int EPI>
-static int launch(const Args& a, cudaStream_t st) {
+static int launch(const Args& a0, cudaStream_t st) {
+  Args a = a0;
+  mn_strides(&a.mn_lbo, &a.mn_sbo);
   if (a.n_rows <= 0 || a.B <= 0 || a.N - a.n_begin <= 0) return QP_OK;
   int ktot = 0;
   for (int s = 0; s < a.nseg; ++s) {
     QP_REQUIRE(a.seg[s].K > 0 && a.seg[s].K % BK == 0, "tc gemm: K segment %d not a multiple of %d", a.seg[s].K, BK);
     ktot += a.seg[s].K;
   }
-  QP_REQUIRE(a.BN >= 32 && a.BN <= 256 && a.BN % 32 == 0 && (a.N - a.n_begin) % 32 == 0 && a.ldw >= ktot,
+  QP_REQUIRE(a.BN >= 32 && a.BN <= 256 && a.BN % 32 == 0 && (a.N - a.n_begin) % 32 == 0 && (a.w_mn || a.ldw >= ktot),
              "tc gemm: bad tile shape N=%d BN=%d", a.N, a.BN);
+  if (a.w_mn)
+    QP_REQUIRE(a.BN % 64 == 0 && (a.N - a.n_begin) % 64 == 0 && a.ldw % 8 == 0 && a.n_begin % 8 == 0,
+               "tc gemm: MN-major weights need 64-column blocks (N=%d BN=%d ldw=%d)", a.N, a.BN, a.ldw);
   const size_t smem = (size_t)STAGES * (BM * 128 + a.BN * 128) + (2 * STAGES + 1) * 8 + 16 + 1024;
-  static bool configured[3] = {false, false, false};
+  static bool configured[5] = {false, false, false, false, false};
   if (!configured[EPI]) {
     QP_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     configured[EPI] = true;
@@ -309,23 +415,32 @@ static int launch(const Args& a, cudaStream_t st) {
 int gemm_gate(const Args& a, cudaStream_t st) { return launch<EPI_GATE>(a, st); }
 int gemm_resskip(const Args& a, cudaStream_t st) { return launch<EPI_RESSKIP>(a, st); }
 int gemm_head(const Args& a, cudaStream_t st) { return launch<EPI_HEAD>(a, st); }
+int gemm_dgate(const Args& a, cudaStream_t st) {
+  QP_REQUIRE(a.w_mn && a.gin && a.dgate_bf, "tc dgate gemm: missing operands");
+  return launch<EPI_DGATE>(a, st);
+}
+int gemm_dx(const Args& a, cudaStream_t st) {
+  QP_REQUIRE(a.w_mn && a.dx && a.dh && a.C % 32 == 0, "tc dx gemm: missing operands");
+  return launch<EPI_DX>(a, st);
+}
 
 // ------------------------------------------------------------------ small bf16 helpers
 __global__ void f32_to_bf16_pad_kernel(const float* __restrict__ src, long long rows, int K, int Kp,
-                                       __nv_bfloat16* __restrict__ dst, int relu) {
+                                       __nv_bfloat16* __restrict__ dst, int relu, int ones_col) {
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= rows * Kp) return;
   long long r = i / Kp;
   int k = (int)(i % Kp);
-  float v = k < K ? src[r * K + k] : 0.f;
+  float v = k < K ? src[r * K + k] : (k == ones_col ? 1.f : 0.f);
   if (relu) v = fmaxf(v, 0.f);
   dst[i] = __float2bfloat16_rn(v);
 }
 
-int f32_to_bf16_pad(const float* src, long long rows, int K, int Kp, __nv_bfloat16* dst, int relu, cudaStream_t st) {
+int f32_to_bf16_pad(const float* src, long long rows, int K, int Kp, __nv_bfloat16* dst, int relu, cudaStream_t st,
+                    int ones_col) {
   long long n = rows * Kp;
   if (n <= 0) return QP_OK;
-  f32_to_bf16_pad_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(src, rows, K, Kp, dst, relu);
+  f32_to_bf16_pad_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(src, rows, K, Kp, dst, relu, ones_col);
   QP_LAUNCH_CHECK();
   return QP_OK;
 }
@@ -344,6 +459,225 @@ __global__ void pack_wg_bf16_kernel(const float* __restrict__ Wg, long long rows
 int pack_wg_bf16(const float* Wg, long long rows, int twoC, int Kg, int Kgp, __nv_bfloat16* dst, cudaStream_t st) {
   long long n = rows * Kgp;
   pack_wg_bf16_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(Wg, rows, twoC, Kg, Kgp, dst);
+  QP_LAUNCH_CHECK();
+  return QP_OK;
+}
+
+// ------------------------------------------------------------------ fp32 -> bf16 copy with column sums
+// block: 64 rows; thread -> column quad tid % (K / 4), row lane tid / (K / 4)
+constexpr int CVT_ROWS = 64;
+__global__ void __launch_bounds__(256) f32_to_bf16_colsum_kernel(const float* __restrict__ src, long long rows, int K,
+                                                                 __nv_bfloat16* __restrict__ dst, float* __restrict__ colsum) {
+  __shared__ float4 red[256];
+  const int kq = K >> 2, lanes = 256 / kq, tid = threadIdx.x;
+  const int cq = tid % kq, rl = tid / kq;
+  float4 s4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  const long long r0 = (long long)blockIdx.x * CVT_ROWS, r1 = min(rows, r0 + CVT_ROWS);
+  if (rl < lanes) {
+    for (long long r = r0 + rl; r < r1; r += lanes) {
+      const float4 v = *(const float4*)(src + r * K + 4 * cq);
+      *(uint2*)(dst + r * K + 4 * cq) = make_uint2(pack_bf16(v.x, v.y), pack_bf16(v.z, v.w));
+      s4.x += v.x; s4.y += v.y; s4.z += v.z; s4.w += v.w;
+    }
+  }
+  if (!colsum) return;
+  red[tid] = s4;
+  __syncthreads();
+  if (rl == 0) {
+    for (int l = 1; l < lanes; ++l) { const float4 o = red[l * kq + cq]; s4.x += o.x; s4.y += o.y; s4.z += o.z; s4.w += o.w; }
+    red_add4(colsum + 4 * cq, s4.x, s4.y, s4.z, s4.w);
+  }
+}
+
+int f32_to_bf16_colsum(const float* src, long long rows, int K, __nv_bfloat16* dst, float* colsum, cudaStream_t st) {
+  if (rows <= 0) return QP_OK;
+  QP_REQUIRE(K > 0 && K % 4 == 0 && K <= 1024, "f32_to_bf16_colsum: K=%d", K);
+  f32_to_bf16_colsum_kernel<<<(unsigned)((rows + CVT_ROWS - 1) / CVT_ROWS), 256, 0, st>>>(src, rows, K, dst, colsum);
+  QP_LAUNCH_CHECK();
+  return QP_OK;
+}
+
+// ------------------------------------------------------------------ weight gradients on tcgen05
+// out[128 i x BJ j] (fp32, TMEM) += P[64 rows x 128 i]^T * Q[64 rows x BJ j] per stage, both operands MN-major: a stage row
+// is one time row r, so the gathered past-tap rows of Q are again plain row copies (cp.async, 128 bytes per 64-column
+// block).  warps 0-3: producers, then the epilogue (TMEM lane = output row i, fp32 red.v4 into the zeroed output);
+// warp 4: TMEM allocation + the MMA-issuing thread.  grid = (i tiles, j tiles, row splits).
+constexpr int WG_STAGES = 4;
+constexpr int WG_MAXBLK = 6;   // 64-column blocks per stage: 2 of P (128 output rows) + up to 4 of Q (256 output columns)
+struct WBlk {
+  const __nv_bfloat16* base;   // segment base + first column of the block; nullptr: all-zero block
+  const int* rowmap;
+  long long bstride;
+  int ld, row_off, src_rows;
+};
+
+__device__ __forceinline__ WBlk wblk_resolve(const Seg* segs, int nseg, int col) {
+  WBlk w; w.base = nullptr; w.rowmap = nullptr; w.bstride = 0; w.ld = 0; w.row_off = 0; w.src_rows = 0;
+  int off = 0;
+  for (int s = 0; s < nseg; ++s) {
+    if (col - off < segs[s].K) {
+      if (segs[s].base) {
+        w.base = segs[s].base + (col - off); w.rowmap = segs[s].rowmap; w.bstride = segs[s].bstride; w.ld = segs[s].ld;
+        w.row_off = segs[s].row_off; w.src_rows = segs[s].src_rows;
+      }
+      return w;
+    }
+    off += segs[s].K;
+  }
+  return w;
+}
+
+__global__ void __launch_bounds__(THREADS, 1) tc_wgrad_kernel(WgradArgs a) {
+  extern __shared__ unsigned char smem_raw[];
+  __shared__ WBlk sblk[WG_MAXBLK];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t sbase = (raw + 1023u) & ~1023u;
+  unsigned char* sm = smem_raw + (sbase - raw);
+  const int stage_bytes = (2 + (a.BJ >> 6)) * (int)MN_LBO;
+  const uint32_t bar0 = sbase + WG_STAGES * stage_bytes;
+  uint32_t* tmem_slot = (uint32_t*)(sm + WG_STAGES * stage_bytes + (2 * WG_STAGES + 1) * 8);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int i0 = blockIdx.x * BM, j0 = blockIdx.y * a.BJ;
+  int jp = 0;
+  for (int s = 0; s < a.nq; ++s) jp += a.q[s].K;
+  const int ncols = min(a.BJ, jp - j0);            // multiple of 64
+  const int nblk = 2 + (ncols >> 6);
+  const int row_begin = blockIdx.z * a.chunk, row_end = min(a.n_rows, row_begin + a.chunk);
+  const int steps_b = (row_end - row_begin + BK - 1) / BK;
+  const int nk = a.B * steps_b;
+
+  if (tid == 0) {
+    for (int i = 0; i < WG_STAGES; ++i) { mbar_init(bar0 + 8 * i, PRODUCERS); mbar_init(bar0 + 8 * (WG_STAGES + i), 1); }
+    mbar_init(bar0 + 8 * 2 * WG_STAGES, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+  }
+  if (tid < nblk) sblk[tid] = tid < 2 ? wblk_resolve(a.p, a.np, i0 + 64 * tid) : wblk_resolve(a.q, a.nq, j0 + 64 * (tid - 2));
+  if (warp == 4) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(tmem_slot)), "r"(TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp < 4) {
+    // ================================================================== producer
+    // thread -> 16-byte piece tid & 7 (8 columns) of stage rows (tid >> 3) + 16 g of every block
+    const int c = tid & 7, kr = tid >> 3;
+    const __nv_bfloat16* dummy = a.q[0].base;
+    for (int kc = 0; kc < nk; ++kc) {
+      const int b = kc / steps_b, r0 = row_begin + (kc - b * steps_b) * BK;
+      const int stage = kc % WG_STAGES, it = kc / WG_STAGES;
+      if (it > 0) mbar_wait(bar0 + 8 * (WG_STAGES + stage), (uint32_t)(it - 1) & 1u);
+      const uint32_t st0 = sbase + stage * stage_bytes;
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        const int k = kr + 16 * g, r = r0 + k;
+        const uint32_t dst = st0 + mn_piece(k, c);
+        const bool rin = r < row_end;
+        for (int q = 0; q < nblk; ++q) {
+          const WBlk w = sblk[q];
+          int src = -1;
+          if (rin && w.base) src = w.rowmap ? w.rowmap[(long long)b * a.n_rows + r] : r + w.row_off;
+          const bool ok = src >= 0 && src < w.src_rows;
+          const __nv_bfloat16* gp = ok ? w.base + (long long)b * w.bstride + (long long)src * w.ld + c * 8 : dummy;
+          cp_async16z(dst + q * MN_LBO, gp, ok ? 16u : 0u);
+        }
+      }
+      cp_async_commit();
+      if (kc >= LAG) {
+        cp_async_wait<LAG>();
+        fence_proxy_async();
+        mbar_arrive(bar0 + 8 * ((kc - LAG) % WG_STAGES));
+      }
+    }
+    cp_async_wait<0>();
+    fence_proxy_async();
+    for (int j = max(0, nk - LAG); j < nk; ++j) mbar_arrive(bar0 + 8 * (j % WG_STAGES));
+
+    // ================================================================== epilogue
+    if (nk > 0) {
+      mbar_wait(bar0 + 8 * 2 * WG_STAGES, 0);
+      tc_fence_after();
+      const int i = i0 + tid;
+      const bool iv = i < a.I;
+      const uint32_t trow = tmem + ((uint32_t)(warp * 32) << 16);
+      for (int g = 0; g < ncols; g += 32) {
+        uint32_t v[32];
+        tmem_ld32(trow + g, v);
+        const int j = j0 + g;
+        if (iv) {
+          float* o = a.out + (long long)i * a.ldo + j;
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            if (j + 4 * q + 3 < a.J) {
+              red_add4(o + 4 * q, __uint_as_float(v[4 * q]), __uint_as_float(v[4 * q + 1]), __uint_as_float(v[4 * q + 2]),
+                       __uint_as_float(v[4 * q + 3]));
+            } else {
+#pragma unroll
+              for (int e = 0; e < 4; ++e)
+                if (j + 4 * q + e < a.J) atomicAdd(o + 4 * q + e, __uint_as_float(v[4 * q + e]));
+            }
+          }
+          if (a.ones_out && a.ones_col >= j && a.ones_col < j + 32) {
+#pragma unroll
+            for (int e = 0; e < 32; ++e)
+              if (j + e == a.ones_col) atomicAdd(a.ones_out + i, __uint_as_float(v[e]));
+          }
+        }
+      }
+    }
+  } else {
+    // ================================================================== MMA issuer (one thread)
+    if (lane == 0) {
+      const uint32_t idesc = umma_idesc(BM, ncols, 1, 1);
+      for (int kc = 0; kc < nk; ++kc) {
+        const int stage = kc % WG_STAGES, it = kc / WG_STAGES;
+        mbar_wait(bar0 + 8 * stage, (uint32_t)it & 1u);
+        tc_fence_after();
+        const uint32_t st0 = sbase + stage * stage_bytes;
+        const uint64_t ad = umma_desc_mn(st0, a.mn_lbo, a.mn_sbo);
+        const uint64_t bd = umma_desc_mn(st0 + 2 * MN_LBO, a.mn_lbo, a.mn_sbo);
+#pragma unroll
+        for (int k = 0; k < BK / 16; ++k)          // K = 16 per instruction = two 8-row groups of the MN-major blocks
+          umma(tmem, ad + ((2 * MN_SBO) >> 4) * k, bd + ((2 * MN_SBO) >> 4) * k, idesc, (uint32_t)(kc | k));
+        umma_commit(bar0 + 8 * (WG_STAGES + stage));
+      }
+      if (nk > 0) umma_commit(bar0 + 8 * 2 * WG_STAGES);
+    }
+    __syncwarp();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 4) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem), "r"(TMEM_COLS) : "memory");
+}
+
+int wgrad(const WgradArgs& a0, cudaStream_t st) {
+  WgradArgs a = a0;
+  if (a.n_rows <= 0 || a.B <= 0 || a.I <= 0 || a.J <= 0) return QP_OK;
+  int ip = 0, jp = 0;
+  for (int s = 0; s < a.np; ++s) { QP_REQUIRE(a.p[s].K > 0 && a.p[s].K % 64 == 0, "tc wgrad: P segment width %d", a.p[s].K); ip += a.p[s].K; }
+  for (int s = 0; s < a.nq; ++s) { QP_REQUIRE(a.q[s].K > 0 && a.q[s].K % 64 == 0 && a.q[s].base, "tc wgrad: Q segment width %d", a.q[s].K); jp += a.q[s].K; }
+  QP_REQUIRE(a.I <= ip && a.J <= jp && a.ldo % 4 == 0 && (((size_t)a.out) & 15) == 0, "tc wgrad: bad output shape I=%d J=%d ldo=%d", a.I, a.J, a.ldo);
+  mn_strides(&a.mn_lbo, &a.mn_sbo);
+  const int jblocks = jp / 64, ntj = (jblocks + 3) / 4;
+  a.BJ = 64 * ((jblocks + ntj - 1) / ntj);
+  const int tiles = ((a.I + BM - 1) / BM) * ntj;
+  // row splits: about two CTAs per SM in flight over the launch, at least 512 rows each
+  static int waves = -1;
+  if (waves < 0) { const char* e = getenv("QPNET_WGRAD_WAVES"); waves = e ? atoi(e) : 2; if (waves < 1) waves = 1; }
+  int nsplit = std::max(1, std::min((148 * waves) / std::max(tiles, 1), a.n_rows / 512));
+  a.chunk = ((a.n_rows + nsplit - 1) / nsplit + BK - 1) / BK * BK;
+  nsplit = (a.n_rows + a.chunk - 1) / a.chunk;
+  const size_t smem = (size_t)WG_STAGES * (2 + a.BJ / 64) * MN_LBO + (2 * WG_STAGES + 1) * 8 + 16 + 1024;
+  static bool configured = false;
+  if (!configured) {
+    QP_CUDA(cudaFuncSetAttribute(tc_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));   // + static sblk
+    configured = true;
+  }
+  dim3 grid((a.I + BM - 1) / BM, ntj, nsplit);
+  tc_wgrad_kernel<<<grid, THREADS, smem, st>>>(a);
   QP_LAUNCH_CHECK();
   return QP_OK;
 }

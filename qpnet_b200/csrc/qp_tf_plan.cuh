@@ -40,11 +40,17 @@ struct TfPlan {
   __nv_bfloat16* Wrs_bf;        // (L, C+S, C)
   __nv_bfloat16* W1_bf;         // (S, S)
   __nv_bfloat16* W2_bf;         // (Q, S)
-  __nv_bfloat16* Xbf[2];        // ping-pong block inputs (B, L0, C)
-  __nv_bfloat16* Zbf;           // (B, nmax, C)
+  __nv_bfloat16* Xbf[2 * QP_MAX_LAYERS + 1];  // block inputs (B, Lin[l], C): one per block with QP_F_SAVE, else ping-pong
+  __nv_bfloat16* Zbf[2 * QP_MAX_LAYERS];      // gated outputs (B, n_l, C): one per block with QP_F_SAVE, else shared
   __nv_bfloat16* Hup_bf;        // (B, L0, 64)
   __nv_bfloat16* skip_bf;       // (B, bl, S) relu(sum of skips)
   __nv_bfloat16* H1_bf;         // (B, bl, S) relu(head-1)
+  int ones_col;                 // column of Hup_bf holding 1.0 (bias gradient of the gate GEMM), -1: none
+  // bf16 backward operands (QP_F_BF16 | QP_F_SAVE)
+  __nv_bfloat16* dgate_bf;      // (B, nmax, 2C)
+  __nv_bfloat16* dX_bf;         // (B, L0, C)
+  __nv_bfloat16* dskip_bf;      // (B, bl, S)
+  float* dbskip;                // (S) column sum of dskip
 };
 
 // Fills `p`; returns total bytes.  `base` may be NULL (sizing only).
@@ -117,14 +123,30 @@ inline size_t make_tf_plan(const QpArch* a, int B, int T, int F, int bl, int M, 
     p->dup = ar.take<float>(pd.U + 1);
   }
   p->Kgp = 2 * C + 64;
+  p->ones_col = -1;
   if (flags & QP_F_BF16) {
     p->Wg_bf = ar.take<__nv_bfloat16>((size_t)pd.L * 2 * C * p->Kgp);
     p->Wrs_bf = ar.take<__nv_bfloat16>((size_t)pd.L * (C + S) * C);
     p->W1_bf = ar.take<__nv_bfloat16>((size_t)S * S);
     p->W2_bf = ar.take<__nv_bfloat16>((size_t)Q * S);
-    p->Xbf[0] = ar.take<__nv_bfloat16>((size_t)B * p->L0 * C);
-    p->Xbf[1] = ar.take<__nv_bfloat16>((size_t)B * p->L0 * C);
-    p->Zbf = ar.take<__nv_bfloat16>((size_t)B * p->nmax * C);
+    if (save) {
+      for (int l = 0; l < pd.L; ++l) {
+        p->Xbf[l] = ar.take<__nv_bfloat16>((size_t)B * p->Lin[l] * C);
+        p->Zbf[l] = ar.take<__nv_bfloat16>((size_t)B * (p->Lin[l] - p->shift[l]) * C);
+      }
+      p->Xbf[pd.L] = p->Xbf[0];   // the (dead) residual output of the last block
+      p->dgate_bf = ar.take<__nv_bfloat16>((size_t)B * p->nmax * 2 * C);
+      p->dX_bf = ar.take<__nv_bfloat16>((size_t)B * p->L0 * C);
+      p->dskip_bf = ar.take<__nv_bfloat16>((size_t)B * bl * S);
+      p->dbskip = ar.take<float>(S);
+    } else {
+      __nv_bfloat16* xp0 = ar.take<__nv_bfloat16>((size_t)B * p->L0 * C);
+      __nv_bfloat16* xp1 = ar.take<__nv_bfloat16>((size_t)B * p->L0 * C);
+      __nv_bfloat16* zs = ar.take<__nv_bfloat16>((size_t)B * p->nmax * C);
+      for (int l = 0; l <= pd.L; ++l) p->Xbf[l] = (l & 1) ? xp1 : xp0;
+      for (int l = 0; l < pd.L; ++l) p->Zbf[l] = zs;
+    }
+    p->ones_col = pd.Ap < 64 ? pd.Ap : -1;
     p->Hup_bf = ar.take<__nv_bfloat16>((size_t)B * p->L0 * 64);
     p->skip_bf = ar.take<__nv_bfloat16>((size_t)B * bl * S);
     p->H1_bf = ar.take<__nv_bfloat16>((size_t)B * bl * S);
