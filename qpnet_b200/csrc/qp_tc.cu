@@ -24,9 +24,8 @@ namespace tc {
 constexpr int BM = 128;      // UMMA M: time rows per tile
 constexpr int BK = 64;       // bf16 elements per stage row = one 128-byte swizzle row
 constexpr int STAGES = 4;
-constexpr int LAG = 2;       // cp.async groups in flight per producer thread
-constexpr int PRODUCERS = 128;
-constexpr int THREADS = 160;
+constexpr int PRODUCERS = 256;   // warps 0-7: producers, then the epilogue; warp 8: TMEM allocation + MMA issue
+constexpr int THREADS = 288;
 constexpr int TMEM_COLS = 256;
 constexpr long long WAIT_TIMEOUT_CYCLES = 4000000000LL;   // ~2 s: a lost barrier traps instead of hanging the GPU
 
@@ -37,6 +36,11 @@ __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
 // src_bytes = 0: the 16 destination bytes are zero-filled (rows outside a segment's source range)
 __device__ __forceinline__ void cp_async16z(uint32_t dst, const void* src, uint32_t src_bytes) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+// the mbarrier receives one (pre-counted) arrival once every cp.async this thread has issued so far has landed: the
+// producer never blocks on its own loads, only on a free slot
+__device__ __forceinline__ void cp_async_arrive_noinc(uint32_t bar) {
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];\n" ::"r"(bar) : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
 template <int N>
@@ -139,7 +143,7 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(Args a) {
     mbar_init(bar0 + 8 * 2 * STAGES, 1);
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
   }
-  if (warp == 4) {
+  if (warp == PRODUCERS / 32) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(tmem_slot)), "r"(TMEM_COLS) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
   }
@@ -148,68 +152,64 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(Args a) {
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
 
-  if (warp < 4) {
+  if (warp < PRODUCERS / 32) {
     // ================================================================== producer
-    const int rr = min(r0 + tid, a.n_rows - 1);
-    const uint32_t row_off = (uint32_t)((tid >> 3) * 1024 + (tid & 7) * 128), sw = (uint32_t)(tid & 7);
-    const int w0 = min(n0 + tid, a.N - 1), w1 = min(n0 + 128 + tid, a.N - 1);
-    // a thread only copies the weight rows that exist in this tile (BN may be 32..256 in steps of 32)
-    const bool ldb0 = tid < a.BN, ldb1 = 128 + tid < a.BN;
-    // MN-major weights (w_mn): thread -> 16-byte piece tid & 7 of K rows (tid >> 3) + 16 g, every 64-column block
-    const int wc = tid & 7, wkr = tid >> 3, wblk = ncols >> 6;
+    // thread -> 16-byte piece c of tile rows rg + 32 j: eight threads copy one 128-byte row (one cache line per
+    // quarter warp), and since 32 j is a multiple of 8 every row of a thread has the same swizzle phase: one smem
+    // offset + j * 4096 serves the A rows, the K-major weight rows and the K rows of the MN-major weight blocks alike.
+    const int c = tid & 7, rg = tid >> 3;
+    const uint32_t off0 = (uint32_t)((rg >> 3) * 1024 + (rg & 7) * 128 + ((c ^ (rg & 7)) << 4));
+    const int wblk = ncols >> 6;                 // MN-major weights: 64-column blocks in this tile
     int kc = 0, koff = 0;
     for (int s = 0; s < a.nseg; ++s) {
       const Seg sg = a.seg[s];
-      int src = sg.rowmap ? sg.rowmap[(long long)b * a.n_rows + rr] : rr + sg.row_off;
-      const uint32_t abytes = (sg.base != nullptr && src >= 0 && src < sg.src_rows) ? 16u : 0u;   // else the row reads zero
-      src = max(0, min(src, sg.src_rows - 1));
-      const __nv_bfloat16* arow = abytes ? sg.base + (long long)b * sg.bstride + (long long)src * sg.ld : a.W;
-      const __nv_bfloat16* wrow0 = a.W + (long long)w0 * a.ldw + koff;
-      const __nv_bfloat16* wrow1 = a.W + (long long)w1 * a.ldw + koff;
+      const __nv_bfloat16* ap[4];
+      uint32_t abytes[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int rr = min(r0 + rg + 32 * j, a.n_rows - 1);
+        const int src = sg.rowmap ? sg.rowmap[(long long)b * a.n_rows + rr] : rr + sg.row_off;
+        const bool ok = sg.base != nullptr && src >= 0 && src < sg.src_rows;          // else the row reads zero
+        abytes[j] = ok ? 16u : 0u;
+        ap[j] = ok ? sg.base + (long long)b * sg.bstride + (long long)src * sg.ld + c * 8 : a.W;
+      }
+      // K-major weights: rows n0 + rg + 32 j (j < ncols / 32);  MN-major: K rows koff + k0 + rg + 32 g, blocks q
+      const __nv_bfloat16* wp = a.w_mn ? a.W + (long long)(koff + rg) * a.ldw + n0 + c * 8
+                                       : a.W + (long long)(n0 + rg) * a.ldw + koff + c * 8;
+      const long long wstep = 32LL * a.ldw;
       for (int k0 = 0; k0 < sg.K; k0 += BK, ++kc) {
         const int stage = kc % STAGES, it = kc / STAGES;
         if (it > 0) mbar_wait(bar0 + 8 * (STAGES + stage), (uint32_t)(it - 1) & 1u);
-        const uint32_t sA = sbase + stage * stage_bytes + row_off;
+        const uint32_t sA = sbase + stage * stage_bytes + off0;
         const uint32_t sB = sA + BM * 128;
 #pragma unroll
-        for (int c = 0; c < 8; ++c) cp_async16z(sA + ((c ^ sw) << 4), abytes ? arow + k0 + c * 8 : arow, abytes);
+        for (int j = 0; j < 4; ++j) cp_async16z(sA + j * 4096, abytes[j] ? ap[j] + k0 : ap[j], abytes[j]);
         if (a.w_mn) {
-          const uint32_t sBm = sbase + stage * stage_bytes + BM * 128;
+          const __nv_bfloat16* wk = wp + (long long)k0 * a.ldw;
 #pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            const int k = wkr + 16 * g;
-            const __nv_bfloat16* wr = a.W + (long long)(koff + k0 + k) * a.ldw + n0 + wc * 8;
-            const uint32_t dst = sBm + mn_piece(k, wc);
-            for (int q = 0; q < wblk; ++q) cp_async16(dst + q * MN_LBO, wr + q * 64);
-          }
-        } else if (ldb0) {
+          for (int q = 0; q < 4; ++q)
+            if (q < wblk) {
+              cp_async16(sB + q * MN_LBO, wk + q * 64);
+              cp_async16(sB + q * MN_LBO + 4096, wk + wstep + q * 64);
+            }
+        } else {
 #pragma unroll
-          for (int c = 0; c < 8; ++c) cp_async16(sB + ((c ^ sw) << 4), wrow0 + k0 + c * 8);
+          for (int j = 0; j < 8; ++j)
+            if (rg + 32 * j < ncols) cp_async16(sB + j * 4096, wp + j * wstep + k0);
         }
-        if (!a.w_mn && ldb1) {
-#pragma unroll
-          for (int c = 0; c < 8; ++c) cp_async16(sB + 16 * 1024 + ((c ^ sw) << 4), wrow1 + k0 + c * 8);
-        }
-        cp_async_commit();
-        if (kc >= LAG) {
-          cp_async_wait<LAG>();
-          fence_proxy_async();
-          mbar_arrive(bar0 + 8 * ((kc - LAG) % STAGES));
-        }
+        cp_async_arrive_noinc(bar0 + 8 * stage);
       }
       koff += sg.K;
     }
-    cp_async_wait<0>();
-    fence_proxy_async();
-    for (int j = max(0, nk - LAG); j < nk; ++j) mbar_arrive(bar0 + 8 * (j % STAGES));
 
     // ================================================================== epilogue
     mbar_wait(bar0 + 8 * 2 * STAGES, 0);
     tc_fence_after();
-    const int r = r0 + tid;
+    // a warp reads the TMEM lanes 32 (warp % 4) ..: warps w and w + 4 share their rows and take alternate column groups
+    const int r = r0 + 32 * (warp & 3) + lane;
     const bool rv = r < a.n_rows;
-    const uint32_t trow = tmem + ((uint32_t)(warp * 32) << 16);
-    for (int g = 0; g < ncols; g += 32) {
+    const uint32_t trow = tmem + ((uint32_t)((warp & 3) * 32) << 16);
+    for (int g = 32 * (warp >> 2); g < ncols; g += 64) {
       uint32_t v[32];
       tmem_ld32(trow + g, v);
       const int n = n0 + g;
@@ -359,6 +359,7 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(Args a) {
       for (int kc = 0; kc < nk; ++kc) {
         const int stage = kc % STAGES, it = kc / STAGES;
         mbar_wait(bar0 + 8 * stage, (uint32_t)it & 1u);
+        fence_proxy_async();     // the producers' cp.async writes (generic proxy) -> tcgen05 operand reads (async proxy)
         tc_fence_after();
         const uint64_t ad = umma_desc(sbase + stage * stage_bytes);
         const uint32_t sb = sbase + stage * stage_bytes + BM * 128;
@@ -374,7 +375,7 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(Args a) {
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 4) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem), "r"(TMEM_COLS) : "memory");
+  if (warp == PRODUCERS / 32) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem), "r"(TMEM_COLS) : "memory");
 }
 
 // QPNET_MN_SWAP=1 exchanges the two MN-major descriptor strides (bring-up aid; the default is the cute convention)
@@ -552,7 +553,7 @@ __global__ void __launch_bounds__(THREADS, 1) tc_wgrad_kernel(WgradArgs a) {
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
   }
   if (tid < nblk) sblk[tid] = tid < 2 ? wblk_resolve(a.p, a.np, i0 + 64 * tid) : wblk_resolve(a.q, a.nq, j0 + 64 * (tid - 2));
-  if (warp == 4) {
+  if (warp == PRODUCERS / 32) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(tmem_slot)), "r"(TMEM_COLS) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
   }
@@ -561,49 +562,47 @@ __global__ void __launch_bounds__(THREADS, 1) tc_wgrad_kernel(WgradArgs a) {
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
 
-  if (warp < 4) {
+  if (warp < PRODUCERS / 32) {
     // ================================================================== producer
-    // thread -> 16-byte piece tid & 7 (8 columns) of stage rows (tid >> 3) + 16 g of every block
-    const int c = tid & 7, kr = tid >> 3;
+    // thread -> 16-byte piece c (8 columns) of stage rows rg and rg + 32 of every 64-column block; the block table
+    // lives in registers (fully unrolled), one smem offset + g * 4096 + q * 8192 addresses every copy
+    const int c = tid & 7, rg = tid >> 3;
+    const uint32_t off0 = mn_piece(rg, c);
+    WBlk w[WG_MAXBLK];
+#pragma unroll
+    for (int q = 0; q < WG_MAXBLK; ++q) w[q] = sblk[q < nblk ? q : 0];
     const __nv_bfloat16* dummy = a.q[0].base;
     for (int kc = 0; kc < nk; ++kc) {
       const int b = kc / steps_b, r0 = row_begin + (kc - b * steps_b) * BK;
       const int stage = kc % WG_STAGES, it = kc / WG_STAGES;
       if (it > 0) mbar_wait(bar0 + 8 * (WG_STAGES + stage), (uint32_t)(it - 1) & 1u);
-      const uint32_t st0 = sbase + stage * stage_bytes;
+      const uint32_t st0 = sbase + stage * stage_bytes + off0;
 #pragma unroll
-      for (int g = 0; g < 4; ++g) {
-        const int k = kr + 16 * g, r = r0 + k;
-        const uint32_t dst = st0 + mn_piece(k, c);
+      for (int g = 0; g < 2; ++g) {
+        const int r = r0 + rg + 32 * g;
         const bool rin = r < row_end;
-        for (int q = 0; q < nblk; ++q) {
-          const WBlk w = sblk[q];
-          int src = -1;
-          if (rin && w.base) src = w.rowmap ? w.rowmap[(long long)b * a.n_rows + r] : r + w.row_off;
-          const bool ok = src >= 0 && src < w.src_rows;
-          const __nv_bfloat16* gp = ok ? w.base + (long long)b * w.bstride + (long long)src * w.ld + c * 8 : dummy;
-          cp_async16z(dst + q * MN_LBO, gp, ok ? 16u : 0u);
+#pragma unroll
+        for (int q = 0; q < WG_MAXBLK; ++q) {
+          if (q < nblk) {
+            int src = -1;
+            if (rin && w[q].base) src = w[q].rowmap ? w[q].rowmap[(long long)b * a.n_rows + r] : r + w[q].row_off;
+            const bool ok = (unsigned)src < (unsigned)w[q].src_rows;
+            const __nv_bfloat16* gp = ok ? w[q].base + (long long)b * w[q].bstride + (long long)src * w[q].ld + c * 8 : dummy;
+            cp_async16z(st0 + g * 4096 + q * MN_LBO, gp, ok ? 16u : 0u);
+          }
         }
       }
-      cp_async_commit();
-      if (kc >= LAG) {
-        cp_async_wait<LAG>();
-        fence_proxy_async();
-        mbar_arrive(bar0 + 8 * ((kc - LAG) % WG_STAGES));
-      }
+      cp_async_arrive_noinc(bar0 + 8 * stage);
     }
-    cp_async_wait<0>();
-    fence_proxy_async();
-    for (int j = max(0, nk - LAG); j < nk; ++j) mbar_arrive(bar0 + 8 * (j % WG_STAGES));
 
     // ================================================================== epilogue
     if (nk > 0) {
       mbar_wait(bar0 + 8 * 2 * WG_STAGES, 0);
       tc_fence_after();
-      const int i = i0 + tid;
+      const int i = i0 + 32 * (warp & 3) + lane;     // warps w and w + 4 share their TMEM lanes, alternate column groups
       const bool iv = i < a.I;
-      const uint32_t trow = tmem + ((uint32_t)(warp * 32) << 16);
-      for (int g = 0; g < ncols; g += 32) {
+      const uint32_t trow = tmem + ((uint32_t)((warp & 3) * 32) << 16);
+      for (int g = 32 * (warp >> 2); g < ncols; g += 64) {
         uint32_t v[32];
         tmem_ld32(trow + g, v);
         const int j = j0 + g;
@@ -635,6 +634,7 @@ __global__ void __launch_bounds__(THREADS, 1) tc_wgrad_kernel(WgradArgs a) {
       for (int kc = 0; kc < nk; ++kc) {
         const int stage = kc % WG_STAGES, it = kc / WG_STAGES;
         mbar_wait(bar0 + 8 * stage, (uint32_t)it & 1u);
+        fence_proxy_async();
         tc_fence_after();
         const uint32_t st0 = sbase + stage * stage_bytes;
         const uint64_t ad = umma_desc_mn(st0, a.mn_lbo, a.mn_sbo);
@@ -650,7 +650,7 @@ __global__ void __launch_bounds__(THREADS, 1) tc_wgrad_kernel(WgradArgs a) {
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 4) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem), "r"(TMEM_COLS) : "memory");
+  if (warp == PRODUCERS / 32) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem), "r"(TMEM_COLS) : "memory");
 }
 
 int wgrad(const WgradArgs& a0, cudaStream_t st) {
