@@ -123,6 +123,66 @@ __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
   return (uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(lo)) | ((uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(hi)) << 16);
 }
 
+// ---- coalesced epilogue I/O ------------------------------------------------------------------------------------
+// In the epilogue a thread owns one output row (its TMEM lane).  Storing row-per-thread makes every 16-byte store of
+// a warp hit a different 128-byte line; instead the warp's 32 x NB-byte tile goes through a warp-private shared buffer
+// (pitch NB + 16: conflict-free both ways) and is moved with the lanes laid along the rows: NB / 16 lanes per row, so
+// an instruction touches 32 * 16 / NB rows with full sectors.  Rows [lo, hi) of the warp's 32 exist in memory.
+constexpr int EPI_BUF = 32 * (128 + 16);   // bytes per warp
+template <int NB>
+__device__ __forceinline__ void warp_store_rows(unsigned char* buf, const uint4 (&v)[NB / 16], unsigned char* g0,
+                                                long long pitch, int lo, int hi) {
+  const int lane = threadIdx.x & 31;
+  constexpr int P = NB / 16;
+  __syncwarp();
+#pragma unroll
+  for (int i = 0; i < P; ++i) *(uint4*)(buf + lane * (NB + 16) + 16 * i) = v[i];
+  __syncwarp();
+#pragma unroll
+  for (int j = 0; j < P; ++j) {
+    const int e = j * 32 + lane, row = e / P, piece = e % P;
+    if (row >= lo && row < hi) *(uint4*)(g0 + row * pitch + 16 * piece) = *(const uint4*)(buf + row * (NB + 16) + 16 * piece);
+  }
+}
+template <int NB>
+__device__ __forceinline__ void warp_load_rows(unsigned char* buf, uint4 (&v)[NB / 16], const unsigned char* g0,
+                                               long long pitch, int lo, int hi) {
+  const int lane = threadIdx.x & 31;
+  constexpr int P = NB / 16;
+  __syncwarp();
+#pragma unroll
+  for (int j = 0; j < P; ++j) {
+    const int e = j * 32 + lane, row = e / P, piece = e % P;
+    uint4 t = make_uint4(0u, 0u, 0u, 0u);
+    if (row >= lo && row < hi) t = *(const uint4*)(g0 + row * pitch + 16 * piece);
+    *(uint4*)(buf + row * (NB + 16) + 16 * piece) = t;
+  }
+  __syncwarp();
+#pragma unroll
+  for (int i = 0; i < P; ++i) v[i] = *(const uint4*)(buf + lane * (NB + 16) + 16 * i);
+}
+// fp32 red.add of the warp's 32 x 128-byte tile into rows g0 + rowoff(row) (rowoff < 0: skip), lanes laid along the rows
+__device__ __forceinline__ void warp_red_rows(unsigned char* buf, const uint4 (&v)[8], float* g0, long long my_rowoff,
+                                              int npieces = 8) {
+  const int lane = threadIdx.x & 31;
+  __syncwarp();
+#pragma unroll
+  for (int i = 0; i < 8; ++i) *(uint4*)(buf + lane * 144 + 16 * i) = v[i];
+  __syncwarp();
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int row = j * 4 + (lane >> 3), piece = lane & 7;
+    const long long off = __shfl_sync(0xffffffffu, my_rowoff, row);
+    if (off >= 0 && piece < npieces) {
+      const float4 t = *(const float4*)(buf + row * 144 + 16 * piece);
+      red_add4(g0 + off + 4 * piece, t.x, t.y, t.z, t.w);
+    }
+  }
+}
+__device__ __forceinline__ uint4 f4_as_u4(float x, float y, float z, float w) {
+  return make_uint4(__float_as_uint(x), __float_as_uint(y), __float_as_uint(z), __float_as_uint(w));
+}
+
 template <int EPI>
 __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(Args a) {
   extern __shared__ unsigned char smem_raw[];
@@ -205,9 +265,12 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(Args a) {
     // ================================================================== epilogue
     mbar_wait(bar0 + 8 * 2 * STAGES, 0);
     tc_fence_after();
-    // a warp reads the TMEM lanes 32 (warp % 4) ..: warps w and w + 4 share their rows and take alternate column groups
-    const int r = r0 + 32 * (warp & 3) + lane;
-    const bool rv = r < a.n_rows;
+    // a warp reads the TMEM lanes 32 (warp % 4) ..: warps w and w + 4 share their rows and take alternate column groups.
+    // Every load has landed and every MMA has retired: the stage ring is free and holds the warps' transpose buffers.
+    unsigned char* buf = sm + warp * EPI_BUF;
+    const int rw = r0 + 32 * (warp & 3);              // first row of this warp
+    const int hi = min(32, a.n_rows - rw);            // rows [0, hi) of the warp exist
+    const long long row0 = (long long)b * a.n_rows + rw;
     const uint32_t trow = tmem + ((uint32_t)((warp & 3) * 32) << 16);
     for (int g = 32 * (warp >> 2); g < ncols; g += 64) {
       uint32_t v[32];
@@ -224,130 +287,148 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(Args a) {
           v[2 * j] = __float_as_uint(sg_);
           v[2 * j + 1] = __float_as_uint(th_);
         }
-        if (rv) {
-          const int halfN = a.N >> 1, c0 = n >> 1;
-          uint4* zb = (uint4*)(a.z_bf + ((long long)b * a.n_rows + r) * halfN + c0);
-          zb[0] = make_uint4(pack_bf16(z[0], z[1]), pack_bf16(z[2], z[3]), pack_bf16(z[4], z[5]), pack_bf16(z[6], z[7]));
-          zb[1] = make_uint4(pack_bf16(z[8], z[9]), pack_bf16(z[10], z[11]), pack_bf16(z[12], z[13]), pack_bf16(z[14], z[15]));
-          if (a.z_f32) {
-            float4* zf = (float4*)(a.z_f32 + ((long long)b * a.n_rows + r) * halfN + c0);
+        const int halfN = a.N >> 1, c0 = n >> 1;
+        {
+          uint4 o[2] = {make_uint4(pack_bf16(z[0], z[1]), pack_bf16(z[2], z[3]), pack_bf16(z[4], z[5]), pack_bf16(z[6], z[7])),
+                        make_uint4(pack_bf16(z[8], z[9]), pack_bf16(z[10], z[11]), pack_bf16(z[12], z[13]), pack_bf16(z[14], z[15]))};
+          warp_store_rows<32>(buf, o, (unsigned char*)(a.z_bf + row0 * halfN + c0), 2LL * halfN, 0, hi);
+        }
+        if (a.z_f32) {
+          uint4 o[4];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) zf[j] = make_float4(z[4 * j], z[4 * j + 1], z[4 * j + 2], z[4 * j + 3]);
-          }
-          if (a.gsave) {
-            uint4* gs = (uint4*)(a.gsave + ((long long)b * a.n_rows + r) * a.N + n);
+          for (int j = 0; j < 4; ++j) o[j] = f4_as_u4(z[4 * j], z[4 * j + 1], z[4 * j + 2], z[4 * j + 3]);
+          warp_store_rows<64>(buf, o, (unsigned char*)(a.z_f32 + row0 * halfN + c0), 4LL * halfN, 0, hi);
+        }
+        if (a.gsave) {
+          uint4 o[8];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) gs[j] = make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-          }
+          for (int j = 0; j < 8; ++j) o[j] = make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+          warp_store_rows<128>(buf, o, (unsigned char*)(a.gsave + row0 * a.N + n), 4LL * a.N, 0, hi);
         }
       } else if (EPI == EPI_RESSKIP) {
-        if (rv) {
-          if (n < a.C) {
-            // residual projection + x(current row), fp32 stream + bf16 operand copy (qpnet.py:668-669)
-            const float4* xc = (const float4*)(a.xcur + (long long)b * a.xcur_bstride + (long long)(r + a.xcur_off) * a.C + n);
-            float4* xo = (float4*)(a.xnext + ((long long)b * a.n_rows + r) * a.C + n);
-            uint4* xb = (uint4*)(a.xnext_bf + ((long long)b * a.n_rows + r) * a.C + n);
-            float o[32];
+        if (n < a.C) {
+          // residual projection + x(current row), fp32 stream + bf16 operand copy (qpnet.py:668-669)
+          uint4 x[8];
+          warp_load_rows<128>(buf, x, (const unsigned char*)(a.xcur + (long long)b * a.xcur_bstride + (long long)(rw + a.xcur_off) * a.C + n),
+                              4LL * a.C, 0, hi);
+          float o[32];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              float4 x4 = xc[j];
-              o[4 * j] = __uint_as_float(v[4 * j]) + __ldg(a.bias + n + 4 * j) + x4.x;
-              o[4 * j + 1] = __uint_as_float(v[4 * j + 1]) + __ldg(a.bias + n + 4 * j + 1) + x4.y;
-              o[4 * j + 2] = __uint_as_float(v[4 * j + 2]) + __ldg(a.bias + n + 4 * j + 2) + x4.z;
-              o[4 * j + 3] = __uint_as_float(v[4 * j + 3]) + __ldg(a.bias + n + 4 * j + 3) + x4.w;
-              xo[j] = make_float4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
-            }
+          for (int j = 0; j < 8; ++j) {
+            o[4 * j] = __uint_as_float(v[4 * j]) + __ldg(a.bias + n + 4 * j) + __uint_as_float(x[j].x);
+            o[4 * j + 1] = __uint_as_float(v[4 * j + 1]) + __ldg(a.bias + n + 4 * j + 1) + __uint_as_float(x[j].y);
+            o[4 * j + 2] = __uint_as_float(v[4 * j + 2]) + __ldg(a.bias + n + 4 * j + 2) + __uint_as_float(x[j].z);
+            o[4 * j + 3] = __uint_as_float(v[4 * j + 3]) + __ldg(a.bias + n + 4 * j + 3) + __uint_as_float(x[j].w);
+            x[j] = f4_as_u4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
+          }
+          warp_store_rows<128>(buf, x, (unsigned char*)(a.xnext + row0 * a.C + n), 4LL * a.C, 0, hi);
+          uint4 ob[4];
 #pragma unroll
-            for (int j = 0; j < 4; ++j)
-              xb[j] = make_uint4(pack_bf16(o[8 * j], o[8 * j + 1]), pack_bf16(o[8 * j + 2], o[8 * j + 3]),
-                                 pack_bf16(o[8 * j + 4], o[8 * j + 5]), pack_bf16(o[8 * j + 6], o[8 * j + 7]));
-          } else if (r >= a.skip_row0) {
-            // skip projection, accumulated over the blocks for the last bl rows only (qpnet.py:667, 283)
-            float4* sk = (float4*)(a.skip + (long long)b * a.skip_bstride + (long long)(r - a.skip_row0) * a.S + (n - a.C));
+          for (int j = 0; j < 4; ++j)
+            ob[j] = make_uint4(pack_bf16(o[8 * j], o[8 * j + 1]), pack_bf16(o[8 * j + 2], o[8 * j + 3]),
+                               pack_bf16(o[8 * j + 4], o[8 * j + 5]), pack_bf16(o[8 * j + 6], o[8 * j + 7]));
+          warp_store_rows<64>(buf, ob, (unsigned char*)(a.xnext_bf + row0 * a.C + n), 2LL * a.C, 0, hi);
+        } else {
+          // skip projection, accumulated over the blocks for the last bl rows only (qpnet.py:667, 283)
+          const int lo = max(0, a.skip_row0 - rw);
+          if (lo < hi) {
+            unsigned char* sk = (unsigned char*)(a.skip + (long long)b * a.skip_bstride + (long long)(rw - a.skip_row0) * a.S + (n - a.C));
+            uint4 p[8];
+            if (a.skip_accum) warp_load_rows<128>(buf, p, sk, 4LL * a.S, lo, hi);
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
               float4 o = make_float4(__uint_as_float(v[4 * j]) + __ldg(a.bias + n + 4 * j),
                                      __uint_as_float(v[4 * j + 1]) + __ldg(a.bias + n + 4 * j + 1),
                                      __uint_as_float(v[4 * j + 2]) + __ldg(a.bias + n + 4 * j + 2),
                                      __uint_as_float(v[4 * j + 3]) + __ldg(a.bias + n + 4 * j + 3));
-              if (a.skip_accum) { float4 p = sk[j]; o.x += p.x; o.y += p.y; o.z += p.z; o.w += p.w; }
-              sk[j] = o;
+              if (a.skip_accum) { o.x += __uint_as_float(p[j].x); o.y += __uint_as_float(p[j].y); o.z += __uint_as_float(p[j].z); o.w += __uint_as_float(p[j].w); }
+              p[j] = f4_as_u4(o.x, o.y, o.z, o.w);
             }
+            warp_store_rows<128>(buf, p, sk, 4LL * a.S, lo, hi);
           }
         }
       } else if (EPI == EPI_DGATE) {
         // acc = dz[r][c], c = n .. n + 31 -> dgate columns 2c, 2c + 1 through the saved sigmoid / tanh values
-        if (rv) {
-          const long long row = (long long)b * a.n_rows + r;
-          const float4* gp = (const float4*)(a.gin + row * (2 * a.N) + 2 * n);
-          float o[64];
+        const unsigned char* gp = (const unsigned char*)(a.gin + row0 * (2 * a.N) + 2 * n);
+        uint4 g0[8], g1[8];
+        warp_load_rows<128>(buf, g0, gp, 8LL * a.N, 0, hi);          // (sg, th) of channels n .. n + 15
+        warp_load_rows<128>(buf, g1, gp + 128, 8LL * a.N, 0, hi);    // channels n + 16 .. n + 31
+        float o[64];
 #pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            const float4 gv = gp[j];   // (sg, th) of channels n + 2j, n + 2j + 1
-            const float dz0 = __uint_as_float(v[2 * j]), dz1 = __uint_as_float(v[2 * j + 1]);
-            o[4 * j] = dz0 * gv.y * gv.x * (1.f - gv.x);
-            o[4 * j + 1] = dz0 * gv.x * (1.f - gv.y * gv.y);
-            o[4 * j + 2] = dz1 * gv.w * gv.z * (1.f - gv.z);
-            o[4 * j + 3] = dz1 * gv.z * (1.f - gv.w * gv.w);
-          }
-          uint4* ob = (uint4*)(a.dgate_bf + row * (2 * a.N) + 2 * n);
+        for (int j = 0; j < 16; ++j) {
+          const uint4 gv = j < 8 ? g0[j] : g1[j - 8];   // (sg, th) of channels n + 2j, n + 2j + 1
+          const float sg0 = __uint_as_float(gv.x), th0 = __uint_as_float(gv.y), sg1 = __uint_as_float(gv.z), th1 = __uint_as_float(gv.w);
+          const float dz0 = __uint_as_float(v[2 * j]), dz1 = __uint_as_float(v[2 * j + 1]);
+          o[4 * j] = dz0 * th0 * sg0 * (1.f - sg0);
+          o[4 * j + 1] = dz0 * sg0 * (1.f - th0 * th0);
+          o[4 * j + 2] = dz1 * th1 * sg1 * (1.f - sg1);
+          o[4 * j + 3] = dz1 * sg1 * (1.f - th1 * th1);
+        }
 #pragma unroll
-          for (int j = 0; j < 8; ++j)
-            ob[j] = make_uint4(pack_bf16(o[8 * j], o[8 * j + 1]), pack_bf16(o[8 * j + 2], o[8 * j + 3]),
-                               pack_bf16(o[8 * j + 4], o[8 * j + 5]), pack_bf16(o[8 * j + 6], o[8 * j + 7]));
-          if (a.dgate_f32) {
-            float4* of = (float4*)(a.dgate_f32 + row * (2 * a.N) + 2 * n);
+        for (int j = 0; j < 8; ++j)
+          g0[j] = make_uint4(pack_bf16(o[8 * j], o[8 * j + 1]), pack_bf16(o[8 * j + 2], o[8 * j + 3]),
+                             pack_bf16(o[8 * j + 4], o[8 * j + 5]), pack_bf16(o[8 * j + 6], o[8 * j + 7]));
+        warp_store_rows<128>(buf, g0, (unsigned char*)(a.dgate_bf + row0 * (2 * a.N) + 2 * n), 4LL * a.N, 0, hi);
+        if (a.dgate_f32) {
+          unsigned char* of = (unsigned char*)(a.dgate_f32 + row0 * (2 * a.N) + 2 * n);
 #pragma unroll
-            for (int j = 0; j < 16; ++j) of[j] = make_float4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
-          }
+          for (int j = 0; j < 8; ++j) g0[j] = f4_as_u4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
+          warp_store_rows<128>(buf, g0, of, 8LL * a.N, 0, hi);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) g0[j] = f4_as_u4(o[32 + 4 * j], o[32 + 4 * j + 1], o[32 + 4 * j + 2], o[32 + 4 * j + 3]);
+          warp_store_rows<128>(buf, g0, of + 128, 8LL * a.N, 0, hi);
         }
       } else if (EPI == EPI_DX) {
         // acc = (dgate * Wg)[r][k], k = n .. n + 31 inside one of [past C | current C | aux]
-        if (rv) {
+        const int r = rw + lane;
+        const bool rv = r < a.n_rows;
+        if (n < 2 * a.C) {
+          uint4 o[8];
+          long long off = -1;
           if (n < a.C) {
-            const int src = a.dx_rowmap ? a.dx_rowmap[(long long)b * a.n_rows + r] : r + a.dx_past_off;
-            if (src >= 0 && src < a.dx_rows) {
-              float* q = a.dx + (long long)b * a.dx_bstride + (long long)src * a.C + n;
+            const int src = rv ? (a.dx_rowmap ? a.dx_rowmap[(long long)b * a.n_rows + r] : r + a.dx_past_off) : -1;
+            if (src >= 0 && src < a.dx_rows) off = (long long)src * a.C + n;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) o[j] = make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+          } else {
+            const int c = n - a.C;
+            if (rv) off = (long long)(r + a.dx_cur_off) * a.C + c;
+            if (a.resid) {
+              warp_load_rows<128>(buf, o, (const unsigned char*)(a.resid + (long long)b * a.resid_bstride + (long long)rw * a.C + c),
+                                  4LL * a.C, 0, hi);
 #pragma unroll
               for (int j = 0; j < 8; ++j)
-                red_add4(q + 4 * j, __uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]),
-                         __uint_as_float(v[4 * j + 3]));
-            }
-          } else if (n < 2 * a.C) {
-            const int c = n - a.C;
-            float* q = a.dx + (long long)b * a.dx_bstride + (long long)(r + a.dx_cur_off) * a.C + c;
-            const float4* rs = a.resid ? (const float4*)(a.resid + (long long)b * a.resid_bstride + (long long)r * a.C + c) : nullptr;
+                o[j] = f4_as_u4(__uint_as_float(v[4 * j]) + __uint_as_float(o[j].x), __uint_as_float(v[4 * j + 1]) + __uint_as_float(o[j].y),
+                                __uint_as_float(v[4 * j + 2]) + __uint_as_float(o[j].z), __uint_as_float(v[4 * j + 3]) + __uint_as_float(o[j].w));
+            } else {
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              float4 x4 = rs ? rs[j] : make_float4(0.f, 0.f, 0.f, 0.f);
-              red_add4(q + 4 * j, __uint_as_float(v[4 * j]) + x4.x, __uint_as_float(v[4 * j + 1]) + x4.y,
-                       __uint_as_float(v[4 * j + 2]) + x4.z, __uint_as_float(v[4 * j + 3]) + x4.w);
+              for (int j = 0; j < 8; ++j) o[j] = make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
             }
-          } else {
-            const int ka = n - 2 * a.C;
-            float* q = a.dh + (long long)b * a.dh_bstride + (long long)(r + a.dh_off) * a.A;
-#pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (ka + j < a.A) q[ka + j] += __uint_as_float(v[j]);
           }
+          warp_red_rows(buf, o, a.dx + (long long)b * a.dx_bstride, off);
+        } else if (rv) {
+          const int ka = n - 2 * a.C;
+          float* q = a.dh + (long long)b * a.dh_bstride + (long long)(r + a.dh_off) * a.A;
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (ka + j < a.A) q[ka + j] += __uint_as_float(v[j]);
         }
       } else {  // EPI_HEAD: out = acc + bias (fp32, pre-activation) and optionally relu(out) as the next bf16 operand
-        if (rv) {
-          float o[32];
+        float o[32];
 #pragma unroll
-          for (int j = 0; j < 32; ++j) o[j] = __uint_as_float(v[j]) + __ldg(a.bias + n + j);
-          float4* op = (float4*)(a.out + (long long)b * a.out_bstride + (long long)r * a.ldo + n);
+        for (int j = 0; j < 32; ++j) o[j] = __uint_as_float(v[j]) + __ldg(a.bias + n + j);
+        uint4 of[8];
 #pragma unroll
-          for (int j = 0; j < 8; ++j) op[j] = make_float4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
-          if (a.out_relu_bf) {
-            uint4* ob = (uint4*)(a.out_relu_bf + (long long)b * a.out_bstride + (long long)r * a.ldo + n);
+        for (int j = 0; j < 8; ++j) of[j] = f4_as_u4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
+        warp_store_rows<128>(buf, of, (unsigned char*)(a.out + (long long)b * a.out_bstride + (long long)rw * a.ldo + n), 4LL * a.ldo, 0, hi);
+        if (a.out_relu_bf) {
+          uint4 ob[4];
 #pragma unroll
-            for (int j = 0; j < 4; ++j)
-              ob[j] = make_uint4(pack_bf16(fmaxf(o[8 * j], 0.f), fmaxf(o[8 * j + 1], 0.f)),
-                                 pack_bf16(fmaxf(o[8 * j + 2], 0.f), fmaxf(o[8 * j + 3], 0.f)),
-                                 pack_bf16(fmaxf(o[8 * j + 4], 0.f), fmaxf(o[8 * j + 5], 0.f)),
-                                 pack_bf16(fmaxf(o[8 * j + 6], 0.f), fmaxf(o[8 * j + 7], 0.f)));
-          }
+          for (int j = 0; j < 4; ++j)
+            ob[j] = make_uint4(pack_bf16(fmaxf(o[8 * j], 0.f), fmaxf(o[8 * j + 1], 0.f)),
+                               pack_bf16(fmaxf(o[8 * j + 2], 0.f), fmaxf(o[8 * j + 3], 0.f)),
+                               pack_bf16(fmaxf(o[8 * j + 4], 0.f), fmaxf(o[8 * j + 5], 0.f)),
+                               pack_bf16(fmaxf(o[8 * j + 6], 0.f), fmaxf(o[8 * j + 7], 0.f)));
+          warp_store_rows<64>(buf, ob, (unsigned char*)(a.out_relu_bf + (long long)b * a.out_bstride + (long long)rw * a.ldo + n), 2LL * a.ldo, 0, hi);
         }
       }
     }
@@ -601,29 +682,20 @@ __global__ void __launch_bounds__(THREADS, 1) tc_wgrad_kernel(WgradArgs a) {
       tc_fence_after();
       const int i = i0 + 32 * (warp & 3) + lane;     // warps w and w + 4 share their TMEM lanes, alternate column groups
       const bool iv = i < a.I;
+      unsigned char* buf = sm + warp * EPI_BUF;      // the stage ring is free: every load landed, every MMA retired
       const uint32_t trow = tmem + ((uint32_t)((warp & 3) * 32) << 16);
       for (int g = 32 * (warp >> 2); g < ncols; g += 64) {
         uint32_t v[32];
         tmem_ld32(trow + g, v);
         const int j = j0 + g;
-        if (iv) {
-          float* o = a.out + (long long)i * a.ldo + j;
+        uint4 o[8];
 #pragma unroll
-          for (int q = 0; q < 8; ++q) {
-            if (j + 4 * q + 3 < a.J) {
-              red_add4(o + 4 * q, __uint_as_float(v[4 * q]), __uint_as_float(v[4 * q + 1]), __uint_as_float(v[4 * q + 2]),
-                       __uint_as_float(v[4 * q + 3]));
-            } else {
+        for (int q = 0; q < 8; ++q) o[q] = make_uint4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+        warp_red_rows(buf, o, a.out, iv ? (long long)i * a.ldo + j : -1LL, min(8, (a.J - j) >> 2));
+        if (iv && a.ones_out && a.ones_col >= j && a.ones_col < j + 32) {
 #pragma unroll
-              for (int e = 0; e < 4; ++e)
-                if (j + 4 * q + e < a.J) atomicAdd(o + 4 * q + e, __uint_as_float(v[4 * q + e]));
-            }
-          }
-          if (a.ones_out && a.ones_col >= j && a.ones_col < j + 32) {
-#pragma unroll
-            for (int e = 0; e < 32; ++e)
-              if (j + e == a.ones_col) atomicAdd(a.ones_out + i, __uint_as_float(v[e]));
-          }
+          for (int e = 0; e < 32; ++e)
+            if (j + e == a.ones_col) atomicAdd(a.ones_out + i, __uint_as_float(v[e]));
         }
       }
     }
@@ -659,7 +731,7 @@ int wgrad(const WgradArgs& a0, cudaStream_t st) {
   int ip = 0, jp = 0;
   for (int s = 0; s < a.np; ++s) { QP_REQUIRE(a.p[s].K > 0 && a.p[s].K % 64 == 0, "tc wgrad: P segment width %d", a.p[s].K); ip += a.p[s].K; }
   for (int s = 0; s < a.nq; ++s) { QP_REQUIRE(a.q[s].K > 0 && a.q[s].K % 64 == 0 && a.q[s].base, "tc wgrad: Q segment width %d", a.q[s].K); jp += a.q[s].K; }
-  QP_REQUIRE(a.I <= ip && a.J <= jp && a.ldo % 4 == 0 && (((size_t)a.out) & 15) == 0, "tc wgrad: bad output shape I=%d J=%d ldo=%d", a.I, a.J, a.ldo);
+  QP_REQUIRE(a.I <= ip && a.J <= jp && a.ldo % 4 == 0 && a.J % 4 == 0 && (((size_t)a.out) & 15) == 0, "tc wgrad: bad output shape I=%d J=%d ldo=%d", a.I, a.J, a.ldo);
   mn_strides(&a.mn_lbo, &a.mn_sbo);
   const int jblocks = jp / 64, ntj = (jblocks + 3) / 4;
   a.BJ = 64 * ((jblocks + ntj - 1) / ntj);
