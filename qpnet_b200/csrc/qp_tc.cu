@@ -23,7 +23,7 @@ namespace tc {
 
 constexpr int BM = 128;      // UMMA M: time rows per tile
 constexpr int BK = 64;       // bf16 elements per stage row = one 128-byte swizzle row
-constexpr int STAGES = 4;
+constexpr int STAGES = 2;       // two CTAs per SM: one runs its epilogue while the other feeds the tensor cores
 constexpr int PRODUCERS = 256;   // warps 0-7: producers, then the epilogue; warp 8: TMEM allocation + MMA issue
 constexpr int THREADS = 288;
 constexpr int TMEM_COLS = 256;
@@ -184,7 +184,7 @@ __device__ __forceinline__ uint4 f4_as_u4(float x, float y, float z, float w) {
 }
 
 template <int EPI>
-__global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(Args a) {
+__global__ void __launch_bounds__(THREADS, 2) tc_gemm_kernel(Args a) {
   extern __shared__ unsigned char smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t sbase = (raw + 1023u) & ~1023u;              // SWIZZLE_128B atoms need 1024-byte alignment
@@ -584,7 +584,7 @@ int f32_to_bf16_colsum(const float* src, long long rows, int K, __nv_bfloat16* d
 // is one time row r, so the gathered past-tap rows of Q are again plain row copies (cp.async, 128 bytes per 64-column
 // block).  warps 0-3: producers, then the epilogue (TMEM lane = output row i, fp32 red.v4 into the zeroed output);
 // warp 4: TMEM allocation + the MMA-issuing thread.  grid = (i tiles, j tiles, row splits).
-constexpr int WG_STAGES = 4;
+constexpr int WG_STAGES = 2;
 constexpr int WG_MAXBLK = 6;   // 64-column blocks per stage: 2 of P (128 output rows) + up to 4 of Q (256 output columns)
 struct WBlk {
   const __nv_bfloat16* base;   // segment base + first column of the block; nullptr: all-zero block
@@ -609,7 +609,7 @@ __device__ __forceinline__ WBlk wblk_resolve(const Seg* segs, int nseg, int col)
   return w;
 }
 
-__global__ void __launch_bounds__(THREADS, 1) tc_wgrad_kernel(WgradArgs a) {
+__global__ void __launch_bounds__(THREADS, 2) tc_wgrad_kernel(WgradArgs a) {
   extern __shared__ unsigned char smem_raw[];
   __shared__ WBlk sblk[WG_MAXBLK];
   const uint32_t raw = smem_u32(smem_raw);
@@ -653,27 +653,37 @@ __global__ void __launch_bounds__(THREADS, 1) tc_wgrad_kernel(WgradArgs a) {
 #pragma unroll
     for (int q = 0; q < WG_MAXBLK; ++q) w[q] = sblk[q < nblk ? q : 0];
     const __nv_bfloat16* dummy = a.q[0].base;
-    for (int kc = 0; kc < nk; ++kc) {
-      const int b = kc / steps_b, r0 = row_begin + (kc - b * steps_b) * BK;
-      const int stage = kc % WG_STAGES, it = kc / WG_STAGES;
-      if (it > 0) mbar_wait(bar0 + 8 * (WG_STAGES + stage), (uint32_t)(it - 1) & 1u);
-      const uint32_t st0 = sbase + stage * stage_bytes + off0;
+    int kc = 0;
+    for (int b = 0; b < a.B; ++b) {
+      // per batch element: block bases with this thread's column piece folded in; offsets inside one element fit 32 bits
+      const __nv_bfloat16* pb[WG_MAXBLK];
+      const int* rm[WG_MAXBLK];
 #pragma unroll
-      for (int g = 0; g < 2; ++g) {
-        const int r = r0 + rg + 32 * g;
-        const bool rin = r < row_end;
+      for (int q = 0; q < WG_MAXBLK; ++q) {
+        pb[q] = w[q].base ? w[q].base + (long long)b * w[q].bstride + c * 8 : nullptr;
+        rm[q] = w[q].rowmap ? w[q].rowmap + (long long)b * a.n_rows : nullptr;
+      }
+      for (int r0 = row_begin; r0 < row_end; r0 += BK, ++kc) {
+        const int stage = kc % WG_STAGES, it = kc / WG_STAGES;
+        if (it > 0) mbar_wait(bar0 + 8 * (WG_STAGES + stage), (uint32_t)(it - 1) & 1u);
+        const uint32_t st0 = sbase + stage * stage_bytes + off0;
 #pragma unroll
-        for (int q = 0; q < WG_MAXBLK; ++q) {
-          if (q < nblk) {
-            int src = -1;
-            if (rin && w[q].base) src = w[q].rowmap ? w[q].rowmap[(long long)b * a.n_rows + r] : r + w[q].row_off;
-            const bool ok = (unsigned)src < (unsigned)w[q].src_rows;
-            const __nv_bfloat16* gp = ok ? w[q].base + (long long)b * w[q].bstride + (long long)src * w[q].ld + c * 8 : dummy;
-            cp_async16z(st0 + g * 4096 + q * MN_LBO, gp, ok ? 16u : 0u);
+        for (int g = 0; g < 2; ++g) {
+          const int r = r0 + rg + 32 * g;
+          const bool rin = r < row_end;
+#pragma unroll
+          for (int q = 0; q < WG_MAXBLK; ++q) {
+            if (q < nblk) {
+              int src = -1;
+              if (rin && pb[q]) src = rm[q] ? rm[q][r] : r + w[q].row_off;
+              const bool ok = (unsigned)src < (unsigned)w[q].src_rows;
+              const __nv_bfloat16* gp = ok ? pb[q] + (unsigned)(src * w[q].ld) : dummy;
+              cp_async16z(st0 + g * 4096 + q * MN_LBO, gp, ok ? 16u : 0u);
+            }
           }
         }
+        cp_async_arrive_noinc(bar0 + 8 * stage);
       }
-      cp_async_arrive_noinc(bar0 + 8 * stage);
     }
 
     // ================================================================== epilogue
