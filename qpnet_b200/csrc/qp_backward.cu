@@ -244,8 +244,13 @@ int tf_backward_f32(const QpArch* arch, const float* const* tensors, const int64
   QP_CUDA(cudaMemsetAsync(p.dW.E1, 0, sizeof(float) * (size_t)Q * C, st));
   embed_grad_kernel<<<dim3(L0, B), 128, 0, st>>>(x, p.T, L0, C, Q, dXnext, p.dW.E0, p.dW.E1);
   QP_LAUNCH_CHECK();
-  colsum_kernel<<<(C + 31) / 32, 256, 0, st>>>(dXnext, (int64_t)B * L0, C, grads[tm.causal_b()]);
-  QP_LAUNCH_CHECK();
+  if (mask) {
+    QP_CUDA(cudaMemsetAsync(grads[tm.causal_b()], 0, sizeof(float) * C, st));
+    if (int e = tc::f32_to_bf16_colsum(dXnext, (long long)B * L0, C, nullptr, grads[tm.causal_b()], st)) return e;
+  } else {
+    colsum_kernel<<<(C + 31) / 32, 256, 0, st>>>(dXnext, (int64_t)B * L0, C, grads[tm.causal_b()]);
+    QP_LAUNCH_CHECK();
+  }
   QP_CUDA(cudaMemsetAsync(grads[tm.up_b()], 0, sizeof(float), st));
   upsample_grad_kernel<<<pd.U, 64, 0, st>>>(p.dHup, h, B, A, p.F, pd.U, L0, grads[tm.up_w()], grads[tm.up_b()]);
   QP_LAUNCH_CHECK();

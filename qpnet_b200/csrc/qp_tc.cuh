@@ -76,7 +76,7 @@ struct WgradArgs {
 };
 int wgrad(const WgradArgs& a, cudaStream_t st);
 
-// dst = bf16(src) (rows x K, K % 4 == 0, K <= 1024) and colsum[k] += sum_r src[r][k] (colsum zeroed by the caller, may be NULL)
+// dst = bf16(src) (rows x K, K % 4 == 0, K <= 1024; dst may be NULL) and colsum[k] += sum_r src[r][k] (colsum zeroed by the caller, may be NULL)
 int f32_to_bf16_colsum(const float* src, long long rows, int K, __nv_bfloat16* dst, float* colsum, cudaStream_t st);
 
 // dst[r][k] = bf16(k < K ? (relu?) src[r][k] : 0), k < Kp
