@@ -79,7 +79,7 @@ __global__ void upsample_grad_kernel(const float* __restrict__ dHup, const float
 
 // Which contractions of the bf16 training path's backward run on tcgen05 (qp_tc.cu), bit mask, default all:
 // 1 weight gradients, 2 dz -> dgate GEMM, 4 dX GEMM.  QPNET_BWD_TC=0 is the TF32 mma.sync backward (A/B timing, bring-up).
-static int bwd_tc_mask() {
+int bwd_tc_mask() {
   static int m = -1;
   if (m < 0) { const char* e = getenv("QPNET_BWD_TC"); m = e ? atoi(e) & 7 : 7; }
   return m;
@@ -155,6 +155,7 @@ int tf_backward_f32(const QpArch* arch, const float* const* tensors, const int64
       g.seg[s++] = tc::Seg{p.dskip_bf, (long long)bl * S, S, nullptr, -(n - bl), bl, S};
       g.nseg = s;
       g.W = p.Wrs_bf + (size_t)l * (C + S) * C + (dXnext ? 0 : (size_t)C * C); g.ldw = C; g.w_mn = 1;
+      g.Wb = p.WrsMN + (size_t)l * (C + S) * C; g.wb_pitch = C / 64; g.wb_k0 = dXnext ? 0 : C / 64;
       g.B = B; g.n_rows = n; g.N = C; g.BN = C < 256 ? C : 256;
       g.gin = p.G[l]; g.dgate_bf = p.dgate_bf; g.dgate_f32 = (tc_w && tc_dx) ? nullptr : p.dgate;
       if (int e = tc::gemm_dgate(g, st)) return e;
@@ -220,6 +221,7 @@ int tf_backward_f32(const QpArch* arch, const float* const* tensors, const int64
         tc::Args g = {};
         g.seg[0] = tc::Seg{p.dgate_bf, (long long)n * 2 * C, 2 * C, nullptr, 0, n, 2 * C}; g.nseg = 1;
         g.W = p.Wg_bf + (size_t)l * 2 * C * Kgp; g.ldw = Kgp; g.w_mn = 1;
+        g.Wb = p.WgMN + (size_t)l * 2 * C * Kgp; g.wb_pitch = Kgp / 64;
         g.B = B; g.n_rows = n; g.N = Kgp; g.BN = Kgp < 256 ? Kgp : 256; g.C = C; g.A = A;
         g.dx = dX; g.dx_bstride = (long long)Lin * C; g.dx_rowmap = rowmap; g.dx_past_off = 0; g.dx_cur_off = sh; g.dx_rows = Lin;
         g.resid = dXnext; g.resid_bstride = (long long)n * C;

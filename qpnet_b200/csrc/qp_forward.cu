@@ -124,11 +124,19 @@ int tf_forward_bf16(const QpArch* arch, const float* const* tensors, const int64
   const TensorMap tm = tensor_map(arch);
   const int C = pd.C, S = pd.S, Q = pd.Q, A = pd.A, B = p.B, L0 = p.L0, bl = p.bl, Kgp = p.Kgp;
   const bool save = flags & QP_F_SAVE;
+  // the fp32 copy of z only feeds the TF32 weight-gradient kernel; the tcgen05 one reads the bf16 operand copy
+  const bool save_zf = save && !((bwd_tc_mask() & 1) && p.ones_col >= 0);
   QP_CUDA(cudaMemsetAsync(p.status, 0, sizeof(int32_t), st));
   if (int e = upload_tensor_table(arch, tensors, p.tab, st)) return e;
   if (int e = pack_f32(arch, p.tab, p.W, st)) return e;
   if (int e = tc::pack_wg_bf16(p.W.Wg, (long long)pd.L * 2 * C, 2 * C, pd.Kg, Kgp, p.Wg_bf, st)) return e;
   if (int e = tc::f32_to_bf16_pad(p.W.Wrs, (long long)pd.L * (C + S), C, C, p.Wrs_bf, 0, st)) return e;
+  if (int e = tc::block_pack(p.Wg_bf, pd.L, 2 * C, Kgp, 1, p.WgK, st)) return e;
+  if (int e = tc::block_pack(p.Wrs_bf, pd.L, C + S, C, 1, p.WrsK, st)) return e;
+  if (save) {
+    if (int e = tc::block_pack(p.Wg_bf, pd.L, 2 * C, Kgp, 0, p.WgMN, st)) return e;
+    if (int e = tc::block_pack(p.Wrs_bf, pd.L, C + S, C, 0, p.WrsMN, st)) return e;
+  }
   if (int e = tc::f32_to_bf16_pad(tensors[tm.post1_w()], S, S, S, p.W1_bf, 0, st)) return e;
   if (int e = tc::f32_to_bf16_pad(tensors[tm.post2_w()], Q, S, S, p.W2_bf, 0, st)) return e;
   embed_kernel<<<dim3(L0, B), 128, 0, st>>>(x, p.T, L0, C, Q, p.W.E0, p.W.E1, tensors[tm.causal_b()], p.X[0]);
@@ -154,15 +162,17 @@ int tf_forward_bf16(const QpArch* arch, const float* const* tensors, const int64
     g.seg[2] = tc::Seg{p.Hup_bf, (long long)L0 * 64, 64, nullptr, L0 - n, L0, 64};
     g.nseg = 3;
     g.W = p.Wg_bf + (size_t)l * 2 * C * Kgp; g.ldw = Kgp;
+    g.Wb = p.WgK + (size_t)l * 2 * C * Kgp; g.wb_pitch = 2 * C / 64;
     g.bias = p.W.bg + (size_t)2 * C * l;
     g.B = B; g.n_rows = n; g.N = 2 * C; g.n_begin = 0; g.BN = 2 * C < 256 ? 2 * C : 256;
-    g.z_bf = p.Zbf[l]; g.z_f32 = save ? p.Z[l] : nullptr; g.gsave = save ? p.G[l] : nullptr;
+    g.z_bf = p.Zbf[l]; g.z_f32 = save_zf ? p.Z[l] : nullptr; g.gsave = save ? p.G[l] : nullptr;
     if (int e = tc::gemm_gate(g, st)) return e;
 
     tc::Args r = {};
     r.seg[0] = tc::Seg{p.Zbf[l], (long long)n * C, C, nullptr, 0, n, C};
     r.nseg = 1;
     r.W = p.Wrs_bf + (size_t)l * (C + S) * C; r.ldw = C;
+    r.Wb = p.WrsK + (size_t)l * (C + S) * C; r.wb_pitch = (C + S) / 64;
     r.bias = p.W.brs + (size_t)(C + S) * l;
     r.B = B; r.n_rows = n; r.N = C + S;
     r.n_begin = (l == pd.L - 1) ? C : 0;   // the last block's residual projection is dead (caveat C7)

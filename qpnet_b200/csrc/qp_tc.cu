@@ -67,6 +67,14 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     }
   }
 }
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("{\n .reg .b64 st;\n mbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n}\n" ::"r"(bar), "r"(bytes) : "memory");
+}
+// global -> shared bulk copy (bytes % 16 == 0), completes on an mbarrier of this CTA
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n"
+               ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory"); }
 
@@ -203,7 +211,8 @@ __global__ void __launch_bounds__(THREADS, 2) tc_gemm_kernel(Args a) {
   for (int s = 0; s < a.nseg; ++s) nk += a.seg[s].K / BK;
 
   if (tid == 0) {
-    for (int i = 0; i < STAGES; ++i) { mbar_init(bar0 + 8 * i, PRODUCERS); mbar_init(bar0 + 8 * (STAGES + i), 1); }
+    // full: one pre-counted arrival per producer thread (+ the expect_tx arrival of the weight bulk copy)
+    for (int i = 0; i < STAGES; ++i) { mbar_init(bar0 + 8 * i, PRODUCERS + (a.Wb ? 1 : 0)); mbar_init(bar0 + 8 * (STAGES + i), 1); }
     mbar_init(bar0 + 8 * 2 * STAGES, 1);
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
   }
@@ -248,7 +257,14 @@ __global__ void __launch_bounds__(THREADS, 2) tc_gemm_kernel(Args a) {
         const uint32_t sB = sA + BM * 128;
 #pragma unroll
         for (int j = 0; j < 4; ++j) cp_async16z(sA + j * 4096, abytes[j] ? ap[j] + k0 : ap[j], abytes[j]);
-        if (a.w_mn) {
+        if (a.Wb) {
+          if (tid == 0) {      // the whole weight tile of this stage: ncols / 64 consecutive 8 KB blocks
+            const uint32_t bytes = (uint32_t)(ncols >> 6) * MN_LBO;
+            mbar_expect_tx(bar0 + 8 * stage, bytes);
+            bulk_g2s(sbase + stage * stage_bytes + BM * 128,
+                     a.Wb + ((long long)(a.wb_k0 + ((koff + k0) >> 6)) * a.wb_pitch + (n0 >> 6)) * (MN_LBO / 2), bytes, bar0 + 8 * stage);
+          }
+        } else if (a.w_mn) {
           const __nv_bfloat16* wk = wp + (long long)k0 * a.ldw;
 #pragma unroll
           for (int q = 0; q < 4; ++q)
@@ -483,6 +499,9 @@ static int launch(const Args& a0, cudaStream_t st) {
   }
   QP_REQUIRE(a.BN >= 32 && a.BN <= 256 && a.BN % 32 == 0 && (a.N - a.n_begin) % 32 == 0 && (a.w_mn || a.ldw >= ktot),
              "tc gemm: bad tile shape N=%d BN=%d", a.N, a.BN);
+  if (a.Wb)
+    QP_REQUIRE(a.BN % 64 == 0 && (a.N - a.n_begin) % 64 == 0 && a.n_begin % 64 == 0 && (((size_t)a.Wb) & 15) == 0,
+               "tc gemm: blocked weights need 64-column tiles (N=%d BN=%d n_begin=%d)", a.N, a.BN, a.n_begin);
   if (a.w_mn)
     QP_REQUIRE(a.BN % 64 == 0 && (a.N - a.n_begin) % 64 == 0 && a.ldw % 8 == 0 && a.n_begin % 8 == 0,
                "tc gemm: MN-major weights need 64-column blocks (N=%d BN=%d ldw=%d)", a.N, a.BN, a.ldw);
@@ -527,6 +546,29 @@ int f32_to_bf16_pad(const float* src, long long rows, int K, int Kp, __nv_bfloat
   long long n = rows * Kp;
   if (n <= 0) return QP_OK;
   f32_to_bf16_pad_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(src, rows, K, Kp, dst, relu, ones_col);
+  QP_LAUNCH_CHECK();
+  return QP_OK;
+}
+
+// one thread per 16-byte piece (8 consecutive columns of one row)
+__global__ void block_pack_kernel(const __nv_bfloat16* __restrict__ src, long long pieces, int R, int Cc, int col_outer,
+                                  __nv_bfloat16* __restrict__ dst) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= pieces) return;
+  const int pc = Cc >> 3;                       // pieces per row
+  const long long per_mat = (long long)R * pc;
+  const long long m = i / per_mat;
+  const int rem = (int)(i - m * per_mat), row = rem / pc, piece = rem - row * pc;
+  const int rb = row >> 6, rr = row & 63, cb = piece >> 3, cp = piece & 7;
+  const long long blk = col_outer ? (long long)cb * (R >> 6) + rb : (long long)rb * (Cc >> 6) + cb;
+  const long long off = m * (long long)R * Cc + blk * 4096 + rr * 64 + ((cp ^ (rr & 7)) << 3);   // elements
+  *(uint4*)(dst + off) = *(const uint4*)(src + m * (long long)R * Cc + (long long)row * Cc + piece * 8);
+}
+
+int block_pack(const __nv_bfloat16* src, int mats, int R, int Cc, int col_outer, __nv_bfloat16* dst, cudaStream_t st) {
+  QP_REQUIRE(R % 64 == 0 && Cc % 64 == 0 && mats > 0, "block_pack: %d x %d is not made of 64 x 64 blocks", R, Cc);
+  const long long pieces = (long long)mats * R * (Cc >> 3);
+  block_pack_kernel<<<(unsigned)((pieces + 255) / 256), 256, 0, st>>>(src, pieces, R, Cc, col_outer, dst);
   QP_LAUNCH_CHECK();
   return QP_OK;
 }

@@ -51,6 +51,10 @@ struct Args {
   const float* resid; long long resid_bstride;
   float* dh; long long dh_bstride; int dh_off; int A;
   uint32_t mn_lbo, mn_sbo; // MN-major descriptor strides (filled in by the launcher)
+  // Optional pre-blocked copy of W (block_pack): 64 x 64 blocks of 8 KB with the 128-byte swizzle applied, ordered
+  // [K stage][64-column block], so the weight tile of a stage is ONE contiguous piece that a single thread moves with
+  // cp.async.bulk onto the stage mbarrier.  wb_pitch = 64-column blocks per K stage; K stage index = wb_k0 + k / 64.
+  const __nv_bfloat16* Wb; int wb_pitch; int wb_k0;
 };
 
 int gemm_gate(const Args& a, cudaStream_t st);
@@ -83,6 +87,10 @@ int f32_to_bf16_colsum(const float* src, long long rows, int K, __nv_bfloat16* d
 // ones_col >= 0: that (padding) column is set to 1 instead of 0
 int f32_to_bf16_pad(const float* src, long long rows, int K, int Kp, __nv_bfloat16* dst, int relu, cudaStream_t st,
                     int ones_col = -1);
+// src [mats][R][Cc] bf16 (R, Cc multiples of 64) -> the same elements as 64 x 64 row-major blocks of 8 KB whose 16-byte
+// pieces are XOR-ed with (row & 7) (SWIZZLE_128B), blocks ordered [col block][row block] (col_outer: K-major B operand,
+// K = columns) or [row block][col block] (MN-major B operand, K = rows)
+int block_pack(const __nv_bfloat16* src, int mats, int R, int Cc, int col_outer, __nv_bfloat16* dst, cudaStream_t st);
 int pack_wg_bf16(const float* Wg, long long rows, int twoC, int Kg, int Kgp, __nv_bfloat16* dst, cudaStream_t st);
 
 }  // namespace tc

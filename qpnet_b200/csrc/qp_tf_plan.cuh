@@ -38,6 +38,9 @@ struct TfPlan {
   int Kgp;                      // gate K with the aux segment padded to 64: 2C + 64
   __nv_bfloat16* Wg_bf;         // (L, 2C, Kgp)
   __nv_bfloat16* Wrs_bf;        // (L, C+S, C)
+  // the same weights as 64 x 64 swizzled blocks (tc::block_pack): K-major order for the forward GEMMs, MN-major order
+  // for the backward GEMMs that contract against the un-transposed weights (MN copies with QP_F_SAVE only)
+  __nv_bfloat16* WgK; __nv_bfloat16* WrsK; __nv_bfloat16* WgMN; __nv_bfloat16* WrsMN;
   __nv_bfloat16* W1_bf;         // (S, S)
   __nv_bfloat16* W2_bf;         // (Q, S)
   __nv_bfloat16* Xbf[2 * QP_MAX_LAYERS + 1];  // block inputs (B, Lin[l], C): one per block with QP_F_SAVE, else ping-pong
@@ -52,6 +55,9 @@ struct TfPlan {
   __nv_bfloat16* dskip_bf;      // (B, bl, S)
   float* dbskip;                // (S) column sum of dskip
 };
+
+// QPNET_BWD_TC bit mask (qp_backward.cu): which contractions of the bf16 backward run on tcgen05
+int bwd_tc_mask();
 
 // Fills `p`; returns total bytes.  `base` may be NULL (sizing only).
 inline size_t make_tf_plan(const QpArch* a, int B, int T, int F, int bl, int M, uint32_t flags, void* base,
@@ -127,6 +133,10 @@ inline size_t make_tf_plan(const QpArch* a, int B, int T, int F, int bl, int M, 
   if (flags & QP_F_BF16) {
     p->Wg_bf = ar.take<__nv_bfloat16>((size_t)pd.L * 2 * C * p->Kgp);
     p->Wrs_bf = ar.take<__nv_bfloat16>((size_t)pd.L * (C + S) * C);
+    p->WgK = ar.take<__nv_bfloat16>((size_t)pd.L * 2 * C * p->Kgp);
+    p->WrsK = ar.take<__nv_bfloat16>((size_t)pd.L * (C + S) * C);
+    p->WgMN = save ? ar.take<__nv_bfloat16>((size_t)pd.L * 2 * C * p->Kgp) : nullptr;
+    p->WrsMN = save ? ar.take<__nv_bfloat16>((size_t)pd.L * (C + S) * C) : nullptr;
     p->W1_bf = ar.take<__nv_bfloat16>((size_t)S * S);
     p->W2_bf = ar.take<__nv_bfloat16>((size_t)Q * S);
     if (save) {

@@ -171,7 +171,7 @@ class QPNet(nn.Module):
         # it; False selects the exact fp32 SIMT path (tight-tolerance parity)
         self.tensor_cores = (n_resch % 64 == 0 and n_skipch % 64 == 0 and n_quantize % 32 == 0 and n_aux <= 64)
         self.last_launches = 0      # kernels launched by the most recent call (bench accounting)
-        self.train_dtype = "bf16 forward GEMMs (tcgen05), fp32 backward"
+        self.train_dtype = "bf16 (tcgen05 forward and backward GEMMs, fp32 accumulation / residual stream / gradients)"
         # widths the folded cluster generator is built for (qp_generate_fold2.cu); 32 utterances per launch
         self._folded_ok = (n_resch == 512 and n_skipch == 256 and n_quantize == 256 and n_aux <= 48
                            and len(self.dilationsF) >= 3 and len(self.dilationsF) + len(self.dilationsA) <= 16)

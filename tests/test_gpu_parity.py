@@ -201,6 +201,33 @@ def test_forward_bf16_tensor_cores_vs_fp32_path(dev, C, S, B, frames, bl, fac):
     print("worst per-tensor relative L2 gradient difference bf16-forward vs fp32:", worst)
 
 
+def test_backward_tcgen05_vs_tf32_backward(dev, tmp_path):
+    """The tcgen05 backward of the bf16 path (MN-major UMMA weight gradients, dz / dX GEMMs against the un-transposed
+    weights, QPNET_BWD_TC = 7, the default) against the TF32 mma.sync backward (QPNET_BWD_TC = 0) on the SAME saved
+    forward activations: the only difference is the bf16 rounding of dgate / dX / dskip as tensor-core operands, so
+    every gradient tensor must agree to 2 % relative L2 (measured 0.55 % worst over the three shapes).  The mask is
+    read once per process, hence the two subprocesses (tools/bwd_tc_probe.py)."""
+    import os, subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    probe = os.path.join(root, "tools", "bwd_tc_probe.py")
+    dumps = {}
+    for mask in ("0", "7"):
+        out = str(tmp_path / f"grads_{mask}.pt")
+        env = dict(os.environ, QPNET_BWD_TC=mask)
+        subprocess.run([sys.executable, probe, "dump", out], check=True, env=env, cwd=root, timeout=600,
+                       stdout=subprocess.DEVNULL)
+        dumps[mask] = torch.load(out)
+    worst = (0.0, None)
+    for ci, ref in dumps["0"].items():
+        for k, v in ref.items():
+            if v.numel() == 1 or float(v.abs().max()) == 0.0:
+                continue
+            e = float((v - dumps["7"][ci][k]).norm() / v.norm())
+            assert e < 0.02, (ci, k, e)
+            worst = max(worst, (e, k))
+    print("tcgen05 vs TF32 backward, worst per-tensor relative L2:", worst)
+
+
 def test_forward_batch_elements_are_independent(dev):
     """C1: permuting the batch permutes the output (the reference fails this for B > 1)."""
     kw, a, p, x, h, d, t, bl = cases.forward_inputs("small_s2_b1")
