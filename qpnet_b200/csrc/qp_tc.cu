@@ -695,10 +695,19 @@ __global__ void __launch_bounds__(THREADS, 2) tc_wgrad_kernel(WgradArgs a) {
     // lives in registers (fully unrolled), one smem offset + g * 4096 + q * 8192 addresses every copy
     const int c = tid & 7, rg = tid >> 3;
     const uint32_t off0 = mn_piece(rg, c);
-    WBlk w[WG_MAXBLK];
-#pragma unroll
-    for (int q = 0; q < WG_MAXBLK; ++q) w[q] = sblk[q < nblk ? q : 0];
+    // Per block: source row = r + off (or the gathered row), valid iff (unsigned)src < hi.  hi folds the row range of the
+    // segment AND the end of this CTA's row chunk into one compare; an all-zero block has hi = 0.  Invalid rows copy
+    // nothing (zero fill) from row 0 of the block, so the address is always a real one.
     const __nv_bfloat16* dummy = a.q[0].base;
+    int off[WG_MAXBLK], hi[WG_MAXBLK], ld[WG_MAXBLK];
+    bool gather = false;
+#pragma unroll
+    for (int q = 0; q < WG_MAXBLK; ++q) {
+      const WBlk w = sblk[q < nblk ? q : 0];
+      off[q] = w.row_off; ld[q] = w.base ? w.ld : 0;
+      hi[q] = w.base ? (w.rowmap ? w.src_rows : max(0, min(w.src_rows, row_end + w.row_off))) : 0;
+      gather |= (q < nblk) && w.base && w.rowmap;
+    }
     int kc = 0;
     for (int b = 0; b < a.B; ++b) {
       // per batch element: block bases with this thread's column piece folded in; offsets inside one element fit 32 bits
@@ -706,25 +715,40 @@ __global__ void __launch_bounds__(THREADS, 2) tc_wgrad_kernel(WgradArgs a) {
       const int* rm[WG_MAXBLK];
 #pragma unroll
       for (int q = 0; q < WG_MAXBLK; ++q) {
-        pb[q] = w[q].base ? w[q].base + (long long)b * w[q].bstride + c * 8 : nullptr;
-        rm[q] = w[q].rowmap ? w[q].rowmap + (long long)b * a.n_rows : nullptr;
+        const WBlk w = sblk[q < nblk ? q : 0];
+        pb[q] = w.base ? w.base + (long long)b * w.bstride + c * 8 : dummy;
+        rm[q] = (w.base && w.rowmap) ? w.rowmap + (long long)b * a.n_rows : nullptr;
       }
       for (int r0 = row_begin; r0 < row_end; r0 += BK, ++kc) {
         const int stage = kc % WG_STAGES, it = kc / WG_STAGES;
         if (it > 0) mbar_wait(bar0 + 8 * (WG_STAGES + stage), (uint32_t)(it - 1) & 1u);
         const uint32_t st0 = sbase + stage * stage_bytes + off0;
+        if (!gather) {
 #pragma unroll
-        for (int g = 0; g < 2; ++g) {
-          const int r = r0 + rg + 32 * g;
-          const bool rin = r < row_end;
+          for (int g = 0; g < 2; ++g) {
+            const int r = r0 + rg + 32 * g;
 #pragma unroll
-          for (int q = 0; q < WG_MAXBLK; ++q) {
-            if (q < nblk) {
-              int src = -1;
-              if (rin && pb[q]) src = rm[q] ? rm[q][r] : r + w[q].row_off;
-              const bool ok = (unsigned)src < (unsigned)w[q].src_rows;
-              const __nv_bfloat16* gp = ok ? pb[q] + (unsigned)(src * w[q].ld) : dummy;
-              cp_async16z(st0 + g * 4096 + q * MN_LBO, gp, ok ? 16u : 0u);
+            for (int q = 0; q < WG_MAXBLK; ++q) {
+              if (q < nblk) {
+                const int src = r + off[q];
+                const bool ok = (unsigned)src < (unsigned)hi[q];
+                cp_async16z(st0 + g * 4096 + q * MN_LBO, pb[q] + (unsigned)((ok ? src : 0) * ld[q]), ok ? 16u : 0u);
+              }
+            }
+          }
+        } else {
+#pragma unroll
+          for (int g = 0; g < 2; ++g) {
+            const int r = r0 + rg + 32 * g;
+            const bool rin = r < row_end;
+#pragma unroll
+            for (int q = 0; q < WG_MAXBLK; ++q) {
+              if (q < nblk) {
+                int src = r + off[q];
+                if (rm[q]) src = rin ? rm[q][r] : -1;
+                const bool ok = (unsigned)src < (unsigned)hi[q];
+                cp_async16z(st0 + g * 4096 + q * MN_LBO, pb[q] + (unsigned)((ok ? src : 0) * ld[q]), ok ? 16u : 0u);
+              }
             }
           }
         }
