@@ -77,6 +77,21 @@ def _stream():
     return torch.cuda.current_stream().cuda_stream
 
 
+def flat_layout(tensors):
+    """Element offsets of ``tensors`` inside one flat buffer, each piece starting on a 16-byte boundary."""
+    offs, off = [], 0
+    for t in tensors:
+        offs.append(off)
+        off += (t.numel() + 3) // 4 * 4
+    return offs, off
+
+
+def flat_grad_views(tensors):
+    offs, total = flat_layout(tensors)
+    flat = torch.zeros(total, dtype=torch.float32, device=tensors[0].device)
+    return flat, [flat[o:o + t.numel()].view(t.shape) for o, t in zip(offs, tensors)]
+
+
 class _TeacherForced(torch.autograd.Function):
     """logits = stack(x, h, d; params) with the hand-written backward (qp_forward / qp_backward)."""
 
@@ -111,7 +126,10 @@ class _TeacherForced(torch.autograd.Function):
         if not (ctx.flags & _lib.QP_F_SAVE):
             raise RuntimeError("forward ran without gradient tracking")
         dlogits = dlogits.contiguous().float()
-        grads = [torch.empty_like(t) for t in tensors]
+        # every gradient is a view of ONE flat fp32 buffer (16-byte aligned pieces): autograd adopts the views as
+        # p.grad, and the data-parallel bucket all-reduces the buffer in place instead of copying 216 tensors twice
+        flat, grads = flat_grad_views(tensors)
+        ctx.model._flat_grad = flat
         check(lib.qp_backward(ctx.model._arch, _lib.ptr_array(tensors), x.data_ptr(), h.data_ptr(), d.data_ptr(),
                               B, T, F, bl, M, dlogits.data_ptr(), _lib.ptr_array(grads), ctx.ws.data_ptr(), ctx.nbytes,
                               ctx.flags, _stream()))
@@ -171,6 +189,7 @@ class QPNet(nn.Module):
         # it; False selects the exact fp32 SIMT path (tight-tolerance parity)
         self.tensor_cores = (n_resch % 64 == 0 and n_skipch % 64 == 0 and n_quantize % 32 == 0 and n_aux <= 64)
         self.last_launches = 0      # kernels launched by the most recent call (bench accounting)
+        self._flat_grad = None      # flat buffer behind the parameter gradients of the most recent backward
         self.train_dtype = "bf16 (tcgen05 forward and backward GEMMs, fp32 accumulation / residual stream / gradients)"
         # widths the folded cluster generator is built for (qp_generate_fold2.cu); 32 utterances per launch
         self._folded_ok = (n_resch == 512 and n_skipch == 256 and n_quantize == 256 and n_aux <= 48

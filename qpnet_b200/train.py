@@ -17,6 +17,8 @@ from __future__ import annotations
 
 import math
 
+import os
+
 import torch
 import torch.distributed as dist
 
@@ -67,8 +69,28 @@ class GradBucket:
             else:
                 v.copy_(p.grad)
 
-    def allreduce_mean(self):
-        """sum over ranks, then divide: every rank ends with the mean gradient (and writes it back)."""
+    def flat_in_place(self, flat):
+        """True when every p.grad is a view into ``flat`` at the layout of ``qpnet.flat_layout`` (what the hand-written
+        backward returns): the buffer can then be reduced where it is."""
+        if flat is None or flat.dtype != torch.float32:
+            return False
+        from .qpnet import flat_layout
+        offs, total = flat_layout(self.params)
+        if flat.numel() != total:
+            return False
+        base = flat.data_ptr()
+        return all(p.grad is not None and p.grad.is_contiguous() and p.grad.data_ptr() == base + 4 * o
+                   for p, o in zip(self.params, offs))
+
+    def allreduce_mean(self, flat=None):
+        """sum over ranks, then divide: every rank ends with the mean gradient (and writes it back).  ``flat``: the
+        buffer the gradients already live in (one all-reduce, no copies); otherwise they are packed into the bucket."""
+        if self.flat_in_place(flat):
+            w = self.world
+            if w > 1:
+                dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group)
+                flat.div_(w)
+            return flat
         self.pack()
         w = self.world
         if w > 1:
@@ -88,7 +110,11 @@ class Trainer:
 
     def __init__(self, model, lr: float = 1e-4, group=None):
         self.model = model
-        self.optimizer = torch.optim.Adam(model.parameters(), lr=lr)     # qpnet_train.py:426-428 (wd 0)
+        # qpnet_train.py:426-428 (Adam, wd 0): same update rule and state_dict; on the device torch's fused multi-tensor
+        # kernel updates all 216 tensors in one pass (plumbing, like the all-reduce: QPNET_FUSED_ADAM=0 for the foreach one)
+        params = list(model.parameters())
+        fused = params[0].is_cuda and os.environ.get("QPNET_FUSED_ADAM", "1") != "0"
+        self.optimizer = torch.optim.Adam(params, lr=lr, fused=True) if fused else torch.optim.Adam(params, lr=lr)
         self.bucket = GradBucket(list(model.parameters()), group)
 
     def step(self, x, h, d, t, bl: int):
@@ -100,6 +126,6 @@ class Trainer:
         loss, dlogits = ops.cross_entropy(logits.detach(), t[:, -bl:])    # fused softmax-CE + gradient
         logits.backward(dlogits)
         if self.bucket.world > 1:
-            self.bucket.allreduce_mean()
+            self.bucket.allreduce_mean(getattr(model, "_flat_grad", None))
         self.optimizer.step()
         return loss.reshape(())

@@ -42,6 +42,20 @@ def _worker(rank, world, port, out):
           and torch.allclose(params[1].grad, torch.arange(5, dtype=torch.float32) * mean)
           and torch.equal(params[2].grad, torch.zeros(2, 2))
           and flat.numel() == 21)
+    # gradients that already live in one flat buffer (what the hand-written backward returns): reduced in place
+    from qpnet_b200.qpnet import flat_grad_views
+    q = [torch.nn.Parameter(torch.zeros(3, 3)), torch.nn.Parameter(torch.zeros(1)), torch.nn.Parameter(torch.zeros(6))]
+    fl, views = flat_grad_views(q)
+    assert fl.numel() == 12 + 4 + 8 and all(v.data_ptr() % 16 == 0 for v in views)
+    for i, (pp, v) in enumerate(zip(q, views)):
+        v.fill_(float((rank + 1) * (i + 1)))
+        pp.grad = v
+    b2 = GradBucket(q)
+    assert b2.flat_in_place(fl)
+    ret = b2.allreduce_mean(fl)
+    ok = ok and ret is fl and all(torch.allclose(pp.grad, torch.full_like(pp, mean * (i + 1))) for i, pp in enumerate(q))
+    q[1].grad = torch.ones(1)                     # a foreign gradient tensor: falls back to the packed bucket
+    ok = ok and not b2.flat_in_place(fl)
     out[rank] = bool(ok)
     dist.barrier()
     dist.destroy_process_group()
