@@ -157,7 +157,7 @@ int tf_backward_f32(const QpArch* arch, const float* const* tensors, const int64
       g.W = p.Wrs_bf + (size_t)l * (C + S) * C + (dXnext ? 0 : (size_t)C * C); g.ldw = C; g.w_mn = 1;
       g.Wb = p.WrsMN + (size_t)l * (C + S) * C; g.wb_pitch = C / 64; g.wb_k0 = dXnext ? 0 : C / 64;
       g.B = B; g.n_rows = n; g.N = C; g.BN = C < 256 ? C : 256;
-      g.gin = p.G[l]; g.dgate_bf = p.dgate_bf; g.dgate_f32 = (tc_w && tc_dx) ? nullptr : p.dgate;
+      g.gin_bf = (const __nv_bfloat16*)p.G[l]; g.dgate_bf = p.dgate_bf; g.dgate_f32 = (tc_w && tc_dx) ? nullptr : p.dgate;
       if (int e = tc::gemm_dgate(g, st)) return e;
     } else {
       GemmArgs g = {};

@@ -126,6 +126,8 @@ int tf_forward_bf16(const QpArch* arch, const float* const* tensors, const int64
   const bool save = flags & QP_F_SAVE;
   // the fp32 copy of z only feeds the TF32 weight-gradient kernel; the tcgen05 one reads the bf16 operand copy
   const bool save_zf = save && !((bwd_tc_mask() & 1) && p.ones_col >= 0);
+  // likewise the sigmoid / tanh values: the tcgen05 dz GEMM reads them back as bf16 (stored in the same G[l] buffer)
+  const bool g_bf = (bwd_tc_mask() & 2) && p.ones_col >= 0;
   QP_CUDA(cudaMemsetAsync(p.status, 0, sizeof(int32_t), st));
   if (int e = upload_tensor_table(arch, tensors, p.tab, st)) return e;
   if (int e = pack_f32(arch, p.tab, p.W, st)) return e;
@@ -165,7 +167,8 @@ int tf_forward_bf16(const QpArch* arch, const float* const* tensors, const int64
     g.Wb = p.WgK + (size_t)l * 2 * C * Kgp; g.wb_pitch = 2 * C / 64;
     g.bias = p.W.bg + (size_t)2 * C * l;
     g.B = B; g.n_rows = n; g.N = 2 * C; g.n_begin = 0; g.BN = 2 * C < 256 ? 2 * C : 256;
-    g.z_bf = p.Zbf[l]; g.z_f32 = save_zf ? p.Z[l] : nullptr; g.gsave = save ? p.G[l] : nullptr;
+    g.z_bf = p.Zbf[l]; g.z_f32 = save_zf ? p.Z[l] : nullptr; g.gsave = (save && !g_bf) ? p.G[l] : nullptr;
+    g.gsave_bf = (save && g_bf) ? (__nv_bfloat16*)p.G[l] : nullptr;
     if (int e = tc::gemm_gate(g, st)) return e;
 
     tc::Args r = {};

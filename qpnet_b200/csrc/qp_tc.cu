@@ -319,6 +319,16 @@ __global__ void __launch_bounds__(THREADS, 2) tc_gemm_kernel(Args a) {
           for (int j = 0; j < 4; ++j) o[j] = f4_as_u4(z[4 * j], z[4 * j + 1], z[4 * j + 2], z[4 * j + 3]);
           warp_store_rows<64>(buf, o, (unsigned char*)(a.z_f32 + row0 * halfN + c0), 4LL * halfN, 0, hi);
         }
+        if (a.gsave_bf) {
+          uint4 o[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            o[j] = make_uint4(pack_bf16(__uint_as_float(v[8 * j]), __uint_as_float(v[8 * j + 1])),
+                              pack_bf16(__uint_as_float(v[8 * j + 2]), __uint_as_float(v[8 * j + 3])),
+                              pack_bf16(__uint_as_float(v[8 * j + 4]), __uint_as_float(v[8 * j + 5])),
+                              pack_bf16(__uint_as_float(v[8 * j + 6]), __uint_as_float(v[8 * j + 7])));
+          warp_store_rows<64>(buf, o, (unsigned char*)(a.gsave_bf + row0 * a.N + n), 2LL * a.N, 0, hi);
+        }
         if (a.gsave) {
           uint4 o[8];
 #pragma unroll
@@ -368,10 +378,22 @@ __global__ void __launch_bounds__(THREADS, 2) tc_gemm_kernel(Args a) {
         }
       } else if (EPI == EPI_DGATE) {
         // acc = dz[r][c], c = n .. n + 31 -> dgate columns 2c, 2c + 1 through the saved sigmoid / tanh values
-        const unsigned char* gp = (const unsigned char*)(a.gin + row0 * (2 * a.N) + 2 * n);
         uint4 g0[8], g1[8];
-        warp_load_rows<128>(buf, g0, gp, 8LL * a.N, 0, hi);          // (sg, th) of channels n .. n + 15
-        warp_load_rows<128>(buf, g1, gp + 128, 8LL * a.N, 0, hi);    // channels n + 16 .. n + 31
+        if (a.gin_bf) {
+          // 64 bf16 values per row: widen into the fp32 layout the arithmetic below reads
+          uint4 gb[8];
+          warp_load_rows<128>(buf, gb, (const unsigned char*)(a.gin_bf + row0 * (2 * a.N) + 2 * n), 4LL * a.N, 0, hi);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const uint4 lo = make_uint4(gb[j].x << 16, gb[j].x & 0xFFFF0000u, gb[j].y << 16, gb[j].y & 0xFFFF0000u);
+            const uint4 hi4 = make_uint4(gb[j].z << 16, gb[j].z & 0xFFFF0000u, gb[j].w << 16, gb[j].w & 0xFFFF0000u);
+            if (j < 4) { g0[2 * j] = lo; g0[2 * j + 1] = hi4; } else { g1[2 * (j - 4)] = lo; g1[2 * (j - 4) + 1] = hi4; }
+          }
+        } else {
+          const unsigned char* gp = (const unsigned char*)(a.gin + row0 * (2 * a.N) + 2 * n);
+          warp_load_rows<128>(buf, g0, gp, 8LL * a.N, 0, hi);          // (sg, th) of channels n .. n + 15
+          warp_load_rows<128>(buf, g1, gp + 128, 8LL * a.N, 0, hi);    // channels n + 16 .. n + 31
+        }
         float o[64];
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
@@ -521,7 +543,7 @@ int gemm_gate(const Args& a, cudaStream_t st) { return launch<EPI_GATE>(a, st); 
 int gemm_resskip(const Args& a, cudaStream_t st) { return launch<EPI_RESSKIP>(a, st); }
 int gemm_head(const Args& a, cudaStream_t st) { return launch<EPI_HEAD>(a, st); }
 int gemm_dgate(const Args& a, cudaStream_t st) {
-  QP_REQUIRE(a.w_mn && a.gin && a.dgate_bf, "tc dgate gemm: missing operands");
+  QP_REQUIRE(a.w_mn && (a.gin || a.gin_bf) && a.dgate_bf, "tc dgate gemm: missing operands");
   return launch<EPI_DGATE>(a, st);
 }
 int gemm_dx(const Args& a, cudaStream_t st) {

@@ -32,6 +32,7 @@ struct Args {
   __nv_bfloat16* z_bf;
   float* z_f32;            // optional fp32 copy (backward)
   float* gsave;            // optional (n_rows, 2C) sigmoid / tanh values (backward)
+  __nv_bfloat16* gsave_bf; // ... or the same as bf16 (what the tcgen05 dz GEMM reads back: half the traffic both ways)
   // EPI_RESSKIP: columns [0,C) residual projection + x(current row); [C,C+S) skip accumulation
   int C, S;
   const float* xcur; long long xcur_bstride; int xcur_off;
@@ -43,6 +44,7 @@ struct Args {
   // EPI_DGATE (backward): N = C columns of dz = [dXnext | dskip] * [R ; K]; gin (n_rows, 2C) fp32 sigmoid / tanh values
   // saved by the forward pass -> dgate (n_rows, 2C): (2c) = dz th sg (1 - sg), (2c+1) = dz sg (1 - th^2)
   const float* gin;
+  const __nv_bfloat16* gin_bf;   // bf16 sigmoid / tanh values instead of gin
   __nv_bfloat16* dgate_bf;
   float* dgate_f32;        // optional fp32 copy
   // EPI_DX (backward): acc = dgate * Wg, columns [past C | current C | aux 64]: scatter-add into dx (zeroed by the
