@@ -186,6 +186,9 @@ int qp_generate(const QpArch* arch, const float* const* tensors_host,
 int qp_workspace_status(const void* ws, void* stream);
 /* kernels launched by the most recent compute call on this thread (bench accounting) */
 int qp_last_launch_count(void);
+/* diagnostics: operand segments the tcgen05 weight-gradient launches of this process have bound to TMA descriptors
+ * (cp.async.bulk.tensor) so far; 0 means every segment went through the cp.async producers */
+int64_t qp_debug_tma_segments(void);
 
 #ifdef __cplusplus
 }

@@ -62,6 +62,7 @@ SIGNATURES = {
     "qp_generate": (C.c_int, [C.POINTER(QpArch), C.POINTER(_P), C.POINTER(QpGenerateArgs), _P, _SZ, _P]),
     "qp_workspace_status": (C.c_int, [_P, _P]),
     "qp_last_launch_count": (C.c_int, []),
+    "qp_debug_tma_segments": (C.c_int64, []),
 }
 
 

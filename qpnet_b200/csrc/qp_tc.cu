@@ -659,16 +659,25 @@ struct WBlk {
   const int* rowmap;
   long long bstride;
   int ld, row_off, src_rows;
+  int tma;                     // index of the segment's TMA descriptor, -1: copied with cp.async
+  int col;                     // first column of the block inside its segment
 };
 
-__device__ __forceinline__ WBlk wblk_resolve(const Seg* segs, int nseg, int col) {
-  WBlk w; w.base = nullptr; w.rowmap = nullptr; w.bstride = 0; w.ld = 0; w.row_off = 0; w.src_rows = 0;
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* tm, int c0, int c1, int c2, uint32_t bar) {
+  asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];\n"
+               ::"r"(dst), "l"(tm), "r"(c0), "r"(c1), "r"(c2), "r"(bar) : "memory");
+}
+
+__device__ __forceinline__ WBlk wblk_resolve(const Seg* segs, int nseg, int col, const int* use_tma, int tm0) {
+  WBlk w; w.base = nullptr; w.rowmap = nullptr; w.bstride = 0; w.ld = 0; w.row_off = 0; w.src_rows = 0; w.tma = -1; w.col = 0;
   int off = 0;
   for (int s = 0; s < nseg; ++s) {
     if (col - off < segs[s].K) {
       if (segs[s].base) {
         w.base = segs[s].base + (col - off); w.rowmap = segs[s].rowmap; w.bstride = segs[s].bstride; w.ld = segs[s].ld;
         w.row_off = segs[s].row_off; w.src_rows = segs[s].src_rows;
+        w.col = col - off;
+        if (use_tma[tm0 + s]) w.tma = tm0 + s;
       }
       return w;
     }
@@ -677,7 +686,7 @@ __device__ __forceinline__ WBlk wblk_resolve(const Seg* segs, int nseg, int col)
   return w;
 }
 
-__global__ void __launch_bounds__(THREADS, 2) tc_wgrad_kernel(WgradArgs a) {
+__global__ void __launch_bounds__(THREADS, 2) tc_wgrad_kernel(const __grid_constant__ WgradArgs a) {
   extern __shared__ unsigned char smem_raw[];
   __shared__ WBlk sblk[WG_MAXBLK];
   const uint32_t raw = smem_u32(smem_raw);
@@ -697,11 +706,13 @@ __global__ void __launch_bounds__(THREADS, 2) tc_wgrad_kernel(WgradArgs a) {
   const int nk = a.B * steps_b;
 
   if (tid == 0) {
-    for (int i = 0; i < WG_STAGES; ++i) { mbar_init(bar0 + 8 * i, PRODUCERS); mbar_init(bar0 + 8 * (WG_STAGES + i), 1); }
+    // full: one pre-counted arrival per producer thread + the expect_tx arrival that announces the TMA blocks
+    for (int i = 0; i < WG_STAGES; ++i) { mbar_init(bar0 + 8 * i, PRODUCERS + 1); mbar_init(bar0 + 8 * (WG_STAGES + i), 1); }
     mbar_init(bar0 + 8 * 2 * WG_STAGES, 1);
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
   }
-  if (tid < nblk) sblk[tid] = tid < 2 ? wblk_resolve(a.p, a.np, i0 + 64 * tid) : wblk_resolve(a.q, a.nq, j0 + 64 * (tid - 2));
+  if (tid < nblk)
+    sblk[tid] = tid < 2 ? wblk_resolve(a.p, a.np, i0 + 64 * tid, a.use_tma, 0) : wblk_resolve(a.q, a.nq, j0 + 64 * (tid - 2), a.use_tma, 2);
   if (warp == PRODUCERS / 32) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(tmem_slot)), "r"(TMEM_COLS) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
@@ -722,12 +733,15 @@ __global__ void __launch_bounds__(THREADS, 2) tc_wgrad_kernel(WgradArgs a) {
     // nothing (zero fill) from row 0 of the block, so the address is always a real one.
     const __nv_bfloat16* dummy = a.q[0].base;
     int off[WG_MAXBLK], hi[WG_MAXBLK], ld[WG_MAXBLK];
-    bool gather = false;
+    bool gather = false, cpa[WG_MAXBLK];     // cpa: the block is copied by the threads (gathered or all-zero), else by TMA
+    int ntma = 0;
 #pragma unroll
     for (int q = 0; q < WG_MAXBLK; ++q) {
       const WBlk w = sblk[q < nblk ? q : 0];
       off[q] = w.row_off; ld[q] = w.base ? w.ld : 0;
       hi[q] = w.base ? (w.rowmap ? w.src_rows : max(0, min(w.src_rows, row_end + w.row_off))) : 0;
+      cpa[q] = (q < nblk) && w.tma < 0;
+      ntma += (q < nblk) && w.tma >= 0;
       gather |= (q < nblk) && w.base && w.rowmap;
     }
     int kc = 0;
@@ -745,13 +759,22 @@ __global__ void __launch_bounds__(THREADS, 2) tc_wgrad_kernel(WgradArgs a) {
         const int stage = kc % WG_STAGES, it = kc / WG_STAGES;
         if (it > 0) mbar_wait(bar0 + 8 * (WG_STAGES + stage), (uint32_t)(it - 1) & 1u);
         const uint32_t st0 = sbase + stage * stage_bytes + off0;
+        if (tid == 0) {     // the non-gathered blocks: one TMA box each (64 rows x 64 columns, swizzled, zero-filled outside)
+          mbar_expect_tx(bar0 + 8 * stage, (uint32_t)ntma * MN_LBO);
+#pragma unroll
+          for (int q = 0; q < WG_MAXBLK; ++q) {
+            if (q < nblk && sblk[q].tma >= 0)
+              tma_load_3d(sbase + stage * stage_bytes + q * MN_LBO, &a.tm[sblk[q].tma], sblk[q].col, r0 + sblk[q].row_off, b,
+                          bar0 + 8 * stage);
+          }
+        }
         if (!gather) {
 #pragma unroll
           for (int g = 0; g < 2; ++g) {
             const int r = r0 + rg + 32 * g;
 #pragma unroll
             for (int q = 0; q < WG_MAXBLK; ++q) {
-              if (q < nblk) {
+              if (cpa[q]) {
                 const int src = r + off[q];
                 const bool ok = (unsigned)src < (unsigned)hi[q];
                 cp_async16z(st0 + g * 4096 + q * MN_LBO, pb[q] + (unsigned)((ok ? src : 0) * ld[q]), ok ? 16u : 0u);
@@ -765,7 +788,7 @@ __global__ void __launch_bounds__(THREADS, 2) tc_wgrad_kernel(WgradArgs a) {
             const bool rin = r < row_end;
 #pragma unroll
             for (int q = 0; q < WG_MAXBLK; ++q) {
-              if (q < nblk) {
+              if (cpa[q]) {
                 int src = r + off[q];
                 if (rm[q]) src = rin ? rm[q][r] : -1;
                 const bool ok = (unsigned)src < (unsigned)hi[q];
@@ -827,8 +850,48 @@ __global__ void __launch_bounds__(THREADS, 2) tc_wgrad_kernel(WgradArgs a) {
   if (warp == PRODUCERS / 32) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem), "r"(TMEM_COLS) : "memory");
 }
 
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn tensor_map_encoder() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)p;
+    const char* e = getenv("QPNET_WGRAD_TMA");
+    if (e && e[0] == '0') fn = nullptr;
+  }
+  return fn;
+}
+// bf16 [B][rows][K] view of a segment (row pitch ld, batch pitch bstride), 64 x 64 boxes, 128-byte swizzle, zero fill
+static bool encode_segment(EncodeTiledFn enc, const Seg& sg, int B, int rows, CUtensorMap* tm) {
+  if (!enc || !sg.base || sg.rowmap || rows <= 0 || (((size_t)sg.base) & 15) || (sg.ld & 7) || (sg.bstride & 7)) return false;
+  const cuuint64_t dims[3] = {(cuuint64_t)sg.K, (cuuint64_t)rows, (cuuint64_t)B};
+  const cuuint64_t strides[2] = {(cuuint64_t)sg.ld * 2, (cuuint64_t)(B > 1 ? sg.bstride : (long long)rows * sg.ld) * 2};
+  const cuuint32_t box[3] = {64, 64, 1}, estr[3] = {1, 1, 1};
+  return enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, (void*)sg.base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+             CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+static long long g_tma_segments = 0;
+long long tma_segments_bound() { return g_tma_segments; }
+
 int wgrad(const WgradArgs& a0, cudaStream_t st) {
   WgradArgs a = a0;
+  {
+    // a segment's rows beyond the last contracted row never meet a non-zero partner: clip the tensor there
+    EncodeTiledFn enc = tensor_map_encoder();
+    for (int s = 0; s < 5; ++s) a.use_tma[s] = 0;
+    for (int s = 0; s < a.np; ++s)
+      a.use_tma[s] = encode_segment(enc, a.p[s], a.B, std::min(a.p[s].src_rows, a.n_rows + a.p[s].row_off), &a.tm[s]);
+    for (int s = 0; s < a.nq; ++s)
+      a.use_tma[2 + s] = encode_segment(enc, a.q[s], a.B, std::min(a.q[s].src_rows, a.n_rows + a.q[s].row_off), &a.tm[2 + s]);
+    for (int s = 0; s < 5; ++s) g_tma_segments += a.use_tma[s];
+  }
   if (a.n_rows <= 0 || a.B <= 0 || a.I <= 0 || a.J <= 0) return QP_OK;
   int ip = 0, jp = 0;
   for (int s = 0; s < a.np; ++s) { QP_REQUIRE(a.p[s].K > 0 && a.p[s].K % 64 == 0, "tc wgrad: P segment width %d", a.p[s].K); ip += a.p[s].K; }
@@ -858,3 +921,5 @@ int wgrad(const WgradArgs& a0, cudaStream_t st) {
 
 }  // namespace tc
 }  // namespace qp
+
+extern "C" int64_t qp_debug_tma_segments(void) { return (int64_t)qp::tc::tma_segments_bound(); }

@@ -1,5 +1,7 @@
 // Interface of the bf16 tcgen05 GEMMs of the teacher-forced stack (qp_tc.cu).
 #pragma once
+#include <cuda.h>   // CUtensorMap (types only: the encoder is fetched through cudaGetDriverEntryPoint)
+
 #include "qp_common.cuh"
 
 namespace qp {
@@ -69,7 +71,12 @@ int gemm_dx(const Args& a, cudaStream_t st);
 // (the contraction runs over the time rows, the operand rows are contiguous in i / j).  P and Q are assembled from
 // column segments whose widths are multiples of 64; rows outside a segment's source range contribute zero.  The rows
 // are split over blockIdx.z and the partial products meet in `out` through fp32 atomics: the caller zeroes `out`.
-struct WgradArgs {
+struct alignas(64) WgradArgs {
+  // TMA descriptors of the non-gathered segments (p[0], p[1], q[0..2]): bf16 [B][rows][cols] tensors, box 64 x 64,
+  // SWIZZLE_128B = exactly one MN-major operand block; rows outside the tensor arrive as zeros.  use_tma[s] = 0:
+  // the segment is gathered (row map) or absent and its blocks are copied by the producer threads with cp.async.
+  CUtensorMap tm[5];
+  int use_tma[5];
   Seg p[2]; int np;        // column segments of P (rows i of the output); base == nullptr: an all-zero segment
   Seg q[3]; int nq;        // column segments of Q (columns j of the output)
   int B, n_rows;

@@ -35,3 +35,5 @@ for tc in (True, False):
         acc += [e[i].elapsed_time(e[i + 1]) for i in range(4)]
     acc /= 3
     print(("bf16 tcgen05 forward" if tc else "fp32 forward"), "ms: forward %.1f  CE %.2f  backward %.1f  adam %.2f  total %.1f" % (*acc, acc.sum()))
+from qpnet_b200 import _lib
+print("weight-gradient operand segments bound to TMA descriptors so far:", _lib.lib.qp_debug_tma_segments())
