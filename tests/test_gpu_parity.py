@@ -510,6 +510,76 @@ def test_generator_full_model_every_kernel_vs_oracle(dev, monkeypatch, fac):
         assert all(len(r) == steps for r in res)
 
 
+# ------------------------------------------------------------------ the deep preset
+DEEP = dict(n_resch=64, n_skipch=64, dilationF_depth=10, dilationF_repeat=3, dilationA_depth=4, dilationA_repeat=1)
+
+
+def test_deep_preset_forward_backward_vs_oracle(dev):
+    """`Rd10Rr3Ed4Er1` (param_model.py:65-71): 30 fixed blocks with dilations up to 512 + 4 adaptive ones (34 blocks,
+    fixed receptive field 3069) at narrow widths.  fp32 teacher-forced logits and gradients against the oracle
+    (2e-4 / 1e-3 of the per-tensor max).  bf16 tcgen05 path: the operand rounding noise accumulates over the blocks
+    like sqrt(L), so the 0.05 bar of the 16-block model becomes 0.05 * sqrt(34 / 16) = 0.073 here (measured 0.053)."""
+    a = orc.Arch(**DEEP)
+    assert len(a.dilF) == 30 and max(a.dilF) == 512 and a.rfF == 3069
+    p = orc.init_params(a, 17, 0.1)
+    frames, bl = 44, 257
+    hs, f0, _ = synth.utterance(frames, 55, 1.0, a.A)
+    T = frames * a.U
+    d = torch.from_numpy(cases.d_from_f0(f0)).float()[None, :T]
+    x = torch.from_numpy(np.random.RandomState(3).randint(0, a.Q, size=(1, T))).long()
+    t = torch.from_numpy(np.random.RandomState(4).randint(0, a.Q, size=(1, bl))).long()
+    h = torch.from_numpy(hs.T.copy())[None]
+    pr = {k: v.clone().requires_grad_(True) for k, v in p.items()}
+    want = orc.forward(a, pr, x, h, d, bl)
+    torch.nn.functional.cross_entropy(want.reshape(-1, a.Q), t.reshape(-1)).backward()
+    blt = torch.tensor([bl], device=dev)
+    m = _model(DEEP, p, dev, tensor_cores=False)
+    got = m(x.to(dev), h.to(dev), d.to(dev), blt)
+    err = float((got.detach().cpu() - want.detach()).abs().max())
+    print("deep preset fp32 max |dlogit| =", err)
+    assert err < 2e-4, err
+    torch.nn.functional.cross_entropy(got.reshape(-1, a.Q), t.to(dev).reshape(-1)).backward()
+    for k, prm in m.named_parameters():
+        ref = pr[k].grad
+        if ref is None or float(ref.abs().max()) == 0.0:
+            continue
+        e = float((prm.grad.cpu() - ref).abs().max() / ref.abs().max())
+        assert e < 1e-3, (k, e)
+    mtc = _model(DEEP, p, dev, tensor_cores=True)
+    with torch.no_grad():
+        gtc = mtc(x.to(dev), h.to(dev), d.to(dev), blt)
+    etc = float((gtc.cpu() - want.detach()).abs().max())
+    print("deep preset bf16 tcgen05 max |dlogit| =", etc)
+    assert etc < 0.05 * (34 / 16) ** 0.5, etc
+
+
+def test_deep_preset_generator_forced_logits_vs_oracle(dev):
+    """The same preset through the generator (generic persistent kernel: ring depths up to 512 fixed, 8 M adaptive):
+    per-step logits under forced symbols against the oracle's generator; the generator's 0.06 bar (16 blocks of bf16
+    weights / activations) scaled by sqrt(34 / 16) like the teacher-forced one: 0.0875 (measured 0.067)."""
+    a = orc.Arch(**DEEP)
+    p = orc.init_params(a, 18, 0.1)
+    B, fr, steps = 2, 3, 300
+    h = np.zeros((B, a.A, fr), np.float32)
+    d = np.zeros((B, fr * a.U), np.float64)
+    for b in range(B):
+        hs, f0, _ = synth.utterance(fr, 900 + b, 1.0, a.A)
+        h[b] = hs.T
+        d[b] = cases.d_from_f0(f0)
+    x = torch.full((B, 1), a.Q // 2, dtype=torch.long)
+    forced = torch.from_numpy(np.random.RandomState(5).randint(0, a.Q, size=(B, steps))).long()
+    lg = []
+    with torch.no_grad():
+        orc.generate(a, p, x, torch.from_numpy(h), [steps] * B, d, mode="argmax", force=forced, logits_out=lg, max_steps=steps)
+    want = torch.stack(lg, dim=1)
+    m = _model(DEEP, p, dev)
+    res, got = m.batch_fast_generate(x, torch.from_numpy(h), [steps] * B, d, None, "argmax", False, force=forced,
+                                     return_logits=True)
+    err = float((got.cpu() - want).abs().max())
+    print("deep preset generator max |dlogit| =", err)
+    assert err < 0.06 * (34 / 16) ** 0.5, err
+
+
 # ------------------------------------------------------------------ training step (qpnet_train.py:517-531)
 def test_training_step_matches_reference_adam_update(dev):
     """One Trainer.step against the reference's recipe run on the CPU oracle: CE on the last bl logits,
