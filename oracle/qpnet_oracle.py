@@ -423,3 +423,57 @@ def decode_pcm16(samples, mu=256):
     wav = decode_mu_law(np.asarray(samples), mu)
     return np.clip(wav * 32768, -32768, 32767).astype(np.int16)
 
+
+# --------------------------------------------------------------------------------------
+# training segmenter (qpnet_train.py:119-145 _validate_length, 181-199 _receptive_field, 242-335 train_generator)
+# --------------------------------------------------------------------------------------
+
+def validate_length(x, h, upsampling):
+    """qpnet_train.py:119-145 with an upsampling factor: trim the waveform to whole frames, or drop the frames the
+    waveform does not reach (one more than strictly needed, like the reference)."""
+    if len(x) > len(h) * upsampling:
+        x = x[: len(h) * upsampling]
+    if len(x) < len(h) * upsampling:
+        short = len(h) * upsampling - len(x)
+        h = h[: len(h) - (short // upsampling + 1)]
+        x = x[: len(h) * upsampling]
+    return x, h
+
+
+def train_segments(utterances, mean, scale, rf_causal, rf_fixed, rf_adaptive, fs, dense_factor, batch_length, batch_size,
+                   max_length, f0_threshold, upsampling, n_quantize=256, passes=1):
+    """CPU restatement of the streaming segmenter: ``utterances`` = [(int16 waveform, fp64 (frames, D) features)] in
+    file order (no shuffle).  Yields (x, h, t, d, b) numpy batches exactly like qpnet_train.py:242-335: buffers grow by
+    one utterance, the receptive field follows the largest dilated factor still buffered (181-199), the segment
+    length is clamped by max_length and rounded down to whole frames (268-284), segments advance by the batch length
+    (310-316)."""
+    xb = np.empty(0, np.float32)
+    hb = np.empty((0, len(mean)), np.float64)
+    db = np.empty(0, np.float64)
+    bx, bh, bt, bd, bb = [], [], [], [], []
+    for _ in range(passes):
+        for wav, raw in utterances:
+            x = np.asarray(wav, np.float32) / 32768
+            x, h = validate_length(x, np.asarray(raw, np.float64), upsampling)
+            f0 = h[:, 1].copy()
+            f0[f0 < f0_threshold] = f0_threshold
+            d = extend_time(dilated_factor(f0, fs, dense_factor), upsampling)
+            xb, hb, db = np.concatenate([xb, x]), np.concatenate([hb, h]), np.concatenate([db, d])
+            rf = int(rf_fixed + rf_adaptive * int(np.ceil(np.nanmax(db))) + rf_causal)
+            bl = batch_length - max(rf + batch_length - max_length, 0)
+            bl -= (rf + bl) % upsampling
+            h_bs = (rf + bl) // upsampling
+            x_bs = h_bs * upsampling + 1
+            want = batch_size - len(bx)
+            while len(hb) > want * h_bs and len(xb) > want * x_bs:
+                sym = encode_mu_law(xb[:x_bs], n_quantize)
+                hz = ((hb[:h_bs] - mean) / scale).astype(np.float32)
+                bx.append(sym[:-1]); bt.append(sym[1:]); bh.append(hz.T); bd.append(db[: x_bs - 1].astype(np.float32))
+                bb.append(bl)
+                want -= 1
+                xb, hb, db = xb[bl // upsampling * upsampling:], hb[bl // upsampling:], db[bl // upsampling * upsampling:]
+                if len(bx) == batch_size:
+                    yield np.stack(bx), np.stack(bh), np.stack(bt), np.stack(bd), np.array(bb)
+                    bx, bh, bt, bd, bb = [], [], [], [], []
+                    want = batch_size
+

@@ -306,8 +306,79 @@ def golden_checkpoint():
     print("checkpoint-7.pkl", os.path.getsize(os.path.join(HERE, "checkpoint-7.pkl")), "bytes")
 
 
+# ---------------------------------------------------------------- G9: the training segmenter, run by the reference
+def segmenter_utterances():
+    """Seeded in-memory stand-ins for the (wav, hdf5) pairs train_generator reads: int16 waveforms and fp64
+    WORLD-style feature matrices (feature_extract.py:343 writes fp64), lengths deliberately inconsistent so that
+    both branches of _validate_length run; one utterance carries an unvoiced hole (f0 == 0)."""
+    rs = np.random.RandomState(11)
+    D, U = 39, synth.UPSAMPLING
+    utts = []
+    for u, (frames, extra) in enumerate(((23, 17), (31, -45), (18, 0), (40, 260))):
+        hs, f0, _ = synth.utterance(frames, 500 + u, 1.0, D)
+        raw = rs.randn(frames, D)
+        raw[:, 0] = (rs.rand(frames) > 0.3)
+        raw[:, 1] = f0
+        if u == 2:
+            raw[5, 1] = 0.0
+        n = frames * U + extra
+        wav = np.clip(np.round(synth.noise_waveform(n, 40 + u) * 32768), -32768, 32767).astype(np.int16)
+        utts.append((wav, raw))
+    mean = rs.randn(D) * 2.0
+    scale = rs.rand(D) * 3.0 + 0.5
+    mean[0], scale[0] = 0.0, 1.0
+    return utts, mean, scale
+
+
+def golden_segmenter():
+    """train_generator itself (qpnet_train.py:200-335, unmodified function body) over the in-memory utterances: the
+    file readers are the only stubs (wavfile.read / read_hdf5 return the arrays, check_filenames is true, the
+    background-prefetch decorator is the identity).  Two passes over the list, small batch_length so that several
+    segments are cut per utterance and the batch_mod1 / batch_mod2 clamps are exercised."""
+    import copy, logging, types
+    from numpy.matlib import repmat
+    from sklearn.preprocessing import StandardScaler
+    utts, mean, scale = segmenter_utterances()
+    scaler = StandardScaler()
+    scaler.mean_, scaler.scale_, scaler.n_features_in_ = mean, scale, mean.shape[0]
+    wavfile = types.SimpleNamespace(read=lambda f: (synth.FS, utts[int(f)][0]))
+    ns = {"np": np, "torch": torch, "copy": copy, "repmat": repmat, "logging": logging, "wavfile": wavfile,
+          "read_hdf5": lambda f, key: utts[int(f)][1], "check_filenames": lambda l: True,
+          "background": lambda max_prefetch=1: (lambda gen: gen)}
+    _reference_functions("/root/reference/src/utils/utils.py", ["extend_time"], ns)
+    _reference_functions("/root/reference/src/bin/qpnet_train.py",
+                         ["_validate_length", "_dilated_factor", "_batch_f0", "_receptive_field", "train_generator"], ns)
+    cuda = torch.cuda.is_available
+    torch.cuda.is_available = lambda: False
+    out = {"mean": mean, "scale": scale}
+    try:
+        for cfg, (bl, bs, maxlen) in enumerate(((1500, 1, 30000), (2200, 2, 3000))):
+            gen = ns["train_generator"]([str(i) for i in range(len(utts))], [str(i) for i in range(len(utts))],
+                                        1, 45, 15, wav_transform=lambda x: ref.encode_mu_law(x, 256),
+                                        feat_transform=lambda x: scaler.transform(x), feature_type="world",
+                                        dense_factor=synth.DENSE_FACTOR, batch_length=bl, batch_size=bs, max_length=maxlen,
+                                        f0_threshold=0, upsampling_factor=synth.UPSAMPLING, shuffle=False)
+            n = 0
+            for k, (bx, bh, bt, bd, bb) in enumerate(gen):
+                if k >= (9 if bs == 1 else 4):
+                    break
+                for name, v in (("x", bx), ("h", bh), ("t", bt), ("d", bd), ("b", bb)):
+                    out[f"c{cfg}/{k}/{name}"] = v.numpy()
+                n += 1
+            out[f"c{cfg}/n"] = np.int64(n)
+            out[f"c{cfg}/cfg"] = np.array([bl, bs, maxlen], dtype=np.int64)
+    finally:
+        torch.cuda.is_available = cuda
+    for i, (wav, raw) in enumerate(utts):
+        out[f"wav{i}"], out[f"raw{i}"] = wav, raw
+    np.savez_compressed(os.path.join(HERE, "segmenter.npz"), **out)
+    print("segmenter.npz:", len(out), "arrays;", [int(out[f"c{c}/n"]) for c in range(2)], "batches")
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["indices", "forward", "generate", "mulaw", "decode", "checkpoint"]
+    which = sys.argv[1:] or ["indices", "forward", "generate", "mulaw", "decode", "checkpoint", "segmenter"]
+    if "segmenter" in which:
+        golden_segmenter()
     if "checkpoint" in which:
         golden_checkpoint()
     if "decode" in which:

@@ -11,6 +11,8 @@ Reference caveat C1: the reference's forward gathers past taps of ev
 element from element 0 (qpnet.py:250); parity is therefore defined against the reference
 called once per batch element, and the kernels gather per element.
 """
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -612,6 +614,39 @@ def test_training_step_matches_reference_adam_update(dev):
     for _ in range(5):
         loss = tr.step(x.to(dev), h.to(dev), d.to(dev), t.to(dev), bl)
     assert float(loss) < l0
+
+
+# ------------------------------------------------------------------ training segmenter
+def test_train_segmenter_vs_reference_goldens(dev):
+    """qpnet_b200.segmenter.TrainSegmenter against batches cut by the reference's own train_generator
+    (tests/golden/segmenter.npz: two configurations, batch sizes 1 and 2, max_length clamp, ragged utterance lengths,
+    an unvoiced hole, two passes over the list).  Batch lengths, z-scored features and dilated factors: bit exact.
+    mu-law symbols: fp64 arithmetic on the float32 samples against the reference's float32 arithmetic -- equal except
+    on rounding ties: at least 99.99 % equal and never more than one level apart."""
+    from qpnet_b200.segmenter import TrainSegmenter
+    g = np.load(os.path.join(cases.GOLDEN, "segmenter.npz"))
+    utts = [(g[f"wav{i}"], g[f"raw{i}"]) for i in range(4)]
+    total = same = 0
+    for c in range(2):
+        bl, bs, ml = [int(v) for v in g[f"c{c}/cfg"]]
+        seg = TrainSegmenter(1, 45, 15, g["mean"], g["scale"], synth.FS, synth.DENSE_FACTOR, bl, bs, ml, 0,
+                             synth.UPSAMPLING, 256, dev)
+        gen = seg.stream(utts)
+        for k in range(int(g[f"c{c}/n"])):
+            x, h, t, d, b = next(gen)
+            assert x.is_cuda and h.is_cuda and d.is_cuda
+            ref = {n: g[f"c{c}/{k}/{n}"] for n in "xhtdb"}
+            np.testing.assert_array_equal(b.cpu().numpy(), ref["b"])
+            assert x.shape == ref["x"].shape and h.shape == ref["h"].shape and d.shape == ref["d"].shape
+            np.testing.assert_array_equal(h.cpu().numpy(), ref["h"])
+            np.testing.assert_array_equal(d.cpu().numpy(), ref["d"])
+            for got, want in ((x, ref["x"]), (t, ref["t"])):
+                diff = np.abs(got.cpu().numpy() - want)
+                assert diff.max() <= 1
+                total += diff.size
+                same += int((diff == 0).sum())
+    print(f"segmenter mu-law symbols equal to the reference's: {same} of {total}")
+    assert same >= 0.9999 * total
 
 
 # ------------------------------------------------------------------ decode front / back end (SURVEY.md 8(f) rank 1)

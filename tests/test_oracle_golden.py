@@ -1,6 +1,8 @@
 """CPU suite: pin the oracle (oracle/qpnet_oracle.py) to the fixtures that
 tests/golden/make_golden.py produced by running the UNMODIFIED reference
 (/root/reference/src/nets/qpnet.py).  Indices and symbols: exact.  Floats: 1e-5."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -178,3 +180,27 @@ def test_decode_batch_lists_follow_the_reference_split():
     got = batch_lists(lengths, 3)
     assert got == [[6, 1, 3], [2, 4], [0, 5]]
     assert batch_lists([], 4) == []
+
+
+def test_train_segmenter_oracle_vs_reference_train_generator():
+    """oracle.train_segments against batches cut by the reference's own train_generator (qpnet_train.py:200-335, run
+    over in-memory utterances by tests/golden/make_golden.py::golden_segmenter): every array bit exact -- symbols,
+    z-scored features, dilated factors and the per-batch segment lengths, for both configurations."""
+    g = np.load(os.path.join(cases.GOLDEN, "segmenter.npz"))
+    utts = [(g[f"wav{i}"], g[f"raw{i}"]) for i in range(4)]
+    for c in range(2):
+        bl, bs, ml = [int(v) for v in g[f"c{c}/cfg"]]
+        gen = orc.train_segments(utts, g["mean"], g["scale"], 1, 45, 15, synth.FS, synth.DENSE_FACTOR, bl, bs, ml, 0,
+                                 synth.UPSAMPLING, 256, passes=3)
+        n = int(g[f"c{c}/n"])
+        assert n >= 4
+        lengths = set()
+        for k in range(n):
+            got = next(gen)
+            for name, v in zip("xhtdb", got):
+                ref = g[f"c{c}/{k}/{name}"]
+                assert v.shape == ref.shape and v.dtype == ref.dtype, (c, k, name, v.dtype, ref.dtype)
+                np.testing.assert_array_equal(v, ref)
+            lengths.add(int(got[4][0]))
+        assert len(lengths) >= 2          # the receptive field (hence the segment length) really changed along the stream
+
