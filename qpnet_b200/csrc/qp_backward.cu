@@ -1,7 +1,8 @@
 // Backward of the teacher-forced stack (what autograd does for the reference around
-// qpnet_train.py:526-531): exact fp32 SIMT contractions, or TF32 tensor-core contractions (fp32 accumulate) when the
-// forward ran on the bf16 tensor-core path (QP_F_BF16).  Consumes the workspace a QP_F_SAVE forward
-// filled.  All contractions reuse the segmented GEMM / weight-gradient kernels.
+// qpnet_train.py:526-531).  Exact fp32 SIMT contractions after an fp32 forward; after a bf16 tensor-core forward
+// (QP_F_BF16) the contractions of the residual blocks run on tcgen05 (qp_tc.cu: dz / dX GEMMs against the un-transposed
+// weights, MN-major weight gradients) and the two head layers on the TF32 mma.sync kernels, which are also the
+// QPNET_BWD_TC = 0 fallback of every contraction.  Consumes the workspace a QP_F_SAVE forward filled.
 #include <stdlib.h>
 
 #include "qp_gemm_f32.cuh"

@@ -1,17 +1,21 @@
-// bf16 tensor-core path of the teacher-forced stack (QP_F_BF16): tcgen05.mma GEMMs with the
-// gate / residual / skip / head math fused into the TMEM epilogue.
+// bf16 tensor-core path of the teacher-forced stack (QP_F_BF16), forward and backward: tcgen05.mma GEMMs with the
+// gate / residual / skip / head / dgate / dX math fused into the TMEM epilogue, and the weight-gradient contraction.
 //
-//   D[128 time rows x BN] (fp32, TMEM) = A[128 x K] (bf16, smem) * W[BN x K]^T (bf16, smem)
+//   tc_gemm_kernel<EPI>:  D[128 time rows x BN] (fp32, TMEM) = A[128 x K] (bf16, smem) * B[BN x K]^T (bf16, smem)
+//   tc_wgrad_kernel:      D[128 i x BJ j]                    = P[rows x 128 i]^T * Q[rows x BJ j]    (both MN-major)
 //
-// * A rows are GATHERED: up to three K-segments [x(past row) | x(current row) | h_up] of
-//   time-major bf16 activations (qpnet.py:295-298, 657-666); a producer thread owns one tile row
-//   and copies its 128-byte K-slices with cp.async into the canonical K-major SWIZZLE_128B
-//   layout tcgen05 reads (8-row x 128-byte atoms, 16-byte pieces XOR-ed with the row index).
-// * warps 0-3: producers (cp.async ring of STAGES slots, completion published per slot through
-//   an mbarrier after fence.proxy.async), afterwards the epilogue (tcgen05.ld 32x32b, one
-//   TMEM lane = one time row per thread).  warp 4: TMEM allocation; its lane 0 issues the MMAs
-//   and releases slots with tcgen05.commit.
-// * one output tile per CTA; grid = (row tiles, column tiles, batch).
+// * A rows are GATHERED: up to three K-segments [x(past row) | x(current row) | h_up] of time-major bf16 activations
+//   (qpnet.py:295-298, 657-666), copied with cp.async (eight threads per 128-byte row) into the canonical K-major
+//   SWIZZLE_128B layout tcgen05 reads (8-row x 128-byte atoms, 16-byte pieces XOR-ed with the row index); rows outside
+//   a segment are zero-filled.  cp.async completion arrives on the stage mbarrier by itself (mbarrier.arrive.noinc).
+// * Weights: K-major (forward) or, for the backward GEMMs, the SAME matrices read un-transposed as an MN-major B
+//   operand; either way one cp.async.bulk per stage from a pre-blocked, pre-swizzled copy (block_pack).
+// * Weight gradients: both operands MN-major (a stage row is a time row); non-gathered segments arrive by TMA
+//   (cp.async.bulk.tensor.3d, 64 x 64 swizzled boxes, zero fill outside the tensor), gathered ones by cp.async.
+// * warps 0-7: producers, afterwards the epilogue (tcgen05.ld 32x32b, one TMEM lane = one output row per thread, row
+//   tiles transposed through warp-private shared buffers so that global stores / loads / red.v4 are coalesced).
+//   warp 8: TMEM allocation; its lane 0 issues the MMAs and releases slots with tcgen05.commit.
+// * one output tile per CTA, two CTAs per SM (2-stage rings): the epilogue of one overlaps the mainloop of the other.
 #include "qp_tc.cuh"
 
 #include <stdlib.h>
@@ -42,16 +46,10 @@ __device__ __forceinline__ void cp_async16z(uint32_t dst, const void* src, uint3
 __device__ __forceinline__ void cp_async_arrive_noinc(uint32_t bar) {
   asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];\n" ::"r"(bar) : "memory");
 }
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }
 
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-  asm volatile("{\n .reg .b64 st;\n mbarrier.arrive.shared::cta.b64 st, [%0];\n}\n" ::"r"(bar) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   uint32_t ok = 0;
