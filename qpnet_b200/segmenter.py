@@ -21,6 +21,24 @@ import torch
 from . import ops
 
 
+def validated_lengths(n_x: int, n_h: int, U: int):
+    """qpnet_train.py:119-145 as length arithmetic: samples / frames kept of a (waveform, features) pair."""
+    if n_x > n_h * U:
+        n_x = n_h * U
+    if n_x < n_h * U:
+        n_h -= (n_h * U - n_x) // U + 1
+        n_x = n_h * U
+    return n_x, n_h
+
+
+def segment_lengths(rf: int, batch_length: int, max_length: int, U: int):
+    """qpnet_train.py:268-284: (segment length bl, frames h_bs, samples x_bs) for the current receptive field."""
+    bl = batch_length - max(rf + batch_length - max_length, 0)
+    bl -= (rf + bl) % U
+    h_bs = (rf + bl) // U
+    return bl, h_bs, h_bs * U + 1
+
+
 class TrainSegmenter:
     def __init__(self, rf_causal: int, rf_fixed: int, rf_adaptive: int, mean, scale, fs: float, dense_factor: float = 8,
                  batch_length: int = 20000, batch_size: int = 1, max_length: int = 30000, f0_threshold: float = 0,
@@ -39,21 +57,11 @@ class TrainSegmenter:
         self.d32 = torch.empty(0, dtype=torch.float32, device=self.dev)
         self._batch = [[], [], [], [], []]
 
-    # ------------------------------------------------------------------ qpnet_train.py:119-145 (lengths only)
-    def _validated_lengths(self, n_x: int, n_h: int):
-        U = self.U
-        if n_x > n_h * U:
-            n_x = n_h * U
-        if n_x < n_h * U:
-            n_h -= (n_h * U - n_x) // U + 1
-            n_x = n_h * U
-        return n_x, n_h
-
     def push(self, wav, raw):
         """Append one utterance (int16 waveform, fp64 (frames, D) features) and return the batches it completes."""
         wav = torch.as_tensor(np.ascontiguousarray(wav)).to(self.dev)
         raw = torch.as_tensor(np.ascontiguousarray(raw, dtype=np.float64)).to(self.dev)
-        n_x, n_h = self._validated_lengths(wav.numel(), raw.shape[0])
+        n_x, n_h = validated_lengths(wav.numel(), raw.shape[0], self.U)
         if n_h <= 0:
             return []
         x = wav[:n_x].to(torch.float32) / 32768                                  # qpnet_train.py:249
@@ -73,10 +81,7 @@ class TrainSegmenter:
         rfC, rfF, rfA = self.rf
         U = self.U
         rf = rfF + rfA * ops.max_ceil(self.d64) + rfC                            # 181-199 on the buffered factors
-        bl = self.batch_length - max(rf + self.batch_length - self.max_length, 0)  # 270-271
-        bl -= (rf + bl) % U                                                      # 273-274
-        h_bs = (rf + bl) // U
-        x_bs = h_bs * U + 1
+        bl, h_bs, x_bs = segment_lengths(rf, self.batch_length, self.max_length, U)   # 268-284
         out = []
         bx, bh, bt, bd, bb = self._batch
         want = self.batch_size - len(bx)

@@ -78,3 +78,27 @@ def test_grad_bucket_single_process_is_identity():
     assert b.world == 1
     b.allreduce_mean()
     assert torch.equal(p[0].grad, torch.tensor([1.0, 2.0, 3.0, 4.0]))
+
+
+def test_segmenter_length_arithmetic_matches_oracle():
+    """The host half of the device segmenter (qpnet_b200/segmenter.py): _validate_length as pure length arithmetic and
+    the per-file segment geometry, against the oracle's array version / the training-step geometry, over ragged lengths."""
+    import numpy as np
+    from oracle import qpnet_oracle as orc
+    from qpnet_b200.segmenter import segment_lengths, validated_lengths
+    from qpnet_b200.train import segment_geometry
+    rs = np.random.RandomState(0)
+    for _ in range(300):
+        U = int(rs.choice([80, 110, 120]))
+        n_h = int(rs.randint(1, 60))
+        n_x = max(1, n_h * U + int(rs.randint(-3 * U, 3 * U)))
+        x, h = orc.validate_length(np.zeros(n_x, np.float32), np.zeros((n_h, 2)), U)
+        assert validated_lengths(n_x, n_h, U) == (len(x), len(h))
+        assert len(x) == len(h) * U
+    # same clamps as Trainer's segment_geometry (qpnet_train.py:268-284) for a given receptive field
+    for M in (20, 62, 123):
+        R, bl, h_bs, x_bs = segment_geometry(M - 0.5, 20000, 110, 1, 45, 15, 30000)
+        assert segment_lengths(R, 20000, 30000, 110) == (bl, h_bs, x_bs)
+    bl, h_bs, x_bs = segment_lengths(976, 29900, 30000, 110)
+    assert 976 + bl <= 30000 and (976 + bl) % 110 == 0 and x_bs == h_bs * 110 + 1
+
