@@ -302,7 +302,7 @@ def main():
         spec = importlib.util.spec_from_file_location("bench_train", os.path.join(ROOT, "tools", "bench_train.py"))
         bench_train = importlib.util.module_from_spec(spec)
         spec.loader.exec_module(bench_train)
-        train = bench_train.measure(dev, rank, world, steps=3, warmup=3)
+        train = bench_train.measure(dev, rank, world, steps=20, warmup=3)
 
     if rank != 0:
         if world > 1:

@@ -143,9 +143,17 @@ int qp_backward(const QpArch* arch, const float* const* tensors_host, const int6
                 size_t ws_bytes, uint32_t flags, void* stream);
 
 /* fused softmax cross-entropy over (rows, Q) logits (qpnet_train.py:426-430,526):
- * loss_sum[0] += sum_r -log softmax(logits[r])[target[r]];  dlogits = (p - onehot)*scale */
+ * loss_sum[0] += sum_r -log softmax(logits[r])[target[r]];  dlogits = (p - onehot)*scale.
+ * A target outside [0, Q) (the reference asserts it away, qpnet_train.py:524) turns the loss into NaN. */
 int qp_cross_entropy(const float* logits, const int64_t* target, int64_t rows, int32_t Q,
                      float scale, float* loss_sum, float* dlogits, void* stream);
+
+/* Adam step over flat fp32 buffers (torch.optim.Adam(lr 1e-4, wd 0), qpnet_train.py:426-428; .step() at 531):
+ * param / grad / exp_avg / exp_avg_sq hold n elements (n % 4 == 0, 16-byte aligned), `step` counts from 1,
+ * `grad_scale` multiplies the gradient first (1 / world after a summed data-parallel all-reduce).  fp32 arithmetic in
+ * torch's operation order; one HBM-bound pass. */
+int qp_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, double lr,
+                 double beta1, double beta2, double eps, int32_t step, double grad_scale, void* stream);
 
 /* ---- autoregressive generator: QPNet.batch_fast_generate (qpnet.py:314-559) -------
  * One persistent cooperative kernel runs priming + every sample step for the batch. */

@@ -58,6 +58,7 @@ SIGNATURES = {
     "qp_backward": (C.c_int, [C.POINTER(QpArch), C.POINTER(_P), _P, _P, _P, _I32, _I32, _I32, _I32, _I32, _P,
                               C.POINTER(_P), _P, _SZ, _U32, _P]),
     "qp_cross_entropy": (C.c_int, [_P, _P, _I64, _I32, _F32, _P, _P, _P]),
+    "qp_adam_step": (C.c_int, [_P, _P, _P, _P, _I64, _F64, _F64, _F64, _F64, _I32, _F64, _P]),
     "qp_generate_workspace_bytes": (_SZ, [C.POINTER(QpArch), _I32, _I32]),
     "qp_generate": (C.c_int, [C.POINTER(QpArch), C.POINTER(_P), C.POINTER(QpGenerateArgs), _P, _SZ, _P]),
     "qp_workspace_status": (C.c_int, [_P, _P]),

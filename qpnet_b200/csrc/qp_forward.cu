@@ -217,9 +217,13 @@ __global__ void cross_entropy_kernel(const float* __restrict__ logits, const int
   float sum = 0.f;
   for (int q = lane; q < Q; q += 32) sum += expf(lr[q] - mx);
   for (int o = 16; o; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-  int t = (int)target[row];
+  // a target outside [0, Q) (the reference asserts max(target) < n_quantize, qpnet_train.py:524) is never used as an
+  // index: the loss becomes NaN, which the caller cannot miss
+  const int64_t t64 = target[row];
+  const bool t_ok = t64 >= 0 && t64 < Q;
+  const int t = t_ok ? (int)t64 : -1;
   float lse = mx + logf(sum);
-  if (lane == 0) atomicAdd(loss_sum, lse - lr[t]);
+  if (lane == 0) atomicAdd(loss_sum, t_ok ? lse - lr[t] : __int_as_float(0x7fc00000));
   if (dlogits) {
     float inv = 1.f / sum;
     for (int q = lane; q < Q; q += 32) {

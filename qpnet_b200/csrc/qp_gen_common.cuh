@@ -1,5 +1,5 @@
-// Device helpers shared by the two persistent generators (qp_generate.cu: generic shapes,
-// qp_generate_cl.cu: cluster K-split kernel for the SI default architecture).
+// Device helpers shared by the persistent generators (qp_generate.cu: generic shapes,
+// qp_generate_fold2.cu / qp_generate_f3.cu: cluster K-split kernels for the SI default architecture).
 #pragma once
 #include <cuda_fp16.h>
 
@@ -96,7 +96,7 @@ __device__ __forceinline__ float philox_uniform(unsigned long long seed, unsigne
   return (float)(c0 >> 8) * (1.0f / 16777216.0f);
 }
 
-// ------------------------------------------------------------------ cluster / mbarrier helpers (qp_generate_cl.cu, qp_generate_fold.cu)
+// ------------------------------------------------------------------ cluster / mbarrier helpers (qp_generate_fold2.cu, qp_generate_f3.cu)
 __device__ __forceinline__ unsigned smem_u32(const void* q) { return (unsigned)__cvta_generic_to_shared(q); }
 __device__ __forceinline__ unsigned mapa(unsigned addr, unsigned rank) {
   unsigned r;

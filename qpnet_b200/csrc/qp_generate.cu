@@ -793,34 +793,28 @@ __global__ void __launch_bounds__(GEN_THREADS, 1) gen_kernel(GenPlan p, GenArgsD
 }  // namespace qp
 
 namespace qp {
-// cluster generators for the SI default widths (qp_generate_cl.cu, qp_generate_fold.cu)
-int cl_generate(const QpArch* arch, const float* const* tensors_host, const QpGenerateArgs* a, void* ws, size_t ws_bytes,
-                cudaStream_t st);
-size_t cl_workspace_bytes(const QpArch* arch, int B, int M);
-bool cl_supported(const QpArch* arch, int B);
-int cl_trace_copy(const QpArch* arch, int B, int M, void* ws, size_t ws_bytes, long long* out_host, int n, cudaStream_t st);
-int fd_generate(const QpArch* arch, const float* const* tensors_host, const QpGenerateArgs* a, void* ws, size_t ws_bytes,
-                cudaStream_t st);
-size_t fd_workspace_bytes(const QpArch* arch, int B, int M);
-bool fd_supported(const QpArch* arch, int B);
-int fd_trace_copy(const QpArch* arch, int B, int M, void* ws, size_t ws_bytes, long long* out_host, int n, cudaStream_t st);
-int fd_stats_copy(const QpArch* arch, int B, int M, void* ws, size_t ws_bytes, long long* out_host, int n, cudaStream_t st);
+// generators for the SI default widths: qp_generate_fold2.cu (mma.sync, <= 32 utterances) and qp_generate_f3.cu
+// (tcgen05, <= 128 utterances per launch)
 int f2_generate(const QpArch* arch, const float* const* tensors_host, const QpGenerateArgs* a, void* ws, size_t ws_bytes,
                 cudaStream_t st);
 size_t f2_workspace_bytes(const QpArch* arch, int B, int M);
 bool f2_supported(const QpArch* arch, int B);
 int f2_trace_copy(const QpArch* arch, int B, int M, void* ws, size_t ws_bytes, long long* out_host, int n, cudaStream_t st);
-static thread_local int g_last_kernel = 0;   // 3: two-level folded, 2: folded, 1: cluster generator, 0: generic
-// QPNET_GEN_KERNEL = fold2 (default) | fold | cluster | generic selects the generator (debugging / A-B timing)
+int f3_generate(const QpArch* arch, const float* const* tensors_host, const QpGenerateArgs* a, void* ws, size_t ws_bytes,
+                cudaStream_t st);
+size_t f3_workspace_bytes(const QpArch* arch, int B, int M);
+bool f3_supported(const QpArch* arch, int B);
+int f3_trace_copy(const QpArch* arch, int B, int M, void* ws, size_t ws_bytes, long long* out_host, int n, cudaStream_t st);
+static thread_local int g_last_kernel = 0;   // 4: tcgen05 folded (f3), 3: two-level folded mma.sync (fold2), 0: generic
+// QPNET_GEN_KERNEL = f3 | fold2 | generic selects the generator (debugging / A-B timing); default: f3 where supported,
+// then fold2, then the generic kernel
 static int wanted_kernel(const QpArch* arch, int B) {
   const char* e = getenv("QPNET_GEN_KERNEL");
-  int want = 3;
+  int want = 4;
   if (e && strcmp(e, "generic") == 0) want = 0;
-  else if (e && strcmp(e, "cluster") == 0) want = 1;
-  else if (e && strcmp(e, "fold") == 0) want = 2;
-  if (want == 3 && !f2_supported(arch, B)) want = 2;
-  if (want == 2 && !fd_supported(arch, B)) want = 1;
-  if (want == 1 && !cl_supported(arch, B)) want = 0;
+  else if (e && strcmp(e, "fold2") == 0) want = 3;
+  if (want == 4 && !f3_supported(arch, B)) want = 3;
+  if (want == 3 && !f2_supported(arch, B)) want = 0;
   return want;
 }
 }  // namespace qp
@@ -855,9 +849,8 @@ size_t qp_generate_workspace_bytes(const QpArch* arch, int32_t B, int32_t M) {
   if (check_arch(arch) != QP_OK || B < 1 || M < 1) return 0;
   GenPlan p;
   size_t n = make_gen_plan(arch, B, 1, M, nullptr, 0, &p);
-  if (cl_supported(arch, B)) n = std::max(n, cl_workspace_bytes(arch, B, M));
-  if (fd_supported(arch, B)) n = std::max(n, fd_workspace_bytes(arch, B, M));
   if (f2_supported(arch, B)) n = std::max(n, f2_workspace_bytes(arch, B, M));
+  if (f3_supported(arch, B)) n = std::max(n, f3_workspace_bytes(arch, B, M));
   return n;
 }
 
@@ -870,21 +863,15 @@ int qp_generate(const QpArch* arch, const float* const* tensors_host, const QpGe
   cudaStream_t st = (cudaStream_t)stream;
   g_last_kernel = 0;
   int want = wanted_kernel(arch, a->B);
+  if (want == 4) {
+    int r = f3_generate(arch, tensors_host, a, ws, ws_bytes, st);
+    if (r != 1) { g_last_kernel = 4; return r; }   // 1: the clusters cannot be co-resident here -> next kernel
+    reset_launch_count();
+    want = f2_supported(arch, a->B) ? 3 : 0;
+  }
   if (want == 3) {
     int r = f2_generate(arch, tensors_host, a, ws, ws_bytes, st);
-    if (r != 1) { g_last_kernel = 3; return r; }   // 1: the clusters cannot be co-resident here -> next kernel
-    reset_launch_count();
-    want = fd_supported(arch, a->B) ? 2 : 1;
-  }
-  if (want == 2) {
-    int r = fd_generate(arch, tensors_host, a, ws, ws_bytes, st);
-    if (r != 1) { g_last_kernel = 2; return r; }   // 1: the clusters cannot be co-resident here -> next kernel
-    reset_launch_count();
-    want = cl_supported(arch, a->B) ? 1 : 0;
-  }
-  if (want == 1) {
-    int r = cl_generate(arch, tensors_host, a, ws, ws_bytes, st);
-    if (r != 1) { g_last_kernel = 1; return r; }
+    if (r != 1) { g_last_kernel = 3; return r; }
     reset_launch_count();
   }
   GenPlan p;
@@ -942,9 +929,8 @@ int qp_workspace_status(const void* ws, void* stream) {
 // debug only (not part of the public header): copy the per-phase clock64 trace of CTA 0
 int qp_debug_gen_trace(const QpArch* arch, int32_t B, int32_t M, void* ws, size_t ws_bytes, long long* out_host,
                        int32_t n, void* stream) {
+  if (g_last_kernel == 4) return f3_trace_copy(arch, B, M, ws, ws_bytes, out_host, n, (cudaStream_t)stream);
   if (g_last_kernel == 3) return f2_trace_copy(arch, B, M, ws, ws_bytes, out_host, n, (cudaStream_t)stream);
-  if (g_last_kernel == 2) return fd_trace_copy(arch, B, M, ws, ws_bytes, out_host, n, (cudaStream_t)stream);
-  if (g_last_kernel == 1) return cl_trace_copy(arch, B, M, ws, ws_bytes, out_host, n, (cudaStream_t)stream);
   GenPlan p;
   make_gen_plan(arch, B, 1, M, ws, ws_bytes, &p);
   int total = 8 * (2 * p.L + 3) * TRACE_EVENTS;
@@ -952,13 +938,6 @@ int qp_debug_gen_trace(const QpArch* arch, int32_t B, int32_t M, void* ws, size_
   QP_CUDA(cudaMemcpyAsync(out_host, p.trace, sizeof(long long) * n, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
   QP_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
   return n;
-}
-
-// debug only: per-CTA cycle sums of the folded generator (QPNET_GEN_TRACE_STEP)
-int qp_debug_gen_stats(const QpArch* arch, int32_t B, int32_t M, void* ws, size_t ws_bytes, long long* out_host,
-                       int32_t n, void* stream) {
-  if (g_last_kernel != 2) return 0;
-  return fd_stats_copy(arch, B, M, ws, ws_bytes, out_host, n, (cudaStream_t)stream);
 }
 
 }  // extern "C"

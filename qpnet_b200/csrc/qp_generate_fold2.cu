@@ -1,7 +1,7 @@
 // Two-level folded cluster generator: QPNet.batch_fast_generate (qpnet.py:314-559) for the SI default widths
 // (n_resch 512, n_skipch 256, n_quantize 256), up to 32 utterances per launch.
 //
-// qp_generate_fold.cu folds the residual 1x1 of block j-1 into the gate of block j, which halves the number of
+// experiments/qp_generate_fold.cu.txt folds the residual 1x1 of block j-1 into the gate of block j, which halves the number of
 // cross-SM exchanges per sample step, but leaves TWO vectors (z_{j-1} and x_{j-1}) and two cluster reductions on the
 // critical path of every phase.  Folding once more moves everything except one 512-vector off that path:
 //
@@ -54,7 +54,8 @@ constexpr int PT2 = 2 * KS + 8;              // finisher tile, top part pitch: [
 constexpr int PS = KS + 8;                   // pitch of the single-block parts: R,K_{j-1} | Wc_{j+1} | Wp_{j-1}
 constexpr int PWH = KH + 8;                  // head tile pitch
 constexpr int PH = AP + 8;                   // aux tile pitch
-constexpr int HR = 40;                       // Hraw pitch (floats)
+constexpr int HR = AP;                       // Hraw pitch (floats): one row per utterance, n_aux <= AP values
+static_assert(HR >= AP, "an aux row must fit its staging pitch");
 constexpr int FT_TOP = NR * PT2;                     // elements
 constexpr int FT_E = FT_TOP + NR * PS, FT_B = FT_E * 2;   // finisher tile [G|H ; R,K]: 25,600 bytes, one bulk copy
 constexpr int ST_E = 2 * NR * PS, ST_B = ST_E * 2;        // streamer tile [Wc ; Wp]: 17,408 bytes, one bulk copy

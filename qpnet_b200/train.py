@@ -23,6 +23,7 @@ import torch
 import torch.distributed as dist
 
 from . import ops
+from ._lib import check, lib
 
 
 def segment_geometry(max_d: float, batch_length: int, upsampling: int, rf_causal: int, rf_fixed: int,
@@ -104,17 +105,119 @@ class GradBucket:
         return self.flat
 
 
+class FlatAdam:
+    """``torch.optim.Adam(params, lr, betas, eps, weight_decay=0)`` (qpnet_train.py:426-428) as ONE hand-written kernel
+    (``qp_adam_step``, qp_optim.cu) over flat buffers.
+
+    The parameters are re-seated as views of one flat fp32 buffer (same layout as the flat gradient buffer the
+    hand-written backward returns, ``qpnet.flat_layout``), so ``state_dict()`` / ``load_state_dict()`` of the model keep
+    working and the step is a single element-wise pass instead of 216 tensor updates.  ``state_dict()`` /
+    ``load_state_dict()`` speak torch.optim.Adam's format, so the reference's checkpoints resume here and ours resume
+    there (qpnet_train.py:346-352, 481-489).  Construct it AFTER ``model.cuda()``: moving the model re-allocates its
+    parameters and drops the flat buffer."""
+
+    def __init__(self, params, lr: float = 1e-4, betas=(0.9, 0.999), eps: float = 1e-8):
+        from .qpnet import flat_layout
+        self.params = list(params)
+        if not self.params or not all(p.is_cuda and p.dtype == torch.float32 for p in self.params):
+            raise RuntimeError("FlatAdam needs float32 parameters on a CUDA (sm_100a) device; there is no CPU path")
+        self.lr, self.betas, self.eps = float(lr), (float(betas[0]), float(betas[1])), float(eps)
+        self.offsets, self.numel = flat_layout(self.params)
+        dev = self.params[0].device
+        self.flat = torch.zeros(self.numel, dtype=torch.float32, device=dev)
+        for p, o in zip(self.params, self.offsets):
+            view = self.flat[o:o + p.numel()].view(p.shape)
+            view.copy_(p.data)
+            p.data = view
+        self.exp_avg = torch.zeros_like(self.flat)
+        self.exp_avg_sq = torch.zeros_like(self.flat)
+        self._grad = None            # packing buffer for gradients that do not already live in one flat buffer
+        self.steps = 0
+
+    def zero_grad(self, set_to_none: bool = True):
+        for p in self.params:
+            if set_to_none:
+                p.grad = None
+            elif p.grad is not None:
+                p.grad.zero_()
+
+    def _grads_in_place(self, flat):
+        if flat is None or flat.dtype != torch.float32 or flat.numel() != self.numel or not flat.is_cuda:
+            return False
+        base = flat.data_ptr()
+        return all(p.grad is not None and p.grad.is_contiguous() and p.grad.data_ptr() == base + 4 * o
+                   for p, o in zip(self.params, self.offsets))
+
+    @torch.no_grad()
+    def step(self, flat_grad=None, grad_scale: float = 1.0):
+        """One Adam step.  ``flat_grad``: the buffer every ``p.grad`` is a view of (``model._flat_grad`` after the
+        hand-written backward); other gradients are packed first (a missing gradient counts as zero)."""
+        if not self._grads_in_place(flat_grad):
+            if self._grad is None:
+                self._grad = torch.zeros_like(self.flat)
+            for p, o in zip(self.params, self.offsets):
+                dst = self._grad[o:o + p.numel()]
+                if p.grad is None:
+                    dst.zero_()
+                else:
+                    dst.copy_(p.grad.reshape(-1))
+            flat_grad = self._grad
+        if self.flat.data_ptr() % 16 or any(p.data_ptr() != self.flat.data_ptr() + 4 * o for p, o in zip(self.params, self.offsets)):
+            raise RuntimeError("the parameters left the flat buffer (model moved after the optimizer was built?)")
+        self.steps += 1
+        check(lib.qp_adam_step(self.flat.data_ptr(), flat_grad.data_ptr(), self.exp_avg.data_ptr(), self.exp_avg_sq.data_ptr(),
+                               self.numel, self.lr, self.betas[0], self.betas[1], self.eps, self.steps, float(grad_scale),
+                               torch.cuda.current_stream().cuda_stream))
+
+    # ---- torch.optim.Adam's checkpoint format ------------------------------------------------
+    def state_dict(self):
+        state = {}
+        if self.steps > 0:
+            for i, (p, o) in enumerate(zip(self.params, self.offsets)):
+                n = p.numel()
+                state[i] = {"step": torch.tensor(float(self.steps)),
+                            "exp_avg": self.exp_avg[o:o + n].view(p.shape).clone(),
+                            "exp_avg_sq": self.exp_avg_sq[o:o + n].view(p.shape).clone()}
+        group = {"lr": self.lr, "betas": self.betas, "eps": self.eps, "weight_decay": 0, "amsgrad": False,
+                 "maximize": False, "foreach": None, "capturable": False, "differentiable": False, "fused": None,
+                 "decoupled_weight_decay": False, "params": list(range(len(self.params)))}
+        return {"state": state, "param_groups": [group]}
+
+    def load_state_dict(self, sd):
+        group = sd["param_groups"][0]
+        if len(group["params"]) != len(self.params):
+            raise ValueError("optimizer state has a different number of parameters")
+        if group.get("weight_decay", 0) != 0 or group.get("amsgrad", False):
+            raise ValueError("only plain Adam (weight_decay 0, no amsgrad) is supported, like qpnet_train.py:426-428")
+        self.lr, self.eps = float(group["lr"]), float(group["eps"])
+        self.betas = (float(group["betas"][0]), float(group["betas"][1]))
+        self.exp_avg.zero_()
+        self.exp_avg_sq.zero_()
+        steps = 0
+        for i, (p, o) in enumerate(zip(self.params, self.offsets)):
+            st = sd["state"].get(group["params"][i])
+            if st is None:                      # torch keeps no state for parameters that never had a gradient (C7)
+                continue
+            n = p.numel()
+            self.exp_avg[o:o + n].copy_(st["exp_avg"].reshape(-1))
+            self.exp_avg_sq[o:o + n].copy_(st["exp_avg_sq"].reshape(-1))
+            steps = max(steps, int(st["step"]))
+        self.steps = steps
+
+
 class Trainer:
     """One SI-QPNet optimisation step per call (qpnet_train.py:517-531), data parallel when
     ``torch.distributed`` is initialised."""
 
     def __init__(self, model, lr: float = 1e-4, group=None):
         self.model = model
-        # qpnet_train.py:426-428 (Adam, wd 0): same update rule and state_dict; on the device torch's fused multi-tensor
-        # kernel updates all 216 tensors in one pass (plumbing, like the all-reduce: QPNET_FUSED_ADAM=0 for the foreach one)
+        # qpnet_train.py:426-428 (Adam, wd 0): the hand-written flat-buffer kernel (FlatAdam); QPNET_TORCH_ADAM=1 selects
+        # torch.optim.Adam(fused=True) on the reference-shaped tensors for A/B timing
         params = list(model.parameters())
-        fused = params[0].is_cuda and os.environ.get("QPNET_FUSED_ADAM", "1") != "0"
-        self.optimizer = torch.optim.Adam(params, lr=lr, fused=True) if fused else torch.optim.Adam(params, lr=lr)
+        if os.environ.get("QPNET_TORCH_ADAM", "0") == "1":
+            self.optimizer = torch.optim.Adam(params, lr=lr, fused=True)
+        else:
+            self.optimizer = FlatAdam(params, lr=lr)
         self.bucket = GradBucket(list(model.parameters()), group)
 
     def step(self, x, h, d, t, bl: int):
@@ -125,7 +228,11 @@ class Trainer:
         logits = model(x, h, d, blt)                                      # (B, bl, Q), autograd-attached
         loss, dlogits = ops.cross_entropy(logits.detach(), t[:, -bl:])    # fused softmax-CE + gradient
         logits.backward(dlogits)
+        flat = getattr(model, "_flat_grad", None)
         if self.bucket.world > 1:
-            self.bucket.allreduce_mean(getattr(model, "_flat_grad", None))
-        self.optimizer.step()
+            self.bucket.allreduce_mean(flat)
+        if isinstance(self.optimizer, FlatAdam):
+            self.optimizer.step(flat)
+        else:
+            self.optimizer.step()
         return loss.reshape(())

@@ -481,7 +481,7 @@ def test_generator_utterance_groups_vs_oracle(dev, monkeypatch, kw, B, groups):
 
 @pytest.mark.parametrize("fac", [1.0, 0.5, 1.5])
 def test_generator_full_model_every_kernel_vs_oracle(dev, monkeypatch, fac):
-    """SI default architecture on every generator kernel (QPNET_GEN_KERNEL = fold2 | fold | cluster | generic), with the
+    """SI default architecture on every generator kernel (QPNET_GEN_KERNEL = f3 | fold2 | generic), with the
     F0 contour scaled x0.5 / x1.5 (BASELINE configs[2]: longest and shortest pitch-dependent look-backs, ring depth up to
     8 * ceil(max d)).  Teacher-forced per-step logits against the CPU oracle, 0.06 absolute; the steps run past the
     look-back of the first adaptive blocks so the rings are read back, not only primed."""
@@ -502,7 +502,7 @@ def test_generator_full_model_every_kernel_vs_oracle(dev, monkeypatch, fac):
                      max_steps=steps)
     want = torch.stack(lg, dim=1)
     m = _model({}, p, dev)
-    for kernel in ("fold2", "fold", "cluster", "generic"):
+    for kernel in ("f3", "fold2", "generic"):
         monkeypatch.setenv("QPNET_GEN_KERNEL", kernel)
         res, got = m.batch_fast_generate(x, torch.from_numpy(h), [steps] * B, d, None, "argmax", False, force=forced,
                                          return_logits=True)
@@ -688,3 +688,59 @@ def test_decode_backend_pcm16_and_pipeline(dev, tmp_path):
     import wave
     with wave.open(str(tmp_path / "a.wav")) as w:
         assert w.getframerate() == synth.FS and w.getnframes() == len(out["a"]) and w.getsampwidth() == 2
+
+
+# ------------------------------------------------------------------ the optimizer step (qpnet_train.py:426-428, 531)
+@pytest.mark.gpu
+def test_flat_adam_matches_torch_adam_and_resumes_reference_checkpoint(dev, tmp_path):
+    """FlatAdam (one hand-written kernel over flat parameter / gradient / moment buffers) against torch.optim.Adam on the
+    same gradients for three steps: parameters and both moments agree to fp32 rounding (the kernel keeps torch's
+    operation order; the bias corrections are computed in double precision on the host).  Then the reference's own
+    checkpoint (tests/golden/checkpoint-7.pkl, written by the unmodified reference class + torch Adam) is resumed into
+    FlatAdam and stepped once against torch Adam resumed from the same file."""
+    from qpnet_b200 import checkpoint as ck
+    from qpnet_b200.qpnet import QPNet
+    from qpnet_b200.train import FlatAdam
+    a = orc.Arch(**cases.SMALL)
+    p = orc.init_params(a, 3, 0.1)
+    m1, m2 = _model(cases.SMALL, p, dev), _model(cases.SMALL, p, dev)
+    o1 = torch.optim.Adam(m1.parameters(), lr=1e-4)
+    o2 = FlatAdam(m2.parameters(), lr=1e-4)
+    gen = torch.Generator(device="cpu").manual_seed(0)
+    for step in range(3):
+        for q1, q2 in zip(m1.parameters(), m2.parameters()):
+            g = (torch.randn(q1.shape, generator=gen) * 10.0 ** float(torch.randint(-6, 1, (1,), generator=gen))).to(dev)
+            q1.grad, q2.grad = g.clone(), g.clone()
+        o1.step()
+        o2.step()
+        for (k, q1), q2 in zip(m1.named_parameters(), m2.parameters()):
+            torch.testing.assert_close(q2.detach(), q1.detach(), rtol=2e-6, atol=1e-9, msg=lambda s: f"{k} step {step}: {s}")
+    s1, s2 = o1.state_dict(), o2.state_dict()
+    assert list(s2["param_groups"][0]["params"]) == list(s1["param_groups"][0]["params"])
+    for i in s1["state"]:
+        assert float(s2["state"][i]["step"]) == float(s1["state"][i]["step"]) == 3.0
+        torch.testing.assert_close(s2["state"][i]["exp_avg"].cpu(), s1["state"][i]["exp_avg"].cpu(), rtol=2e-6, atol=1e-12)
+        torch.testing.assert_close(s2["state"][i]["exp_avg_sq"].cpu(), s1["state"][i]["exp_avg_sq"].cpu(), rtol=2e-6, atol=1e-15)
+    # the model's state_dict still has the reference's names / shapes although the parameters now share one buffer
+    assert [tuple(v.shape) for v in m2.state_dict().values()] == [tuple(v.shape) for v in m1.state_dict().values()]
+    # resume the reference's checkpoint
+    gold = os.path.join(cases.GOLDEN)
+    kw = ck.load_config(os.path.join(gold, "model.conf"))
+    r1, r2 = QPNet(**kw).to(dev), QPNet(**kw).to(dev)
+    t1, t2 = torch.optim.Adam(r1.parameters(), lr=1e-4), FlatAdam(r2.parameters(), lr=1e-4)
+    assert ck.load_checkpoint(os.path.join(gold, "checkpoint-7.pkl"), r1, t1) == 7
+    assert ck.load_checkpoint(os.path.join(gold, "checkpoint-7.pkl"), r2, t2) == 7
+    assert t2.steps == int(t1.state_dict()["state"][0]["step"])
+    for q1, q2 in zip(r1.parameters(), r2.parameters()):
+        assert torch.equal(q1, q2)
+        g = torch.randn(q1.shape, generator=gen).to(dev) * 1e-2
+        q1.grad, q2.grad = g.clone(), g.clone()
+    t1.step()
+    t2.step()
+    for q1, q2 in zip(r1.parameters(), r2.parameters()):
+        torch.testing.assert_close(q2.detach(), q1.detach(), rtol=2e-6, atol=1e-9)
+    path = ck.save_checkpoint(str(tmp_path), r2, t2, 8)
+    again = torch.load(path, weights_only=False)
+    fresh = torch.optim.Adam(QPNet(**kw).parameters(), lr=1e-4)
+    fresh.load_state_dict(again["optimizer"])           # torch accepts what FlatAdam wrote
+    assert float(fresh.state_dict()["state"][0]["step"]) == 8.0

@@ -73,7 +73,7 @@ def measure(dev, rank, world, steps=5, warmup=3, fp32=False, batch_length=20000)
     if rank != 0:
         return None
     peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {}
-    peak = float(peaks.get("bf16_tflops_sustained", 1400.0))
+    peak = float(peaks.get("bf16_tflops_sustained", 1400.0)) * world      # whole-job FLOP/s against world x one GPU's peak
     seg_s = world * steps / sec
     flops = seg_s * bl * 141.5e6
     return {"metric": "train seg/s", "value": seg_s, "unit": "segments/s", "n_gpus": world, "steps": steps,
@@ -82,7 +82,7 @@ def measure(dev, rank, world, steps=5, warmup=3, fp32=False, batch_length=20000)
             "data": "synthetic",
             "config": {"workload": "BASELINE configs[4]: SI-QPNet training step, 1 segment per rank", "bl": bl,
                        "receptive_field": R, "segment_samples": x_bs - 1, "parallelism": f"dp{world}, one NCCL all-reduce of {tr.bucket.numel} fp32 gradients"},
-            "roofline": {"bound": "tensor", "achieved": flops / 1e12, "peak": peak, "unit": "TFLOP/s", "frac": flops / 1e12 / peak,
+            "roofline": {"bound": "tensor", "achieved": flops / 1e12, "peak": peak, "peak_is": f"{world} x measured sustained bf16 (MEASURED_PEAKS.json)", "unit": "TFLOP/s", "frac": flops / 1e12 / peak,
                          "algorithmic_flops_per_step": bl * 141.5e6},
             "loss_first_last": [losses[0], losses[-1]], "gpu_launches_per_step": model.last_launches}
 
