@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define QP_ABI_VERSION 2
+#define QP_ABI_VERSION 3
 #define QP_MAX_LAYERS 64
 
 enum {
@@ -184,6 +184,10 @@ typedef struct QpGenerateArgs {
                                keys the in-kernel Philox stream, so that an utterance
                                draws the same numbers whichever launch / slot it runs in
                                (NULL: the slot index)                                    */
+  int16_t* out_pcm;     /* optional (B, ld_out_pcm): the generated waveform as 16-bit PCM,
+                           decode_mu_law(symbol) * 32768 clipped (qpnet_decode.py:315-318),
+                           written by the generator as its output stage                */
+  int64_t ld_out_pcm;
 } QpGenerateArgs;
 
 size_t qp_generate_workspace_bytes(const QpArch* arch, int32_t B, int32_t M);

@@ -31,7 +31,7 @@ class QpGenerateArgs(C.Structure):
                 ("uniforms", C.c_void_p), ("ld_uniforms", C.c_int64), ("philox_seed", C.c_uint64),
                 ("force", C.c_void_p), ("ld_force", C.c_int64),
                 ("out", C.c_void_p), ("ld_out", C.c_int64), ("logits_out", C.c_void_p),
-                ("utt_ids", C.c_void_p)]
+                ("utt_ids", C.c_void_p), ("out_pcm", C.c_void_p), ("ld_out_pcm", C.c_int64)]
 
 
 # name -> (restype, argtypes): every symbol include/qpnet_b200.h declares
@@ -82,7 +82,7 @@ def _load():
     for name, (res, args) in SIGNATURES.items():
         fn = getattr(lib, name)          # AttributeError here = header / library mismatch
         fn.restype, fn.argtypes = res, args
-    if lib.qp_abi_version() != 2:
+    if lib.qp_abi_version() != 3:
         raise ImportError("libqpnet_b200.so ABI version mismatch")
     return lib
 

@@ -145,6 +145,7 @@ struct GenArgsDev {
   const int32_t* force; long long ld_force;
   const int32_t* utt_ids;   // optional: the caller-side index of every utterance (keys the Philox stream)
   int32_t* out; long long ld_out; float* logits_out;
+  int16_t* out_pcm; long long ld_out_pcm; const int16_t* pcm_lut;   // optional PCM output stage (symbol -> int16 through a 256-entry table)
   int mode, max_steps, d_is_f64;
   const float* causal_b; const float* up_w; const float* up_b;
 };

@@ -805,6 +805,7 @@ int f3_generate(const QpArch* arch, const float* const* tensors_host, const QpGe
 size_t f3_workspace_bytes(const QpArch* arch, int B, int M);
 bool f3_supported(const QpArch* arch, int B);
 int f3_trace_copy(const QpArch* arch, int B, int M, void* ws, size_t ws_bytes, long long* out_host, int n, cudaStream_t st);
+int pcm16_rows(const int32_t* sym, long long ld, int B, int n_steps, int n_quantize, int16_t* out, long long ld_out, cudaStream_t st);   // qp_util.cu
 static thread_local int g_last_kernel = 0;   // 4: tcgen05 folded (f3), 3: two-level folded mma.sync (fold2), 0: generic
 // QPNET_GEN_KERNEL = f3 | fold2 | generic selects the generator (debugging / A-B timing); default: f3 where supported,
 // then fold2, then the generic kernel
@@ -854,8 +855,21 @@ size_t qp_generate_workspace_bytes(const QpArch* arch, int32_t B, int32_t M) {
   return n;
 }
 
+static int generate_symbols(const QpArch* arch, const float* const* tensors_host, const QpGenerateArgs* a, void* ws,
+                            size_t ws_bytes, void* stream);
+
 int qp_generate(const QpArch* arch, const float* const* tensors_host, const QpGenerateArgs* a, void* ws,
                 size_t ws_bytes, void* stream) {
+  int r = generate_symbols(arch, tensors_host, a, ws, ws_bytes, stream);
+  if (r != QP_OK) return r;
+  // PCM output stage (qpnet_decode.py:315-318): the tcgen05 generator writes it itself, the others are post-processed
+  if (a->out_pcm && g_last_kernel != 4)
+    return pcm16_rows(a->out, a->ld_out, a->B, a->max_steps, arch->n_quantize, a->out_pcm, a->ld_out_pcm, (cudaStream_t)stream);
+  return QP_OK;
+}
+
+static int generate_symbols(const QpArch* arch, const float* const* tensors_host, const QpGenerateArgs* a, void* ws,
+                            size_t ws_bytes, void* stream) {
   if (int e = check_device()) return e;
   if (int e = validate_gen(arch, a)) return e;
   QP_REQUIRE(tensors_host && ws, "generate: NULL pointer");
@@ -897,6 +911,7 @@ int qp_generate(const QpArch* arch, const float* const* tensors_host, const QpGe
   g.uniforms = a->uniforms; g.ld_uniforms = a->ld_uniforms; g.philox_seed = a->philox_seed;
   g.force = a->force; g.ld_force = a->ld_force; g.utt_ids = a->utt_ids;
   g.out = a->out; g.ld_out = a->ld_out; g.logits_out = a->logits_out;
+  g.out_pcm = nullptr; g.ld_out_pcm = 0; g.pcm_lut = nullptr;   // PCM output stage: qp_generate() post-processes for this kernel
   g.mode = a->mode; g.max_steps = a->max_steps; g.d_is_f64 = a->d_is_f64;
   g.causal_b = tensors_host[tm.causal_b()]; g.up_w = tensors_host[tm.up_w()]; g.up_b = tensors_host[tm.up_b()];
   const bool full = p.C == 512 && p.S == 256 && p.Q == 256 && p.A == 39;

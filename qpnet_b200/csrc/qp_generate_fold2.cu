@@ -1153,6 +1153,7 @@ int f2_generate(const QpArch* arch, const float* const* tensors_host, const QpGe
   g.uniforms = a->uniforms; g.ld_uniforms = a->ld_uniforms; g.philox_seed = a->philox_seed;
   g.force = a->force; g.ld_force = a->ld_force; g.utt_ids = a->utt_ids;
   g.out = a->out; g.ld_out = a->ld_out; g.logits_out = a->logits_out;
+  g.out_pcm = nullptr; g.ld_out_pcm = 0; g.pcm_lut = nullptr;   // PCM output stage: qp_generate() post-processes for this kernel
   g.mode = a->mode; g.max_steps = a->max_steps; g.d_is_f64 = a->d_is_f64;
   g.causal_b = tensors_host[tm.causal_b()]; g.up_w = tensors_host[tm.up_w()]; g.up_b = tensors_host[tm.up_b()];
   QP_CUDA(cudaLaunchKernelEx(&cfg, kern, p, g));

@@ -118,14 +118,31 @@ __global__ void feat_prepare_kernel(const double* __restrict__ raw, const int32_
 
 // ------------------------------------------------------------------ decode back end (qpnet_decode.py:315-318)
 // symbol -> decode_mu_law (qpnet.py:34-45, fp64) -> * 32768 -> clip [-32768, 32767] -> int16 (numpy astype: truncation)
-__global__ void mulaw_pcm16_kernel(const int32_t* __restrict__ y, int64_t n, double mu, int16_t* __restrict__ out) {
-  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  double fx = ((double)y[i] - 0.5) / mu * 2.0 - 1.0;
+__device__ __forceinline__ int16_t mulaw_pcm16_of(int y, double mu) {
+  double fx = ((double)y - 0.5) / mu * 2.0 - 1.0;
   double sgn = (fx > 0.0) - (fx < 0.0);
   double w = sgn / mu * (pow(1.0 + mu, fabs(fx)) - 1.0) * 32768.0;
   w = fmin(fmax(w, -32768.0), 32767.0);
-  out[i] = (int16_t)w;   // C conversion truncates toward zero, like ndarray.astype(np.int16)
+  return (int16_t)w;   // C conversion truncates toward zero, like ndarray.astype(np.int16)
+}
+__global__ void mulaw_pcm16_kernel(const int32_t* __restrict__ y, int64_t n, double mu, int16_t* __restrict__ out) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  out[i] = mulaw_pcm16_of(y[i], mu);
+}
+// the 256-entry table the tcgen05 generator indexes in its output stage (same arithmetic: bit-identical)
+__global__ void pcm_lut_kernel(int16_t* __restrict__ lut, int n, double mu) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) lut[i] = mulaw_pcm16_of(i, mu);
+}
+
+// PCM output stage for the generators that do not write PCM themselves: symbols (B, ld) -> int16 (B, ld_out)
+__global__ void mulaw_pcm16_rows_kernel(const int32_t* __restrict__ y, long long ld, int B, int n_steps, double mu,
+                                        int16_t* __restrict__ out, long long ld_out) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)B * n_steps) return;
+  const int b = (int)(i / n_steps), t = (int)(i % n_steps);
+  out[(long long)b * ld_out + t] = mulaw_pcm16_of(y[(long long)b * ld + t], mu);
 }
 
 template <typename T>
@@ -159,6 +176,21 @@ __global__ void index_kernel(const TIn* __restrict__ d, int B, int n, int64_t ld
   idx[i] = (TOut)r;
 }
 
+}  // namespace qp
+
+namespace qp {
+int pcm_lut_fill(int16_t* lut, int n_quantize, cudaStream_t st) {
+  pcm_lut_kernel<<<(n_quantize + 255) / 256, 256, 0, st>>>(lut, n_quantize, (double)(n_quantize - 1));
+  QP_LAUNCH_CHECK();
+  return QP_OK;
+}
+int pcm16_rows(const int32_t* sym, long long ld, int B, int n_steps, int n_quantize, int16_t* out, long long ld_out, cudaStream_t st) {
+  const long long n = (long long)B * n_steps;
+  if (n == 0) return QP_OK;
+  mulaw_pcm16_rows_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(sym, ld, B, n_steps, (double)(n_quantize - 1), out, ld_out);
+  QP_LAUNCH_CHECK();
+  return QP_OK;
+}
 }  // namespace qp
 
 using namespace qp;

@@ -141,7 +141,7 @@ class _TeacherForced(torch.autograd.Function):
 class QPNet(nn.Module):
     """QUASI-PERIODIC WAVENET -- same constructor as qpnet.py:174-178."""
 
-    GROUP = 32      # utterances per launch of the folded cluster generator
+    GROUP = 128     # utterances per launch of the tcgen05 cluster generator (qp_generate_f3.cu)
 
     def __init__(self, n_quantize=256, n_aux=39, n_resch=512, n_skipch=256,
                  dilationF_depth=4, dilationF_repeat=3, dilationA_depth=4, dilationA_repeat=1,
@@ -191,9 +191,11 @@ class QPNet(nn.Module):
         self.last_launches = 0      # kernels launched by the most recent call (bench accounting)
         self._flat_grad = None      # flat buffer behind the parameter gradients of the most recent backward
         self.train_dtype = "bf16 (tcgen05 forward and backward GEMMs, fp32 accumulation / residual stream / gradients)"
-        # widths the folded cluster generator is built for (qp_generate_fold2.cu); 32 utterances per launch
-        self._folded_ok = (n_resch == 512 and n_skipch == 256 and n_quantize == 256 and n_aux <= 48
-                           and len(self.dilationsF) >= 3 and len(self.dilationsF) + len(self.dilationsA) <= 16)
+        # widths the cluster generators are built for (qp_generate_f3.cu: tcgen05, 128 utterances per launch, any depth;
+        # qp_generate_fold2.cu: mma.sync, 32 utterances, <= 16 blocks)
+        self._folded_ok = (n_resch == 512 and n_skipch == 256 and n_quantize == 256 and n_aux <= 64
+                           and len(self.dilationsF) >= 1 and self.dilationsF[0] == 1
+                           and 4 <= len(self.dilationsF) + len(self.dilationsA) <= 64)
         self.philox_seed = 100      # qpnet_decode.py:58 default --seed
 
     # ------------------------------------------------------------------ helpers
@@ -230,8 +232,8 @@ class QPNet(nn.Module):
         d (B,F*U) fp64 (numpy flavour of the reference) or fp32 (extra_memory flavour), n_dev (B,)
         int32.  Returns (symbols (B, max_n) int32 on the device, logits or None).
 
-        The folded cluster generator runs 32 utterances per launch.  A larger batch of the SI default widths is
-        dealt to launches of 32, longest first, so every launch retires at its own last step (the reference's decoder
+        The tcgen05 cluster generator runs up to 128 utterances per launch.  A larger batch of the SI default widths is
+        dealt to launches of 128, longest first, so every launch retires at its own last step (the reference's decoder
         sorts by length for the same reason, qpnet_decode.py:257-259); ``utt_ids`` keeps every utterance on the Philox
         stream of its caller-side index, so the symbols do not depend on the grouping."""
         B = h.shape[0]
@@ -259,7 +261,7 @@ class QPNet(nn.Module):
         return self._generate_launch(seed, h, d, n_dev, max_n, qmode, uniforms, force, return_logits, check_status, None)
 
     def _generate_launch(self, seed, h, d, n_dev, max_n, qmode, uniforms, force, return_logits, check_status, utt_ids):
-        """One qp_generate call (<= 32 utterances on the folded kernel, any number on the generic one)."""
+        """One qp_generate call (<= 128 utterances on the tcgen05 cluster kernel, any number on the generic one)."""
         params = self._tensors()
         dev = params[0].device
         ops._need_cuda(seed, h, d, n_dev)

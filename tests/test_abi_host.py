@@ -27,7 +27,7 @@ def test_library_exports_every_declared_symbol():
     assert not missing, missing
     # the ctypes table binds exactly the declared symbols
     assert sorted(_lib.SIGNATURES) == declared
-    assert _lib.lib.qp_abi_version() == 2
+    assert _lib.lib.qp_abi_version() == 3
 
 
 def test_no_cpu_fallback_without_gpu():

@@ -390,13 +390,13 @@ def test_generator_is_deterministic_and_batch_independent(dev):
         assert np.array_equal(solo[0], r)
 
 
-def test_generator_large_batch_is_dealt_to_launches_of_32(dev):
-    """More than 32 utterances of the SI default widths: dealt to launches of 32, longest first (host wrapper).  Every
+def test_generator_large_batch_is_dealt_to_launches_of_128(dev):
+    """More than 128 utterances of the SI default widths: dealt to launches of 128, longest first (host wrapper).  Every
     utterance must come out exactly as in a solo call -- same Philox stream (utt_ids), same arithmetic."""
     a = orc.Arch()
     p = orc.init_params(a, 8, 0.05)
     m = _model({}, p, dev)
-    B = 37
+    B = 131
     frames = [1 + (b % 2) for b in range(B)]
     Fm = max(frames)
     h = np.zeros((B, a.A, Fm), np.float32)
@@ -406,13 +406,13 @@ def test_generator_large_batch_is_dealt_to_launches_of_32(dev):
         hs, f0, n = synth.utterance(frames[b], 900 + b, 1.0, a.A)
         h[b, :, :frames[b]] = hs.T
         d[b, :frames[b] * a.U] = cases.d_from_f0(f0)
-        n_list.append(min(n, 40 + 3 * b))
+        n_list.append(min(n, 40 + b))
     x = torch.full((B, 1), a.Q // 2, dtype=torch.long)
     m.philox_seed = 5
     res = m.batch_fast_generate(x, torch.from_numpy(h), list(n_list), d)
     order = np.argsort(np.array(n_list), kind="stable")
     assert [len(r) for r in res] == sorted(n_list)
-    for b in (0, 17, 36):
+    for b in (0, 17, 130):
         pos = list(order).index(b)
         solo = m.batch_fast_generate(x[b:b + 1], torch.from_numpy(h[b:b + 1]), [n_list[b]], d[b:b + 1])
         # a solo call keys Philox with slot 0, the batch with the caller-side index b: compare through generate_device
