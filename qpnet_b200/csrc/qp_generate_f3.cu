@@ -62,9 +62,12 @@ constexpr int DW = 8;                                  // weight ring depth (chu
 constexpr int ABLK = UB * 128;                         // bytes of one K-block of an A tile (128 rows x 128 B)
 constexpr int NWARP = 19, NT = NWARP * 32;
 enum { K_G = 0, K_RK = 1, K_H = 2, K_WC = 3, K_WP = 4, NKIND = 5 };
-// trace events of CTA 0 (QPNET_GEN_TRACE_STEP): MMA thread 0 z tile seen, 1 gate MMAs committed; ET thread 0: 2 tile in
-// TMEM, 3 partial rows sent, 4 partial rows of the cluster arrived, 5 z published; PZ thread 0: 6 z polled and staged
-constexpr int TRACE_EVENTS = 8;
+// trace events of CTA 0 (QPNET_GEN_TRACE_STEP), per phase j.  MMA thread: 0 z tile seen, 1 gate MMAs committed, 7 [R;K]
+// and H issued (waiting for the x tile), 8 x tile seen, 9 past-tap tile seen, 10 phase issued.  ET thread 0: 2 tile in TMEM,
+// 3 partial rows sent, 4 partial rows of the cluster arrived, 5 z published.  PZ thread 0: 11 z buffer free, 12 first
+// piece fresh, 6 z staged.  EU thread 0: 13 U tile in TMEM, 14 sent, 15 arrived, 16 x published.  PX thread 0: 17 past-tap
+// buffer free, 18 past taps staged, 19 x buffer free, 20 first x piece fresh, 21 x staged
+constexpr int TRACE_EVENTS = 24;
 
 // shared memory map (bytes from a 1024-byte aligned base)
 constexpr int SM_Z = 0, SM_X = SM_Z + 2 * ABLK, SM_XP = SM_X + 2 * ABLK, SM_W = SM_XP + 2 * ABLK;
@@ -107,6 +110,7 @@ struct Plan {
   int16_t* pcm_lut;       // [Q] decode_mu_law(symbol) * 32768 clipped to int16 (qpnet_decode.py:315-318)
   void* tagged_begin; size_t tagged_bytes;
   long long* trace; int trace_step0, trace_nsteps;
+  int poll_all;           // (tuning) 1: no first-piece wait, poll every piece from the start
 };
 
 static int log2_above(int v) { int q = 0; while ((1 << q) <= v) ++q; return q; }
@@ -154,6 +158,7 @@ size_t make_plan(const QpArch* a, int B, int F, int M, void* base, size_t cap, P
   p->tagged_bytes = ar.off - t0;
   p->trace = ar.take<long long>((size_t)8 * (L + 4) * TRACE_EVENTS);
   p->trace_step0 = -1000000; p->trace_nsteps = 8;
+  p->poll_all = 0;
   return align_up(ar.off, 256);
 }
 
@@ -484,15 +489,16 @@ __global__ void __launch_bounds__(NT, 1) f3_gen_kernel(Plan p, GenArgsDev g) {
   // Poll this thread's pieces i < nl of a tagged vector (piece i at src + i * sstep) and stage them at dst + i * dstep.
   // Waiting is light: the thread spins on its FIRST piece only (the chip-wide polling traffic must stay far below the
   // L2 bandwidth the weight and activation tiles need), then loads all of them and re-checks every tag.
-  auto poll_tile = [&](auto nconst, const uint4* src, size_t sstep, int nl, unsigned tag, unsigned char* dst, int dstep) {
+  auto poll_tile = [&](auto nconst, const uint4* src, size_t sstep, int nl, unsigned tag, unsigned char* dst, int dstep, int tr_t, int tr_ph, int tr_ev) {
     constexpr int N = decltype(nconst)::value;
     if (nl <= 0) return;
     unsigned spins = 0; long long t0 = 0;
-    while (true) {
+    while (!p.poll_all) {
       const uint4 a = ld_strong_v4(src);
       if (fresh4(a, tag)) break;
       spin_check(spins, t0);
     }
+    if (tr_ev >= 0) trace(tr_t, tr_ph, tr_ev);
     uint4 v[N];
     while (true) {
 #pragma unroll
@@ -735,6 +741,7 @@ __global__ void __launch_bounds__(NT, 1) f3_gen_kernel(Plan p, GenArgsDev g) {
         if (fin && t128 == 0) mbar_expect_tx(rbar, 4 * 32 * 48);
         mbar_wait(bar(B_UFULL + tb), (unsigned)(nU >> 1) & 1u);
         tc_fence_after();
+        trace(t, j, 13);
         if (w < nlive) {
           uint32_t v[32];
           tmem_ld32(trow + TC_U + 32 * tb, v);
@@ -755,9 +762,11 @@ __global__ void __launch_bounds__(NT, 1) f3_gen_kernel(Plan p, GenArgsDev g) {
           __syncwarp();
           if (lane == 0) mbar_arrive(bar(B_UFREE + tb));
         }
+        trace(t, j, 14);
         if (fin) {
           mbar_wait(rbar, (rupar >> rb3) & 1u);
           rupar ^= 1u << rb3;
+          trace(t, j, 15);
           const int l = j - 1;                              // block whose residual / skip projection this is
           const float* br = sBr + l * 32;
           float r0 = br[4 * q], r1 = br[4 * q + 1], r2 = br[4 * q + 2], r3 = br[4 * q + 3];
@@ -794,6 +803,7 @@ __global__ void __launch_bounds__(NT, 1) f3_gen_kernel(Plan p, GenArgsDev g) {
             if (q == 0 && live) st_strong_v4(p.v256 + (size_t)fu * (S / 2) + 4 * c, make_uint4(w0, w1, w2, w3));
           }
         }
+        trace(t, j, 16);
         ++nU;
       }
     }
@@ -812,8 +822,9 @@ __global__ void __launch_bounds__(NT, 1) f3_gen_kernel(Plan p, GenArgsDev g) {
         const int pc = i128 & 15, ub = i128 >> 4;
         const uint4* src = (const uint4*)(p.vz + ((size_t)(j - 1) * UB + ub) * (C / 2)) + rank * 16 + pc;
         unsigned char* dst = sZ + (pc >> 3) * ABLK + ub * 128 + (((pc & 7) ^ ub) << 4);
-        poll_tile(N16(), src, (size_t)8 * (C / 8), min(16, (B - ub + 7) >> 3), tagz, dst, 1024);
-        if (i128 == 0) trace(t, j, 6);
+        trace(t, j, 11);
+        poll_tile(N16(), src, (size_t)8 * (C / 8), min(16, (B - ub + 7) >> 3), tagz, dst, 1024, t, j, 12);
+        trace(t, j, 6);
         done();
       }
       if (t >= 0) {
@@ -824,7 +835,7 @@ __global__ void __launch_bounds__(NT, 1) f3_gen_kernel(Plan p, GenArgsDev g) {
           const int pc = i128 & 7, ub = i128 >> 3;
           const uint4* src = (const uint4*)(p.v256 + ((size_t)hd * UB + ub) * (S / 2)) + rank * 8 + pc;
           unsigned char* dst = sZ + (ub >> 3) * 1024 + (ub & 7) * 128 + ((pc ^ (ub & 7)) << 4);
-          poll_tile(N8(), src, (size_t)16 * (S / 8), min(8, (B - ub + 15) >> 4), par_t, dst, 2048);
+          poll_tile(N8(), src, (size_t)16 * (S / 8), min(8, (B - ub + 15) >> 4), par_t, dst, 2048, t, 0, -1);
           done();
         }
       }
@@ -839,6 +850,7 @@ __global__ void __launch_bounds__(NT, 1) f3_gen_kernel(Plan p, GenArgsDev g) {
     // past tap of block jb for step t: x_jb(t - k) of every utterance -> XP tile
     auto stage_xp = [&](int jb, int t) {
       if (nXP >= 1) mbar_wait(bar(B_XPFREE), (unsigned)(nXP - 1) & 1u);
+      trace(t, jb - 1, 17);
       unsigned char* dst = sm + SM_XP + tile_off;
       if (t == -NP) {   // the first priming pass has no ring contents yet
 #pragma unroll
@@ -873,6 +885,7 @@ __global__ void __launch_bounds__(NT, 1) f3_gen_kernel(Plan p, GenArgsDev g) {
             if (u0 + 8 * i < B) *(uint4*)(dst + (8 * hb + i) * 1024) = v[i];
         }
       }
+      trace(t, jb - 1, 18);
       fence_proxy_async();
       mbar_arrive(bar(B_XPFULL));
       ++nXP;
@@ -883,7 +896,9 @@ __global__ void __launch_bounds__(NT, 1) f3_gen_kernel(Plan p, GenArgsDev g) {
       unsigned char* dst = sm + SM_X + tile_off;
       const unsigned tag = x_tag(jx, t);
       const uint4* src0 = (const uint4*)(p.xr[jx] + (size_t)x_slot(jx, t) * UB * (C / 2)) + rank * 16 + pc;
-      poll_tile(N16(), src0 + (size_t)ub * (C / 8), (size_t)8 * (C / 8), min(16, (B - ub + 7) >> 3), tag, dst, 1024);
+      trace(t, jx + 1, 19);
+      poll_tile(N16(), src0 + (size_t)ub * (C / 8), (size_t)8 * (C / 8), min(16, (B - ub + 7) >> 3), tag, dst, 1024, t, jx + 1, 20);
+      trace(t, jx + 1, 21);
       fence_proxy_async();
       mbar_arrive(bar(B_XFULL));
       ++nX;
@@ -958,17 +973,21 @@ __global__ void __launch_bounds__(NT, 1) f3_gen_kernel(Plan p, GenArgsDev g) {
               mma8(TC_T + 32 * b, sZ, wv, true);
               wdone(); umma_commit(bar(B_ZFREE)); ++nZ; ++nTf;
             }
+            trace(t, j, 7);
             if (j >= 2) {   // += Wc_{j+1} x_{j-1}
               const uint32_t wv = wchunk();
               mbar_wait(bar(B_XFULL), (unsigned)nX & 1u);
+              trace(t, j, 8);
               mma8(TC_T + 32 * b, sX, wv, false);
               wdone(); umma_commit(bar(B_XFREE)); ++nX;
             }
             {   // += Wp_{j+1} x_{j+1}(t-k)
               const uint32_t wv = wchunk();
               mbar_wait(bar(B_XPFULL), (unsigned)nXP & 1u);
+              trace(t, j, 9);
               mma8(TC_T + 32 * b, sXP, wv, false);
               wdone(); umma_commit(bar(B_XPFREE)); ++nXP;
+              trace(t, j, 10);
             }
           } else {
             umma_commit(bar(B_ZFREE)); ++nZ;
@@ -1120,6 +1139,7 @@ int f3_generate(const QpArch* arch, const float* const* tensors_host, const QpGe
   QP_REQUIRE(smem <= 227 * 1024, "generate: %d bytes of shared memory needed", smem);
   const bool tr = getenv("QPNET_GEN_TRACE_STEP") != nullptr;
   if (tr) p.trace_step0 = atoi(getenv("QPNET_GEN_TRACE_STEP"));
+  if (const char* e = getenv("QPNET_F3_POLL_ALL")) p.poll_all = atoi(e);
   auto kern = tr ? f3::f3_gen_kernel<true> : f3::f3_gen_kernel<false>;
   QP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   cudaLaunchConfig_t cfg = {};

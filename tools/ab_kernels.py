@@ -1,7 +1,7 @@
 #!/usr/bin/env python3
 """A/B timing of the generator kernels on the bench workload shape (device-resident inputs, CUDA events).
 
-    python tools/ab_kernels.py [--utts 32] [--frames 200] [--kernels fold2,fold,cluster]
+    python tools/ab_kernels.py [--utts 32] [--frames 200] [--kernels f3,fold2]
 """
 import argparse
 import os
@@ -16,7 +16,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--utts", type=int, default=32)
     ap.add_argument("--frames", type=int, default=200)
-    ap.add_argument("--kernels", default="fold2,fold,cluster")
+    ap.add_argument("--kernels", default="f3,fold2")
     ap.add_argument("--reps", type=int, default=2)
     args = ap.parse_args()
     import bench
@@ -43,7 +43,7 @@ def main():
             t1.record()
             torch.cuda.synchronize()
             best = min(best, t0.elapsed_time(t1))
-        steps = max(n_list) + 1
+        steps = max(n_list) + 16
         tot = sum(n_list)
         same = "" if ref is None else f"  symbols equal to {args.kernels.split(',')[0]}: {float((out == ref).float().mean()):.4f}"
         if ref is None:

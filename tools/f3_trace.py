@@ -1,0 +1,95 @@
+#!/usr/bin/env python3
+"""Per-phase clock64 trace of CTA 0 of the tcgen05 generator (qp_generate_f3.cu, QPNET_GEN_TRACE_STEP).
+
+    python tools/f3_trace.py [--utts 128] [--frames 20] [--step 1000]
+
+Events per phase j (block j; phase L = final skip): 0 MMA thread sees the staged z_{j-1} tile, 1 gate MMAs committed,
+2 ET thread 0: tile complete in TMEM, 3 partial rows sent, 4 partial rows of the cluster arrived, 5 z_j published,
+6 PZ thread 0: z_{j-1} polled and staged.  Printed per phase: the critical chain
+    published(j-1) -> staged -> MMA issue -> tile in TMEM -> sent -> arrived -> published(j).
+"""
+import argparse
+import ctypes as C
+import os
+import sys
+
+import numpy as np
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--utts", type=int, default=128)
+    ap.add_argument("--frames", type=int, default=20)
+    ap.add_argument("--step", type=int, default=1000)
+    args = ap.parse_args()
+    os.environ["QPNET_GEN_TRACE_STEP"] = str(args.step)
+    os.environ["QPNET_GEN_KERNEL"] = "f3"
+    import bench
+    from qpnet_b200 import _lib, ops
+    from qpnet_b200.qpnet import QPNet, initialize
+    dev = torch.device("cuda:0")
+    torch.manual_seed(0)
+    m = QPNet()
+    m.apply(initialize)
+    m = m.to(dev)
+    L = len(m.dilationsF) + len(m.dilationsA)
+    h, f0, n_list = bench.build_inputs(args.utts, 0, args.frames)
+    d64, _ = ops.f0_to_dilated(torch.from_numpy(f0).to(dev), 22050, 8, 110, want_f32=False)
+    seed = torch.full((args.utts,), 128, dtype=torch.int64, device=dev)
+    n_dev = torch.tensor(n_list, dtype=torch.int32, device=dev)
+    hd = torch.from_numpy(h).to(dev)
+    for _ in range(2):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        m.generate_device(seed, hd, d64, n_dev, max(n_list), check_status=False)
+        e1.record()
+        torch.cuda.synchronize()
+        print(f"kernel ms {e0.elapsed_time(e1):.2f}  us/step {e0.elapsed_time(e1) * 1e3 / (max(n_list) + 16):.2f}")
+    nphase, nev = L + 4, 24
+    n = 8 * nphase * nev
+    buf = (C.c_longlong * n)()
+    fn = _lib.lib.qp_debug_gen_trace
+    fn.restype = C.c_int
+    fn.argtypes = [C.POINTER(_lib.QpArch), C.c_int32, C.c_int32, C.c_void_p, C.c_size_t, C.POINTER(C.c_longlong), C.c_int32, C.c_void_p]
+    ws = m._last_ws
+    fn(m._arch, args.utts, ops.max_ceil(d64), ws.data_ptr(), ws.numel(), buf, n, None)
+    tr = np.array(buf, dtype=np.int64).reshape(8, nphase, nev)
+    labels = ["pub(j-1)->staged", "staged->mma", "mma issue", "commit->TMEM seen", "ld+send", "send->arrived", "finish+publish"]
+    acc = np.zeros(7)
+    cnt = 0
+    for st in range(1, 7):
+        step_total = tr[st + 1, 0, 5] - tr[st, 0, 5]
+        if st <= 2:
+            print(f"--- step {args.step + st}: {step_total} cycles (block-0 publish to block-0 publish); block 0: symbols+tables {tr[st, 0, 5] - tr[st, 0, 2]}")
+        for j in range(1, L):
+            e, prev = tr[st, j], tr[st, j - 1]
+            d = [e[6] - prev[5], e[0] - e[6], e[1] - e[0], e[2] - e[1], e[3] - e[2], e[4] - e[3], e[5] - e[4]]
+            if st <= 2:
+                print(f"blk{j:02d} " + "  ".join(f"{lab} {int(v):5d}" for lab, v in zip(labels, d)) + f"  | phase {int(e[5] - prev[5]):5d}")
+            acc += d
+            cnt += 1
+        if st <= 2:
+            print(f"final+heads+sampling+block0: {tr[st + 1, 0, 5] - tr[st, L - 1, 5]} cycles")
+    # full timeline of two phases of one step, relative to the moment the MMA thread saw z_{j-1}
+    names = {0: "MMA z seen", 1: "MMA gate committed", 7: "MMA RK+H issued", 8: "MMA x tile seen", 9: "MMA past tile seen", 10: "MMA phase issued",
+             2: "ET tile in TMEM", 3: "ET sent", 4: "ET arrived", 5: "ET z published", 11: "PZ z buffer free", 12: "PZ first piece fresh", 6: "PZ z staged",
+             13: "EU tile in TMEM", 14: "EU sent", 15: "EU arrived", 16: "EU x published", 17: "PX past buffer free", 18: "PX past staged",
+             19: "PX x buffer free", 20: "PX first x piece fresh", 21: "PX x staged"}
+    for j in (5, 6, 13):
+        e = tr[2, j]
+        base = e[0]
+        print(f"--- timeline of phase {j} (step {args.step + 2}), cycles relative to 'MMA z seen':")
+        for ev, tstamp in sorted(((k, int(e[k])) for k in names if e[k] != 0), key=lambda kv: kv[1]):
+            print(f"    {tstamp - base:8d}  {names[ev]}")
+    acc /= cnt
+    print("mean over blocks 1..L-1 of 6 steps: " + "  ".join(f"{lab} {v:.0f}" for lab, v in zip(labels, acc)) + f"  | phase {acc.sum():.0f}")
+    tot = np.mean([tr[st + 1, 0, 5] - tr[st, 0, 5] for st in range(1, 7)])
+    tail = np.mean([tr[st + 1, 0, 5] - tr[st, L - 1, 5] for st in range(1, 7)])
+    print(f"step total (mean) {tot:.0f} cycles; after the last gate (final skip, heads, sampling, block 0): {tail:.0f}")
+
+
+if __name__ == "__main__":
+    main()
