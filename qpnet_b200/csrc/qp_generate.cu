@@ -807,13 +807,15 @@ bool f3_supported(const QpArch* arch, int B);
 int f3_trace_copy(const QpArch* arch, int B, int M, void* ws, size_t ws_bytes, long long* out_host, int n, cudaStream_t st);
 int pcm16_rows(const int32_t* sym, long long ld, int B, int n_steps, int n_quantize, int16_t* out, long long ld_out, cudaStream_t st);   // qp_util.cu
 static thread_local int g_last_kernel = 0;   // 4: tcgen05 folded (f3), 3: two-level folded mma.sync (fold2), 0: generic
-// QPNET_GEN_KERNEL = f3 | fold2 | generic selects the generator (debugging / A-B timing); default: f3 where supported,
-// then fold2, then the generic kernel
+// QPNET_GEN_KERNEL = f3 | fold2 | generic selects the generator (debugging / A-B timing).  Default: the mma.sync kernel
+// up to 32 utterances (44 us per sample step), the tcgen05 kernel above (86 us at 32, 123 us at 128 utterances:
+// profiles/r02e_*), the generic kernel for everything else
 static int wanted_kernel(const QpArch* arch, int B) {
   const char* e = getenv("QPNET_GEN_KERNEL");
-  int want = 4;
+  int want = (B <= 32 && f2_supported(arch, B)) ? 3 : 4;
   if (e && strcmp(e, "generic") == 0) want = 0;
   else if (e && strcmp(e, "fold2") == 0) want = 3;
+  else if (e && strcmp(e, "f3") == 0) want = 4;
   if (want == 4 && !f3_supported(arch, B)) want = 3;
   if (want == 3 && !f2_supported(arch, B)) want = 0;
   return want;

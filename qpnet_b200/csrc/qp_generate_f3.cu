@@ -12,13 +12,15 @@
 // * 128 CTAs = 32 clusters of 4, one CTA per SM.  Cluster c owns residual channels [16c, 16c+16) of every block (32 gate
 //   rows, 16 residual rows, 8 skip rows, 8 rows of each head layer); rank r of a cluster contracts over the K-share
 //   [128r, 128r+128) of every 512-vector ([64r, 64r+64) of the 256-vectors of the head).
-// * Every product that feeds the pre-activation of block j accumulates into ONE TMEM tile T_j:
-//       T_j  = Wp_j x_j(t-k) + Wc_j x_{j-2}(t) + H_j z_{j-2}(t)     issued one phase early, off the critical path
-//            + G_j z_{j-1}(t)                                        the only product that waits for this phase's exchange
-//   so a phase has one cluster reduction on its critical path: TMEM -> registers -> fp16 partial rows -> st.async to the
-//   rank that FINISHES those utterances (rank q finishes utterances [32q, 32q+32) of the cluster's rows) -> sum of the
-//   four partial tiles + bias + aux + tables -> z_j = sigmoid * tanh -> published.  U_j = [R ; K]_{j-1} z_{j-1} (residual
-//   and skip rows) goes the same way through its own warps and publishes x_j one phase later.
+// * The pre-activation of block j is the sum of two TMEM tiles:
+//       P_j  = H_j z_{j-2}(t) + Wc_j x_{j-2}(t) + Wp_j x_j(t-k)     built one phase early, off the critical path
+//       C_j  = G_j z_{j-1}(t)                                        the only product that waits for this phase's exchange
+//   and every product of a phase that contracts z_{j-1} is ONE UMMA sequence of N = 96 rows, [G_j ; [R ; K]_{j-1} ;
+//   H_{j+1}] -> [C_j | U_j | P_{j+1}] (96 TMEM columns, two buffers by phase parity; 8 instructions instead of 24).
+//   A phase has one cluster reduction on its critical path: TMEM -> registers (C_j + P_j) -> fp16 partial rows ->
+//   st.async to the rank that FINISHES those utterances (rank q finishes utterances [32q, 32q+32) of the cluster's rows)
+//   -> sum of the four partial tiles + bias + aux + tables -> z_j = sigmoid * tanh -> published.  U_j = [R ; K]_{j-1}
+//   z_{j-1} (residual and skip rows) goes the same way through its own warps and publishes x_j.
 // * Past taps (the reference's FIFOs, qpnet.py:388-393, 431-437): x_j(t) is published into a ring xr[j][t mod R_j] of
 //   bf16 vectors that serves BOTH as the exchange buffer of the current step and, k steps later, as the past tap
 //   x_j(t-k) (k = dil for fixed blocks, -round(-d[t] * dil) for adaptive ones with the reference's rounding,
@@ -28,14 +30,17 @@
 //   (qpnet.py:143-158), so V h_up = w[t % U] (V h_f) + b (V 1).  (V h_f) is recomputed in fp32 once per frame by the
 //   finishing threads, b (V 1) is folded into the bias.  Block 0 reads the causal layer, a function of the last three
 //   symbols: three table lookups and no exchange at all; blocks 1 and 2 reach x_0 through two more tables.
-// * Exchange words carry a 1-bit epoch tag (LSB of the low bf16 / of the fp32 logit) and consumers poll the data itself.
+// * Exchange words carry a 1-bit epoch tag (LSB of the low bf16 / of the fp32 logit), so a consumer never needs a fence: it
+//   polls the data itself and verifies the tags of what it loaded.  (QPNET_F3_POLL_ALL selects a flag-then-load variant,
+//   where a consumer first spins on the step counters its four producer CTAs write after their pieces: less polling
+//   traffic, one more round trip; measured slower, profiles/r02g_*.)
 // * Warp roles (19 warps, no CTA-wide barrier inside the time loop; everything meets through mbarriers):
 //     0-3   ET   T tiles: tcgen05.ld -> partial rows -> finishers of z_j, the two head layers
 //     4-7   EU   U tiles: partial rows -> fp32 residual / skip state, x_j and relu(skip sum) published
 //     8-11  PZ   poll z_{j-1} (and the head's 256-vectors) -> A tile
-//     12-15 PX   poll x_{j-1} -> A tile; gather the past taps x_{j+1}(t-k) -> A tile
+//     12-15 PX   poll x_{j-1} -> A tile; gather the past taps x_{j+1}(t-k) -> A tile (cp.async, completion on an mbarrier)
 //     16    MMA  one thread issues every tcgen05.mma and releases buffers with tcgen05.commit
-//     17    LOAD one thread streams the 8 KB weight chunks (cp.async.bulk, 8-deep ring, L2 evict_last)
+//     17    LOAD one thread streams the weight chunks of the next phase (cp.async.bulk, two slot groups, L2 evict_last)
 //     18    SAMP softmax + inverse-CDF / arg-max of utterance blockIdx.x (qpnet.py:507-512), symbol fed back
 //
 // Priming (qpnet.py:355-440): the pad region is constant in time; the constant is found by running the step NP >= L
@@ -57,43 +62,47 @@ constexpr int KS = C / CL;                    // 128: K-share of a 512-vector
 constexpr int KH = S / CL;                    // 64: K-share of a 256-vector
 constexpr int MAXL = QP_MAX_LAYERS;
 constexpr int WCH_E = 32 * KS, WCH_B = WCH_E * 2;     // weight chunk: 32 rows x 128 K, two 4 KB K-blocks
+constexpr int ZPC_E = 96 * KS, ZPC_B = ZPC_E * 2;     // z-product chunk [G ; [R;K] ; H]: 96 rows x 128 K, two 12 KB K-blocks
 constexpr int HCH_E = 16 * KH, HCH_B = HCH_E * 2;     // head chunk: 16 rows (8 live) x 64 K
-constexpr int DW = 8;                                  // weight ring depth (chunks)
+constexpr int WGRP_B = ZPC_B + 2 * WCH_B;             // weight slot group of one phase: [z-product chunk | Wc | Wp]
 constexpr int ABLK = UB * 128;                         // bytes of one K-block of an A tile (128 rows x 128 B)
 constexpr int NWARP = 19, NT = NWARP * 32;
-enum { K_G = 0, K_RK = 1, K_H = 2, K_WC = 3, K_WP = 4, NKIND = 5 };
-// trace events of CTA 0 (QPNET_GEN_TRACE_STEP), per phase j.  MMA thread: 0 z tile seen, 1 gate MMAs committed, 7 [R;K]
-// and H issued (waiting for the x tile), 8 x tile seen, 9 past-tap tile seen, 10 phase issued.  ET thread 0: 2 tile in TMEM,
-// 3 partial rows sent, 4 partial rows of the cluster arrived, 5 z published.  PZ thread 0: 11 z buffer free, 12 first
-// piece fresh, 6 z staged.  EU thread 0: 13 U tile in TMEM, 14 sent, 15 arrived, 16 x published.  PX thread 0: 17 past-tap
-// buffer free, 18 past taps staged, 19 x buffer free, 20 first x piece fresh, 21 x staged
+constexpr int MAXA = 8;                                // adaptive blocks (look-back table in shared memory)
+// trace events of CTA 0 (QPNET_GEN_TRACE_STEP), per phase j.  MMA thread: 0 z tile seen, 1 z-products committed, 8 x tile
+// seen, 9 past-tap tile seen, 10 phase issued.  ET thread 0: 2 tiles in TMEM, 3 partial rows sent, 4 partial rows of the
+// cluster arrived, 5 z published.  PZ thread 0: 11 z buffer free, 12 first piece fresh, 6 z staged.  EU thread 0: 13 U tile
+// in TMEM, 14 sent, 15 arrived, 16 x published.  PX thread 0: 17 past-tap buffer free, 18 past-tap copies issued, 19 x buffer
+// free, 20 first x piece fresh, 21 x staged
 constexpr int TRACE_EVENTS = 24;
 
 // shared memory map (bytes from a 1024-byte aligned base)
 constexpr int SM_Z = 0, SM_X = SM_Z + 2 * ABLK, SM_XP = SM_X + 2 * ABLK, SM_W = SM_XP + 2 * ABLK;
-constexpr int SM_WH = SM_W + DW * WCH_B;
+constexpr int SM_WH = SM_W + 2 * WGRP_B;
 constexpr int SM_RT = SM_WH + 2 * HCH_B;               // recvT [2][4 src][32 utt][64 B]
 constexpr int SM_RU = SM_RT + 2 * 4 * 32 * 64;         // recvU [3][4][32][48 B]
 constexpr int SM_RH = SM_RU + 3 * 4 * 32 * 48;         // recvH [2][4][32][16 B]
-constexpr int SM_BAR = SM_RH + 2 * 4 * 32 * 16;        // 48 mbarriers
+constexpr int SM_K = SM_RH + 2 * 4 * 32 * 16;          // look-backs of this step [MAXA][UB] uint16
+constexpr int SM_BAR = SM_K + MAXA * UB * 2;           // 48 mbarriers
 constexpr int SM_TMEM = SM_BAR + 48 * 8;
 constexpr int SM_BH = SM_TMEM + 16;                    // head biases [2][8]
-constexpr int SM_BG = SM_BH + 64;                      // gate biases [L][32], then res / skip biases [L][32]
-// mbarrier indices
-constexpr int B_WFULL = 0, B_WFREE = B_WFULL + DW, B_ZFULL = B_WFREE + DW, B_ZFREE = B_ZFULL + 1, B_XFULL = B_ZFREE + 1,
-              B_XFREE = B_XFULL + 1, B_XPFULL = B_XFREE + 1, B_XPFREE = B_XPFULL + 1, B_TFULL = B_XPFREE + 1,
-              B_TFREE = B_TFULL + 2, B_UFULL = B_TFREE + 2, B_UFREE = B_UFULL + 2, B_HFULL = B_UFREE + 2,
-              B_RT = B_HFULL + 2, B_RU = B_RT + 2, B_RH = B_RU + 3, B_COUNT = B_RH + 2;
+constexpr int SM_END = SM_BH + 64;
+static_assert(SM_END + 1024 <= 227 * 1024, "shared memory budget");
+// mbarrier indices ([2] = slot group / TMEM buffer by phase parity)
+constexpr int B_ZPW_FULL = 0, B_ZPW_FREE = 2, B_WCW_FULL = 4, B_WCW_FREE = 6, B_WPW_FULL = 8, B_WPW_FREE = 10,
+              B_ZFULL = 12, B_ZFREE = 13, B_XFULL = 14, B_XFREE = 15, B_XPFULL = 16, B_XPFREE = 17,
+              B_CFULL = 18, B_UFULL = 20, B_PFULL = 22, B_CFREE = 24, B_UFREE = 26, B_PFREE = 28, B_HFULL = 30,
+              B_RT = 32, B_RU = 34, B_RH = 37, B_COUNT = 39;
 static_assert(B_COUNT <= 48, "mbarrier area");
-constexpr int TM_COLS = 256;                           // TMEM columns: T[2] 32 each, U[2] 32 each, head[2] 16 each
-constexpr int TC_T = 0, TC_U = 64, TC_H = 128;
+constexpr int TM_COLS = 256;                           // TMEM columns: buffer b at 96 b: [C | U | P] 32 each; head at 192
+constexpr int TC_C = 0, TC_U = 32, TC_P = 64, TC_BUF = 96, TC_H = 192;
 
 struct Plan {
   int A, L, nF, nA, U, B, F, M, NP;
   int dil[MAXL], depth[MAXL], rlog[MAXL];      // ring of block l: 1 << rlog[l] slots (l >= 1)
   int32_t* status;
   const float** tab;
-  __nv_bfloat16* W;       // [NKIND][L][NCTA][WCH_E]  pre-swizzled chunks (layout in pack_kernel)
+  __nv_bfloat16* Wzp;     // [L phases 1..L][NCTA][ZPC_E]  pre-swizzled z-product chunks (layout in pack_kernel)
+  __nv_bfloat16* Wcp;     // [2: Wc, Wp][L][NCTA][WCH_E]
   __nv_bfloat16* Whead;   // [2][NCTA][HCH_E]
   float* bgate;           // [L][NCL][32]
   float* bres;            // [L][NCL][32]   rows 0-15 residual, 16-23 skip
@@ -107,10 +116,15 @@ struct Plan {
   uint32_t* v256;         // [2][UB][S / 2]   0: relu(skip sum), 1: relu(head-1)
   uint32_t* vlog;         // [UB][Q]  fp32 logits
   uint32_t* vsym;         // [UB][32] fed-back symbol, one line per utterance
+  uint32_t* flagz;        // [L][NCTA]  step counter of the z_l pieces CTA s has published (readiness hint; the data carries the tag)
+  uint32_t* flagx;        // [L][NCTA]  same for x_l
+  uint32_t* flagh;        // [2][NCTA]  same for the two 256-vectors of the head
   int16_t* pcm_lut;       // [Q] decode_mu_law(symbol) * 32768 clipped to int16 (qpnet_decode.py:315-318)
   void* tagged_begin; size_t tagged_bytes;
   long long* trace; int trace_step0, trace_nsteps;
-  int poll_all;           // (tuning) 1: no first-piece wait, poll every piece from the start
+  long long* gtrace;      // [NCTA][L + 4][4] %globaltimer of one step, every CTA: 0 z published, 1 z staged, 2 partial rows arrived, 3 x published
+  int poll_all;           // (tuning) bit 0 / bit 1: poll the z / x pieces themselves from the start instead of waiting for the producers' flags
+  int backoff_ns;         // (tuning) sleep between two polling rounds
 };
 
 static int log2_above(int v) { int q = 0; while ((1 << q) <= v) ++q; return q; }
@@ -118,7 +132,7 @@ static int log2_above(int v) { int q = 0; while ((1 << q) <= v) ++q; return q; }
 bool supported(const QpArch* a, int B) {
   if (a->n_resch != C || a->n_skipch != S || a->n_quantize != Q || a->n_aux > 64 || a->n_aux < 1) return false;
   const int L = a->n_fixed + a->n_adaptive;
-  if (L > MAXL || L < 4 || a->n_fixed < 1 || a->dil_fixed[0] != 1) return false;
+  if (L > MAXL || L < 4 || a->n_fixed < 1 || a->dil_fixed[0] != 1 || a->n_adaptive > MAXA) return false;
   return B >= 1 && B <= UB;
 }
 
@@ -130,7 +144,8 @@ size_t make_plan(const QpArch* a, int B, int F, int M, void* base, size_t cap, P
   Arena ar(base, cap);
   p->status = ar.take<int32_t>(64);
   p->tab = ar.take<const float*>(tensor_map(a).count());
-  p->W = ar.take<__nv_bfloat16>((size_t)NKIND * L * NCTA * WCH_E);
+  p->Wzp = ar.take<__nv_bfloat16>((size_t)L * NCTA * ZPC_E);
+  p->Wcp = ar.take<__nv_bfloat16>((size_t)2 * L * NCTA * WCH_E);
   p->Whead = ar.take<__nv_bfloat16>((size_t)2 * NCTA * HCH_E);
   p->bgate = ar.take<float>((size_t)L * NCL * 32);
   p->bres = ar.take<float>((size_t)L * NCL * 32);
@@ -153,12 +168,17 @@ size_t make_plan(const QpArch* a, int B, int F, int M, void* base, size_t cap, P
   p->v256 = ar.take<uint32_t>((size_t)2 * UB * (S / 2));
   p->vlog = ar.take<uint32_t>((size_t)UB * Q);
   p->vsym = ar.take<uint32_t>((size_t)UB * 32);
+  p->flagz = ar.take<uint32_t>((size_t)L * NCTA);
+  p->flagx = ar.take<uint32_t>((size_t)L * NCTA);
+  p->flagh = ar.take<uint32_t>((size_t)2 * NCTA);
   ar.off = align_up(ar.off, 256);
   p->tagged_begin = base ? (char*)base + t0 : nullptr;
   p->tagged_bytes = ar.off - t0;
   p->trace = ar.take<long long>((size_t)8 * (L + 4) * TRACE_EVENTS);
+  p->gtrace = ar.take<long long>((size_t)NCTA * (L + 4) * 4);
   p->trace_step0 = -1000000; p->trace_nsteps = 8;
-  p->poll_all = 0;
+  p->poll_all = 3;     // measured (profiles/r02g_*): polling the pieces themselves beats flag-then-load at 32 and at 128 utterances
+  p->backoff_ns = 0;
   return align_up(ar.off, 256);
 }
 
@@ -178,46 +198,45 @@ __device__ __forceinline__ float wp_elem(const TensorMap& tm, const float* const
   return gl < nF ? tab[tm.dilF_w(g, gl)][((size_t)ch * C + col) * 2 + 0] : tab[tm.dilA_wP(g, gl - nF)][(size_t)ch * C + col];
 }
 
-// Chunks [kind][layer][CTA s = 4c + r][32 rows x 128 K]: column k is input channel 128 r + k.
-//   K_RK layer l : rows 0-15 R_l row 16c + row (zero for the dead last projection, C7), rows 16-23 K_l row 8c + row - 16
-//   K_WC layer j : Wc_j gate rows (current tap; j >= 3, blocks 1 and 2 reach x_0 through tables)
-//   K_WP layer j : Wp_j gate rows (past tap; j >= 1)
-//   K_G / K_H    : fold_kernel
-// plus head tiles, biases and the causal-layer table.  Every element that is ever loaded is written here.
+// Weight chunks of CTA s = 4c + r; column k of a chunk is input channel 128 r + k.
+//   Wzp[phase j-1][s] (96 rows): rows 0-31  G_j gate rows (fold_kernel; j <= L-1)
+//                                rows 32-47 R_{j-1} row 16c + row - 32 (zero for the dead last projection, C7)
+//                                rows 48-55 K_{j-1} row 8c + row - 48, rows 56-63 zero
+//                                rows 64-95 H_{j+1} gate rows (fold_kernel; j + 1 <= L-1)
+//   Wcp[0][j][s] (32 rows): Wc_j gate rows (current tap; j >= 3, blocks 1 and 2 reach x_0 through tables)
+//   Wcp[1][j][s] (32 rows): Wp_j gate rows (past tap; j >= 1)
+// plus head tiles, biases and the causal-layer table.  Wzp is zeroed before this kernel; every other element that is ever
+// loaded is written here.
 __global__ void pack_kernel(TensorMap tm, Plan p, const float* const* __restrict__ tab) {
   const int L = p.L, A = p.A, nF = p.nF;
   const size_t n_ch = (size_t)L * NCTA * WCH_E;              // per kind
-  const size_t n_w = 3 * n_ch;                               // K_RK, K_WC, K_WP
+  const size_t n_w = 3 * n_ch;                               // [R;K], Wc, Wp
   const size_t n_wh = (size_t)2 * NCTA * HCH_E, n_b = (size_t)L * NCL * 32, n_bh = (size_t)2 * NCL * 8, n_eo = (size_t)NCL * 2 * Q * 16;
   const size_t total = n_w + n_wh + 2 * n_b + n_bh + n_eo;
   const float up_b = tab[tm.up_b()][0];
   for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
     size_t k = idx;
     if (k < n_w) {
-      const int which = (int)(k / n_ch);                      // 0 RK, 1 WC, 2 WP
+      const int which = (int)(k / n_ch);                      // 0 [R;K], 1 Wc, 2 Wp
       size_t q = k % n_ch;
       const int kk = (int)(q % KS); q /= KS;
       const int row = (int)(q % 32); q /= 32;
       const int s = (int)(q % NCTA), l = (int)(q / NCTA);
       const int c = s / CL, r = s % CL, col = KS * r + kk;
       float v = 0.f;
-      int kind;
       if (which == 0) {
-        kind = K_RK;
         if (row < 16) {
           if (l < L - 1) v = l < nF ? tab[tm.resF_w(l)][(size_t)(16 * c + row) * C + col] : tab[tm.resA_w(l - nF)][(size_t)(16 * c + row) * C + col];
         } else if (row < 24) {
           const int sr = 8 * c + row - 16;
           v = l < nF ? tab[tm.skipF_w(l)][(size_t)sr * C + col] : tab[tm.skipA_w(l - nF)][(size_t)sr * C + col];
         }
-      } else if (which == 1) {
-        kind = K_WC;
-        if (l >= 1) v = wc_elem(tm, tab, nF, l, row & 1, 16 * c + (row >> 1), col);
+        p.Wzp[((size_t)l * NCTA + s) * ZPC_E + sw128_elem(32 + row, kk, 96 * 64)] = __float2bfloat16(v);   // phase l + 1
       } else {
-        kind = K_WP;
-        if (l >= 1) v = wp_elem(tm, tab, nF, l, row & 1, 16 * c + (row >> 1), col);
+        if (l >= 1) v = which == 1 ? wc_elem(tm, tab, nF, l, row & 1, 16 * c + (row >> 1), col)
+                                   : wp_elem(tm, tab, nF, l, row & 1, 16 * c + (row >> 1), col);
+        p.Wcp[(((size_t)(which - 1) * L + l) * NCTA + s) * WCH_E + sw128_elem(row, kk, 32 * 64)] = __float2bfloat16(v);
       }
-      p.W[(((size_t)kind * L + l) * NCTA + s) * WCH_E + sw128_elem(row, kk, 32 * 64)] = __float2bfloat16(v);
       continue;
     }
     k -= n_w;
@@ -283,13 +302,13 @@ __global__ void pack_kernel(TensorMap tm, Plan p, const float* const* __restrict
 }
 
 // Folded products for 8 gate rows of a cluster (fp32 accumulate, rounded to bf16 once).  grid (NCL * 4, L, 2):
-//   z = 0: gate block gl = blockIdx.y:  G_gl = Wc_gl R_{gl-1}   (gl >= 1)
-//   z = 1:                              H_gl = Wc_gl R_{gl-2}   (gl >= 2)
+//   z = 0: gate block gl = blockIdx.y:  G_gl = Wc_gl R_{gl-1}   (gl >= 1)  -> rows 0-31 of the z-product chunk of phase gl
+//   z = 1:                              H_gl = Wc_gl R_{gl-2}   (gl >= 2)  -> rows 64-95 of the chunk of phase gl - 1
 // and the bias terms Wc_gl . r_{gl-1} / Wc_gl . r_{gl-2}.  Runs after pack_kernel on the same stream (it adds to bgate).
 __global__ void __launch_bounds__(256) fold_kernel(TensorMap tm, Plan p, const float* const* __restrict__ tab) {
   __shared__ float sWc[8][C];
   const int c = blockIdx.x >> 2, rg = blockIdx.x & 3, gl = blockIdx.y, which = blockIdx.z, tid = threadIdx.x;
-  const int L = p.L, nF = p.nF;
+  const int nF = p.nF;
   const int rl = gl - 1 - which;                    // residual projection folded in
   if (rl < 0) return;                               // G_0, H_0, H_1 do not exist (never loaded)
   for (int e = tid; e < 8 * C; e += 256) {
@@ -310,14 +329,15 @@ __global__ void __launch_bounds__(256) fold_kernel(TensorMap tm, Plan p, const f
       acc[j8][1] = fmaf(w, r1, acc[j8][1]);
     }
   }
-  const int kind = which == 0 ? K_G : K_H;
+  // G_gl is rows 0-31 of the chunk of phase gl, H_gl rows 64-95 of the chunk of phase gl - 1
+  const int ph = which == 0 ? gl - 1 : gl - 2, row0 = which == 0 ? 0 : 64;
 #pragma unroll
   for (int hh = 0; hh < 2; ++hh) {
     const int col = tid + 256 * hh;
     const int s = c * CL + col / KS, kk = col % KS;
-    __nv_bfloat16* dst = p.W + (((size_t)kind * L + gl) * NCTA + s) * WCH_E;
+    __nv_bfloat16* dst = p.Wzp + ((size_t)ph * NCTA + s) * ZPC_E;
 #pragma unroll
-    for (int j8 = 0; j8 < 8; ++j8) dst[sw128_elem(8 * rg + j8, kk, 32 * 64)] = __float2bfloat16(acc[j8][hh]);
+    for (int j8 = 0; j8 < 8; ++j8) dst[sw128_elem(row0 + 8 * rg + j8, kk, 96 * 64)] = __float2bfloat16(acc[j8][hh]);
   }
   if (tid < 8) {
     const float* rb = rl < nF ? tab[tm.resF_b(rl)] : tab[tm.resA_b(rl - nF)];
@@ -418,6 +438,27 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&r)[8]) {
 }
 __device__ __forceinline__ float4 ldcg4(const float* p) { return __ldcg((const float4*)p); }
 
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr) : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+}
+// the mbarrier receives one (pre-counted) arrival once every cp.async this thread has issued so far has landed
+__device__ __forceinline__ void cp_async_arrive_noinc(uint32_t bar) {
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];\n" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void cp_async16_s(uint32_t dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(dst), "l"(src) : "memory");
+}
+// wait parities, one bit per mbarrier of the role; "free" barriers start at 1 (the phase before the first one counts as
+// complete, so the first wait of a producer passes)
+constexpr unsigned long long FREE_BITS =
+    (3ull << B_ZPW_FREE) | (3ull << B_WCW_FREE) | (3ull << B_WPW_FREE) | (1ull << B_ZFREE) | (1ull << B_XFREE) | (1ull << B_XPFREE) |
+    (3ull << B_CFREE) | (3ull << B_UFREE) | (3ull << B_PFREE);
+
 template <bool TRACE>
 __global__ void __launch_bounds__(NT, 1) f3_gen_kernel(Plan p, GenArgsDev g) {
   extern __shared__ unsigned char smem_raw[];
@@ -430,26 +471,22 @@ __global__ void __launch_bounds__(NT, 1) f3_gen_kernel(Plan p, GenArgsDev g) {
   const int rank = (int)cluster_rank();                       // == s % CL
   const int nlive = (B + 31) >> 5;                            // ranks that finish at least one live utterance
   const int half = Q / 2;
+  const bool use_flags = p.poll_all != 3;                     // producers publish step counters only when a consumer waits for them
   float* const sBh = (float*)(sm + SM_BH);
-  float* const sBg = (float*)(sm + SM_BG);
-  float* const sBr = sBg + L * 32;
+  unsigned short* const sK = (unsigned short*)(sm + SM_K);
   auto bar = [&](int i) -> uint32_t { return sbase + SM_BAR + 8 * i; };
 
   // ---- one-time staging ---------------------------------------------------------------
-  for (int e = tid; e < (SM_BG + L * 256) / 16; e += NT) ((uint4*)sm)[e] = make_uint4(0, 0, 0, 0);
+  for (int e = tid; e < SM_END / 16; e += NT) ((uint4*)sm)[e] = make_uint4(0, 0, 0, 0);
   __syncthreads();
   for (int e = tid; e < 2 * HCH_E / 8; e += NT)               // both head tiles stay resident
     ((uint4*)(sm + SM_WH))[e] = ((const uint4*)(p.Whead + ((size_t)(e / (HCH_E / 8)) * NCTA + s) * HCH_E))[e % (HCH_E / 8)];
-  for (int e = tid; e < L * 32; e += NT) {
-    sBg[e] = p.bgate[((size_t)(e >> 5) * NCL + c) * 32 + (e & 31)];
-    sBr[e] = p.bres[((size_t)(e >> 5) * NCL + c) * 32 + (e & 31)];
-  }
   if (tid < 16) sBh[tid] = p.bhead[((size_t)(tid >> 3) * NCL + c) * 8 + (tid & 7)];
   if (tid == 0) {
     for (int i = 0; i < B_COUNT; ++i) {
       unsigned cnt = 1;
       if (i == B_ZFULL || i == B_XFULL || i == B_XPFULL) cnt = 128;
-      else if ((i >= B_TFREE && i < B_TFREE + 2) || (i >= B_UFREE && i < B_UFREE + 2)) cnt = 4;
+      else if (i >= B_CFREE && i < B_PFREE + 2) cnt = 4;
       mbar_init(bar(i), cnt);
     }
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
@@ -469,6 +506,13 @@ __global__ void __launch_bounds__(NT, 1) f3_gen_kernel(Plan p, GenArgsDev g) {
     if (TRACE && s == 0 && (tid & 127) == 0 && t >= p.trace_step0 && t < p.trace_step0 + p.trace_nsteps)
       p.trace[((size_t)(t - p.trace_step0) * (L + 4) + phase) * TRACE_EVENTS + ev] = clock64();
   };
+  auto gtrace = [&](int t, int phase, int ev) {   // the same step on every CTA, on the global clock
+    if (TRACE && (tid & 127) == 0 && t == p.trace_step0 + 2) {
+      unsigned long long ns;
+      asm volatile("mov.u64 %0, %%globaltimer;\n" : "=l"(ns));
+      p.gtrace[((size_t)s * (L + 4) + phase) * 4 + ev] = (long long)ns;
+    }
+  };
   // the watchdog: a word or barrier that never arrives is a bug, not a schedule; record it and stop the grid
   auto spin_check = [&](unsigned& spins, long long& t0) {
     if ((++spins & 1023u) != 0) return;
@@ -479,23 +523,28 @@ __global__ void __launch_bounds__(NT, 1) f3_gen_kernel(Plan p, GenArgsDev g) {
       __trap();
     }
   };
-  auto mbar_wait = [&](uint32_t b, unsigned parity) {
+  unsigned long long par = FREE_BITS;                         // this thread's wait parities
+  auto waitb = [&](int i) {
+    const uint32_t b = bar(i);
+    const unsigned parity = (unsigned)(par >> i) & 1u;
     unsigned spins = 0; long long t0 = 0;
     while (!mbar_try(b, parity)) spin_check(spins, t0);
+    par ^= 1ull << i;
   };
   // slot and tag of x_l at step t (real steps: ring position; priming passes: slot 0, pass parity)
   auto x_slot = [&](int l, int t) -> int { return t < 0 ? 0 : (t & ((1 << p.rlog[l]) - 1)); };
   auto x_tag = [&](int l, int t) -> unsigned { return t < 0 ? ((unsigned)(t + NP) & 1u) : ((unsigned)(t >> p.rlog[l]) & 1u); };
-  // Poll this thread's pieces i < nl of a tagged vector (piece i at src + i * sstep) and stage them at dst + i * dstep.
-  // Waiting is light: the thread spins on its FIRST piece only (the chip-wide polling traffic must stay far below the
-  // L2 bandwidth the weight and activation tiles need), then loads all of them and re-checks every tag.
-  auto poll_tile = [&](auto nconst, const uint4* src, size_t sstep, int nl, unsigned tag, unsigned char* dst, int dstep, int tr_t, int tr_ph, int tr_ev) {
+  // Stage this thread's pieces i < nl of a tagged vector (piece i at src + i * sstep) at dst + i * dstep.  The thread first
+  // spins on `flags` (the step counters of the four CTAs of the producing cluster, one 16-byte load) until the live ranks
+  // show `want`; then it loads the pieces and verifies every tag (a flag may overtake its data: then it simply re-loads).
+  auto poll_tile = [&](auto nconst, const uint4* src, size_t sstep, int nl, unsigned tag, unsigned char* dst, int dstep,
+                       const uint32_t* flags, unsigned want, bool use_flags, int tr_t, int tr_ph, int tr_ev) {
     constexpr int N = decltype(nconst)::value;
     if (nl <= 0) return;
     unsigned spins = 0; long long t0 = 0;
-    while (!p.poll_all) {
-      const uint4 a = ld_strong_v4(src);
-      if (fresh4(a, tag)) break;
+    while (use_flags) {
+      const uint4 f = ld_strong_v4(flags);
+      if (f.x == want && (nlive < 2 || f.y == want) && (nlive < 3 || f.z == want) && (nlive < 4 || f.w == want)) break;
       spin_check(spins, t0);
     }
     if (tr_ev >= 0) trace(tr_t, tr_ph, tr_ev);
@@ -508,6 +557,7 @@ __global__ void __launch_bounds__(NT, 1) f3_gen_kernel(Plan p, GenArgsDev g) {
       for (int i = 0; i < N; ++i) if (i < nl) ok = ok && fresh4(v[i], tag);
       if (ok) break;
       spin_check(spins, t0);
+      if (p.backoff_ns) __nanosleep(p.backoff_ns);
     }
 #pragma unroll
     for (int i = 0; i < N; ++i) if (i < nl) *(uint4*)(dst + i * dstep) = v[i];
@@ -516,7 +566,7 @@ __global__ void __launch_bounds__(NT, 1) f3_gen_kernel(Plan p, GenArgsDev g) {
   using N8 = std::integral_constant<int, 8>;
 
   if (warp < 4) {
-    // ======================================================================================= ET: T tiles, z_j, head
+    // ======================================================================================= ET: C + P tiles, z_j, head
     const int w = warp;                                   // TMEM lanes 32w ..: utterance 32w + lane, finished by rank w
     const int lu = tid >> 2, q = tid & 3;                 // finishing role: utterance 32 rank + lu, rows 8q .. 8q+7
     const int fu = 32 * rank + lu;
@@ -524,10 +574,10 @@ __global__ void __launch_bounds__(NT, 1) f3_gen_kernel(Plan p, GenArgsDev g) {
     const uint32_t trow = tmem + ((uint32_t)(32 * w) << 16);
     int sy_c = half, sy_p1 = half, sy_p2 = half;
     int nT = 0;
-    unsigned rtpar = 0;                                   // wait parities of the two recvT barriers
     float* const myP = p.Paux + ((size_t)s * L * 32 + lu) * 32 + 8 * q;   // + j * 1024
     const float* const T0 = p.T0 + (size_t)c * 3 * Q * 32 + 8 * q;
     const float* const T12 = p.T12 + (size_t)c * 4 * Q * 32 + 8 * q;
+    const float* const bgp = p.bgate + (size_t)c * 32 + 8 * q;            // + j * NCL * 32
 
     auto gate4 = [&](int j, const float (&pre)[8], unsigned tag) {   // z of channels 4q .. 4q+3, published as one 16-byte piece per thread pair
       float z[4];
@@ -592,26 +642,30 @@ __global__ void __launch_bounds__(NT, 1) f3_gen_kernel(Plan p, GenArgsDev g) {
         const float4 a0 = __ldg((const float4*)(T0 + (0 * Q + sy_c) * 32)), a1 = __ldg((const float4*)(T0 + (0 * Q + sy_c) * 32 + 4));
         const float4 b0 = __ldg((const float4*)(T0 + (1 * Q + sy_p1) * 32)), b1 = __ldg((const float4*)(T0 + (1 * Q + sy_p1) * 32 + 4));
         const float4 c0 = __ldg((const float4*)(T0 + (2 * Q + sy_p2) * 32)), c1 = __ldg((const float4*)(T0 + (2 * Q + sy_p2) * 32 + 4));
-        const float* bg = sBg + 8 * q;
-        pre[0] = a0.x + b0.x + c0.x + fmaf(wt, pa.x, bg[0]); pre[1] = a0.y + b0.y + c0.y + fmaf(wt, pa.y, bg[1]);
-        pre[2] = a0.z + b0.z + c0.z + fmaf(wt, pa.z, bg[2]); pre[3] = a0.w + b0.w + c0.w + fmaf(wt, pa.w, bg[3]);
-        pre[4] = a1.x + b1.x + c1.x + fmaf(wt, pb.x, bg[4]); pre[5] = a1.y + b1.y + c1.y + fmaf(wt, pb.y, bg[5]);
-        pre[6] = a1.z + b1.z + c1.z + fmaf(wt, pb.z, bg[6]); pre[7] = a1.w + b1.w + c1.w + fmaf(wt, pb.w, bg[7]);
+        const float4 g0 = __ldg((const float4*)bgp), g1 = __ldg((const float4*)(bgp + 4));
+        pre[0] = a0.x + b0.x + c0.x + fmaf(wt, pa.x, g0.x); pre[1] = a0.y + b0.y + c0.y + fmaf(wt, pa.y, g0.y);
+        pre[2] = a0.z + b0.z + c0.z + fmaf(wt, pa.z, g0.z); pre[3] = a0.w + b0.w + c0.w + fmaf(wt, pa.w, g0.w);
+        pre[4] = a1.x + b1.x + c1.x + fmaf(wt, pb.x, g1.x); pre[5] = a1.y + b1.y + c1.y + fmaf(wt, pb.y, g1.y);
+        pre[6] = a1.z + b1.z + c1.z + fmaf(wt, pb.z, g1.z); pre[7] = a1.w + b1.w + c1.w + fmaf(wt, pb.w, g1.w);
         gate4(0, pre, tagz);
+        if (use_flags) {
+          asm volatile("bar.sync 2, 128;\n" ::: "memory");   // every finishing thread has issued its pieces
+          if (tid == 0) st_strong_u32(p.flagz + s, (unsigned)(t + NP));
+        }
       }
       trace(t, 0, 5);
       // ---- blocks 1 .. L-1
       for (int j = 1; j < L; ++j) {
-        const int b = nT & 1;
-        const uint32_t rbar = bar(B_RT + b);
+        const int b = j & 1, pb_ = (j - 1) & 1, rbuf = nT & 1;
+        const uint32_t rbar = bar(B_RT + rbuf);
         if (fin && tid == 0) mbar_expect_tx(rbar, 4 * 32 * 64);
         // everything the finish needs besides the partial rows: aux, bias, (blocks 1, 2) the x_0 tables
         float pre[8];
         if (fin) {
           const float4 pa = ldcg4(myP + (size_t)j * 1024), pb = ldcg4(myP + (size_t)j * 1024 + 4);
-          const float* bg = sBg + j * 32 + 8 * q;
-          pre[0] = fmaf(wt, pa.x, bg[0]); pre[1] = fmaf(wt, pa.y, bg[1]); pre[2] = fmaf(wt, pa.z, bg[2]); pre[3] = fmaf(wt, pa.w, bg[3]);
-          pre[4] = fmaf(wt, pb.x, bg[4]); pre[5] = fmaf(wt, pb.y, bg[5]); pre[6] = fmaf(wt, pb.z, bg[6]); pre[7] = fmaf(wt, pb.w, bg[7]);
+          const float4 g0 = __ldg((const float4*)(bgp + (size_t)j * NCL * 32)), g1 = __ldg((const float4*)(bgp + (size_t)j * NCL * 32 + 4));
+          pre[0] = fmaf(wt, pa.x, g0.x); pre[1] = fmaf(wt, pa.y, g0.y); pre[2] = fmaf(wt, pa.z, g0.z); pre[3] = fmaf(wt, pa.w, g0.w);
+          pre[4] = fmaf(wt, pb.x, g1.x); pre[5] = fmaf(wt, pb.y, g1.y); pre[6] = fmaf(wt, pb.z, g1.z); pre[7] = fmaf(wt, pb.w, g1.w);
           if (j <= 2) {
             const float* Ta = T12 + ((size_t)(j - 1) * 2 + 0) * Q * 32 + sy_c * 32;
             const float* Tb = T12 + ((size_t)(j - 1) * 2 + 1) * Q * 32 + sy_p1 * 32;
@@ -621,35 +675,40 @@ __global__ void __launch_bounds__(NT, 1) f3_gen_kernel(Plan p, GenArgsDev g) {
             pre[4] += u1.x + v1.x; pre[5] += u1.y + v1.y; pre[6] += u1.z + v1.z; pre[7] += u1.w + v1.w;
           }
         }
-        mbar_wait(bar(B_TFULL + b), (unsigned)(nT >> 1) & 1u);
+        waitb(B_PFULL + pb_);                             // P_j: built during the previous phase
+        waitb(B_CFULL + b);                               // C_j = G_j z_{j-1}
         tc_fence_after();
         trace(t, j, 2);
         if (w < nlive) {
-          uint32_t v[32];
-          tmem_ld32(trow + TC_T + 32 * b, v);
+          unsigned hw[16];                                // the 32 partial rows of (utterance 32w + lane) as fp16 pairs
+#pragma unroll
+          for (int hh = 0; hh < 2; ++hh) {
+            uint32_t cv[16], pv[16];
+            tmem_ld16(trow + TC_BUF * b + TC_C + 16 * hh, cv);
+            tmem_ld16(trow + TC_BUF * pb_ + TC_P + 16 * hh, pv);
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+              hw[8 * hh + i] = pack_h2(__uint_as_float(cv[2 * i]) + __uint_as_float(pv[2 * i]),
+                                       __uint_as_float(cv[2 * i + 1]) + __uint_as_float(pv[2 * i + 1]));
+          }
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(bar(B_TFREE + b));
-          const uint32_t dst = sbase + SM_RT + (uint32_t)(((b * 4 + rank) * 32 + lane) * 64);
+          if (lane == 0) { mbar_arrive(bar(B_CFREE + b)); mbar_arrive(bar(B_PFREE + pb_)); }
+          const uint32_t dst = sbase + SM_RT + (uint32_t)(((rbuf * 4 + rank) * 32 + lane) * 64);
           const uint32_t rdst = mapa(dst, (unsigned)w), rb = mapa(rbar, (unsigned)w);
 #pragma unroll
-          for (int i = 0; i < 4; ++i)
-            st_async_v4(rdst + 16 * i,
-                        make_uint4(pack_h2(__uint_as_float(v[8 * i]), __uint_as_float(v[8 * i + 1])),
-                                   pack_h2(__uint_as_float(v[8 * i + 2]), __uint_as_float(v[8 * i + 3])),
-                                   pack_h2(__uint_as_float(v[8 * i + 4]), __uint_as_float(v[8 * i + 5])),
-                                   pack_h2(__uint_as_float(v[8 * i + 6]), __uint_as_float(v[8 * i + 7]))), rb);
+          for (int i = 0; i < 4; ++i) st_async_v4(rdst + 16 * i, make_uint4(hw[4 * i], hw[4 * i + 1], hw[4 * i + 2], hw[4 * i + 3]), rb);
         } else {
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(bar(B_TFREE + b));
+          if (lane == 0) { mbar_arrive(bar(B_CFREE + b)); mbar_arrive(bar(B_PFREE + pb_)); }
         }
         trace(t, j, 3);
         if (fin) {
-          mbar_wait(rbar, (rtpar >> b) & 1u);
-          rtpar ^= 1u << b;
+          waitb(B_RT + rbuf);
           trace(t, j, 4);
-          const unsigned char* rp = sm + SM_RT + ((b * 4) * 32 + lu) * 64 + 16 * q;
+          gtrace(t, j, 2);
+          const unsigned char* rp = sm + SM_RT + ((rbuf * 4) * 32 + lu) * 64 + 16 * q;
 #pragma unroll
           for (int src = 0; src < 4; ++src) {
             const uint4 h4 = *(const uint4*)(rp + src * 32 * 64);
@@ -658,6 +717,11 @@ __global__ void __launch_bounds__(NT, 1) f3_gen_kernel(Plan p, GenArgsDev g) {
             pre[4] += f2.x; pre[5] += f2.y; pre[6] += f3.x; pre[7] += f3.y;
           }
           gate4(j, pre, tagz);
+          if (use_flags) {
+            asm volatile("bar.sync 2, 128;\n" ::: "memory");
+            if (tid == 0) st_strong_u32(p.flagz + (size_t)j * NCTA + s, (unsigned)(t + NP));
+          }
+          gtrace(t, j, 0);
         }
         trace(t, j, 5);
         ++nT;
@@ -668,7 +732,7 @@ __global__ void __launch_bounds__(NT, 1) f3_gen_kernel(Plan p, GenArgsDev g) {
         for (int hd = 0; hd < 2; ++hd) {
           const uint32_t rbar = bar(B_RH + hd);
           if (fin && tid == 0) mbar_expect_tx(rbar, 4 * 32 * 16);
-          mbar_wait(bar(B_HFULL + hd), par_t);
+          waitb(B_HFULL + hd);
           tc_fence_after();
           if (w < nlive) {
             uint32_t v[8];
@@ -681,7 +745,7 @@ __global__ void __launch_bounds__(NT, 1) f3_gen_kernel(Plan p, GenArgsDev g) {
           }
           tc_fence_before();
           if (fin) {
-            mbar_wait(rbar, par_t);
+            waitb(B_RH + hd);
             float s0 = sBh[hd * 8 + 2 * q], s1 = sBh[hd * 8 + 2 * q + 1];
             const unsigned char* rp = sm + SM_RH + ((hd * 4) * 32 + lu) * 16 + 4 * q;
 #pragma unroll
@@ -694,6 +758,10 @@ __global__ void __launch_bounds__(NT, 1) f3_gen_kernel(Plan p, GenArgsDev g) {
               const unsigned w1 = __shfl_down_sync(0xffffffffu, w0, 1), w2 = __shfl_down_sync(0xffffffffu, w0, 2),
                              w3 = __shfl_down_sync(0xffffffffu, w0, 3);
               if (q == 0 && live) st_strong_v4(p.v256 + ((size_t)UB + fu) * (S / 2) + 4 * c, make_uint4(w0, w1, w2, w3));
+              if (use_flags) {
+                asm volatile("bar.sync 2, 128;\n" ::: "memory");
+                if (tid == 0) st_strong_u32(p.flagh + NCTA + s, (unsigned)t);
+              }
             } else if (live) {
               st_strong_v2(p.vlog + (size_t)fu * Q + 8 * c + 2 * q, (__float_as_uint(s0) & ~1u) | par_t, (__float_as_uint(s1) & ~1u) | par_t);
             }
@@ -710,8 +778,8 @@ __global__ void __launch_bounds__(NT, 1) f3_gen_kernel(Plan p, GenArgsDev g) {
     const uint32_t trow = tmem + ((uint32_t)(32 * w) << 16);
     int sy_c = half, sy_p1 = half;
     int nU = 0;
-    unsigned rupar = 0;
     const float* const Eo = p.Eo + (size_t)c * 2 * Q * 16 + 4 * q;
+    const float* const brp = p.bres + (size_t)c * 32;     // + l * NCL * 32
     for (int t = -NP; t < g.max_steps; ++t) {
       if (t == 0) {
         sy_p1 = sy_c;
@@ -736,27 +804,38 @@ __global__ void __launch_bounds__(NT, 1) f3_gen_kernel(Plan p, GenArgsDev g) {
         xc[0] = e0.x + e1.x; xc[1] = e0.y + e1.y; xc[2] = e0.z + e1.z; xc[3] = e0.w + e1.w;
       }
       for (int j = 1; j <= L; ++j) {
-        const int tb = nU & 1, rb3 = nU % 3;
+        const int tb = j & 1, rb3 = nU % 3;
         const uint32_t rbar = bar(B_RU + rb3);
         if (fin && t128 == 0) mbar_expect_tx(rbar, 4 * 32 * 48);
-        mbar_wait(bar(B_UFULL + tb), (unsigned)(nU >> 1) & 1u);
+        const int l = j - 1;                              // block whose residual / skip projection this is
+        float r0 = 0.f, r1 = 0.f, r2 = 0.f, r3 = 0.f, k0 = 0.f, k1 = 0.f;
+        if (fin) {
+          const float4 br4 = __ldg((const float4*)(brp + (size_t)l * NCL * 32 + 4 * q));
+          const float2 bk2 = __ldg((const float2*)(brp + (size_t)l * NCL * 32 + 16 + 2 * q));
+          r0 = br4.x; r1 = br4.y; r2 = br4.z; r3 = br4.w; k0 = bk2.x; k1 = bk2.y;
+        }
+        waitb(B_UFULL + tb);
         tc_fence_after();
         trace(t, j, 13);
         if (w < nlive) {
-          uint32_t v[32];
-          tmem_ld32(trow + TC_U + 32 * tb, v);
+          uint32_t v0[16], v1[8];
+          tmem_ld16(trow + TC_BUF * tb + TC_U, v0);
+          tmem_ld8(trow + TC_BUF * tb + TC_U + 16, v1);
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(bar(B_UFREE + tb));
           const uint32_t dst = sbase + SM_RU + (uint32_t)(((rb3 * 4 + rank) * 32 + lane) * 48);
           const uint32_t rdst = mapa(dst, (unsigned)w), rb = mapa(rbar, (unsigned)w);
 #pragma unroll
-          for (int i = 0; i < 3; ++i)
+          for (int i = 0; i < 2; ++i)
             st_async_v4(rdst + 16 * i,
-                        make_uint4(pack_h2(__uint_as_float(v[8 * i]), __uint_as_float(v[8 * i + 1])),
-                                   pack_h2(__uint_as_float(v[8 * i + 2]), __uint_as_float(v[8 * i + 3])),
-                                   pack_h2(__uint_as_float(v[8 * i + 4]), __uint_as_float(v[8 * i + 5])),
-                                   pack_h2(__uint_as_float(v[8 * i + 6]), __uint_as_float(v[8 * i + 7]))), rb);
+                        make_uint4(pack_h2(__uint_as_float(v0[8 * i]), __uint_as_float(v0[8 * i + 1])),
+                                   pack_h2(__uint_as_float(v0[8 * i + 2]), __uint_as_float(v0[8 * i + 3])),
+                                   pack_h2(__uint_as_float(v0[8 * i + 4]), __uint_as_float(v0[8 * i + 5])),
+                                   pack_h2(__uint_as_float(v0[8 * i + 6]), __uint_as_float(v0[8 * i + 7]))), rb);
+          st_async_v4(rdst + 32,
+                      make_uint4(pack_h2(__uint_as_float(v1[0]), __uint_as_float(v1[1])), pack_h2(__uint_as_float(v1[2]), __uint_as_float(v1[3])),
+                                 pack_h2(__uint_as_float(v1[4]), __uint_as_float(v1[5])), pack_h2(__uint_as_float(v1[6]), __uint_as_float(v1[7]))), rb);
         } else {
           tc_fence_before();
           __syncwarp();
@@ -764,13 +843,8 @@ __global__ void __launch_bounds__(NT, 1) f3_gen_kernel(Plan p, GenArgsDev g) {
         }
         trace(t, j, 14);
         if (fin) {
-          mbar_wait(rbar, (rupar >> rb3) & 1u);
-          rupar ^= 1u << rb3;
+          waitb(B_RU + rb3);
           trace(t, j, 15);
-          const int l = j - 1;                              // block whose residual / skip projection this is
-          const float* br = sBr + l * 32;
-          float r0 = br[4 * q], r1 = br[4 * q + 1], r2 = br[4 * q + 2], r3 = br[4 * q + 3];
-          float k0 = br[16 + 2 * q], k1 = br[16 + 2 * q + 1];
           const unsigned char* rp = sm + SM_RU + ((rb3 * 4) * 32 + lu) * 48;
 #pragma unroll
           for (int src = 0; src < 4; ++src) {
@@ -795,47 +869,57 @@ __global__ void __launch_bounds__(NT, 1) f3_gen_kernel(Plan p, GenArgsDev g) {
                 st_strong_v4(dstp + (size_t)x_slot(j, t) * UB * (C / 2), piece);
               }
             }
+            if (use_flags) {
+              asm volatile("bar.sync 3, 128;\n" ::: "memory");   // every finishing thread has issued its pieces
+              if (t128 == 0) st_strong_u32(p.flagx + (size_t)j * NCTA + s, (unsigned)(t + NP));
+            }
           } else if (t >= 0) {   // relu(sum of the skip outputs) (qpnet.py:505, 566-567) rows 8c + 2q, +1
             const unsigned par_t = (unsigned)t & 1u;
             const unsigned w0 = pack_tagged(fmaxf(sk0, 0.f), fmaxf(sk1, 0.f), par_t);
             const unsigned w1 = __shfl_down_sync(0xffffffffu, w0, 1), w2 = __shfl_down_sync(0xffffffffu, w0, 2),
                            w3 = __shfl_down_sync(0xffffffffu, w0, 3);
             if (q == 0 && live) st_strong_v4(p.v256 + (size_t)fu * (S / 2) + 4 * c, make_uint4(w0, w1, w2, w3));
+            if (use_flags) {
+              asm volatile("bar.sync 3, 128;\n" ::: "memory");
+              if (t128 == 0) st_strong_u32(p.flagh + s, (unsigned)t);
+            }
           }
         }
         trace(t, j, 16);
+        if (fin) gtrace(t, j, 3);
         ++nU;
       }
     }
   } else if (warp < 12) {
     // ======================================================================================= PZ: z_{j-1} / head vectors -> A tile
     const int i128 = tid - 256;
-    int nZ = 0;
     unsigned char* const sZ = sm + SM_Z;
-    auto begin = [&]() { if (nZ >= 1) mbar_wait(bar(B_ZFREE), (unsigned)(nZ - 1) & 1u); };
-    auto done = [&]() { fence_proxy_async(); mbar_arrive(bar(B_ZFULL)); ++nZ; };
+    auto done = [&]() { fence_proxy_async(); mbar_arrive(bar(B_ZFULL)); };
     for (int t = -NP; t < g.max_steps; ++t) {
       const unsigned tagz = (unsigned)(t + NP) & 1u;
       for (int j = 1; j <= L; ++j) {
-        begin();
+        waitb(B_ZFREE);
         // this rank's K-share of z_{j-1}: 16 pieces of 16 bytes per utterance; thread -> piece pc of utterances ub + 8 i
         const int pc = i128 & 15, ub = i128 >> 4;
         const uint4* src = (const uint4*)(p.vz + ((size_t)(j - 1) * UB + ub) * (C / 2)) + rank * 16 + pc;
         unsigned char* dst = sZ + (pc >> 3) * ABLK + ub * 128 + (((pc & 7) ^ ub) << 4);
         trace(t, j, 11);
-        poll_tile(N16(), src, (size_t)8 * (C / 8), min(16, (B - ub + 7) >> 3), tagz, dst, 1024, t, j, 12);
+        poll_tile(N16(), src, (size_t)8 * (C / 8), min(16, (B - ub + 7) >> 3), tagz, dst, 1024,
+                  p.flagz + (size_t)(j - 1) * NCTA + 4 * (8 * rank + (pc >> 1)), (unsigned)(t + NP), !(p.poll_all & 1), t, j, 12);
         trace(t, j, 6);
+        gtrace(t, j, 1);
         done();
       }
       if (t >= 0) {
         const unsigned par_t = (unsigned)t & 1u;
         for (int hd = 0; hd < 2; ++hd) {
-          begin();
+          waitb(B_ZFREE);
           // K-share of a 256-vector: 8 pieces per utterance; thread -> piece pc of utterances ub + 16 i
           const int pc = i128 & 7, ub = i128 >> 3;
           const uint4* src = (const uint4*)(p.v256 + ((size_t)hd * UB + ub) * (S / 2)) + rank * 8 + pc;
           unsigned char* dst = sZ + (ub >> 3) * 1024 + (ub & 7) * 128 + ((pc ^ (ub & 7)) << 4);
-          poll_tile(N8(), src, (size_t)16 * (S / 8), min(8, (B - ub + 15) >> 4), par_t, dst, 2048, t, 0, -1);
+          poll_tile(N8(), src, (size_t)16 * (S / 8), min(8, (B - ub + 15) >> 4), par_t, dst, 2048,
+                    p.flagh + (size_t)hd * NCTA + 4 * (8 * rank + pc), (unsigned)t, !(p.poll_all & 1), t, 0, -1);
           done();
         }
       }
@@ -844,172 +928,141 @@ __global__ void __launch_bounds__(NT, 1) f3_gen_kernel(Plan p, GenArgsDev g) {
     // ======================================================================================= PX: x_{j-1} and past taps -> A tiles
     const int i128 = tid - 384;
     const int pc = i128 & 15, ub = i128 >> 4;             // piece pc of utterances ub + 8 i, i < 16
-    int nX = 0, nXP = 0;
     const long long ldd = (long long)p.F * U;
     const uint32_t tile_off = (uint32_t)((pc >> 3) * ABLK + ub * 128 + (((pc & 7) ^ ub) << 4));   // + i * 1024
-    // past tap of block jb for step t: x_jb(t - k) of every utterance -> XP tile
+    // past tap of block jb for step t: x_jb(t - k) of every utterance -> XP tile, asynchronously: the copies complete on
+    // the mbarrier the MMA thread waits for, this thread moves on
     auto stage_xp = [&](int jb, int t) {
-      if (nXP >= 1) mbar_wait(bar(B_XPFREE), (unsigned)(nXP - 1) & 1u);
+      waitb(B_XPFREE);
       trace(t, jb - 1, 17);
-      unsigned char* dst = sm + SM_XP + tile_off;
       if (t == -NP) {   // the first priming pass has no ring contents yet
+        unsigned char* dst = sm + SM_XP + tile_off;
 #pragma unroll
         for (int i = 0; i < 16; ++i) *(uint4*)(dst + i * 1024) = make_uint4(0, 0, 0, 0);
+        fence_proxy_async();
+        mbar_arrive(bar(B_XPFULL));
       } else {
-        const int rmask = (1 << p.rlog[jb]) - 1, dl = p.dil[jb], dep = p.depth[jb];
-        const bool adaptive = jb >= p.nF;
-#pragma unroll 1
-        for (int hb = 0; hb < 2; ++hb) {
-          const int u0 = ub + 64 * hb;                    // this thread's utterances of the half: u0 + 8 i
-          if (u0 >= B) break;
-          int slot[8];
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const int u = min(u0 + 8 * i, B - 1);         // (rows >= B are loaded from a live utterance and never stored)
-            int k = dl;
-            if (adaptive && t >= 0) {   // pitch-dependent look-back of this step (qpnet.py:476-483, 613-624)
-              k = g.d_is_f64 ? -gen_index_f64(__ldg((const double*)g.d + (long long)u * ldd + t), dl)
-                             : -gen_index_f32(__ldg((const float*)g.d + (long long)u * ldd + t), dl);
-              if (k <= 0 || k > dep) k = dep;   // k == 0: python index 0 = oldest entry (C4)
-            }
-            slot[i] = t >= 0 ? ((t - k) & rmask) : 0;
+        const int rmask = (1 << p.rlog[jb]) - 1, dl = p.dil[jb];
+        const unsigned short* kt = jb >= p.nF ? sK + (jb - p.nF) * UB : nullptr;   // pitch-dependent look-backs of this step
+        const uint32_t dst = sbase + SM_XP + tile_off;
+        const uint4* src = (const uint4*)p.xr[jb] + rank * 16 + pc;
+#pragma unroll 4
+        for (int i = 0; i < 16; ++i) {
+          const int u = ub + 8 * i;
+          if (u < B) {
+            const int k = kt ? (int)kt[u] : dl;
+            const int slot = t >= 0 ? ((t - k) & rmask) : 0;
+            cp_async16_s(dst + i * 1024, src + ((size_t)slot * UB + u) * (C / 8));
           }
-          uint4 v[8];
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const int u = min(u0 + 8 * i, B - 1);
-            v[i] = ld_strong_v4((const uint4*)(p.xr[jb] + ((size_t)slot[i] * UB + u) * (C / 2)) + rank * 16 + pc);
-          }
-#pragma unroll
-          for (int i = 0; i < 8; ++i)
-            if (u0 + 8 * i < B) *(uint4*)(dst + (8 * hb + i) * 1024) = v[i];
         }
+        cp_async_arrive_noinc(bar(B_XPFULL));
       }
       trace(t, jb - 1, 18);
-      fence_proxy_async();
-      mbar_arrive(bar(B_XPFULL));
-      ++nXP;
     };
     // x_jx of the current step (published during the previous phase) -> X tile
     auto stage_x = [&](int jx, int t) {
-      if (nX >= 1) mbar_wait(bar(B_XFREE), (unsigned)(nX - 1) & 1u);
+      waitb(B_XFREE);
       unsigned char* dst = sm + SM_X + tile_off;
       const unsigned tag = x_tag(jx, t);
       const uint4* src0 = (const uint4*)(p.xr[jx] + (size_t)x_slot(jx, t) * UB * (C / 2)) + rank * 16 + pc;
       trace(t, jx + 1, 19);
-      poll_tile(N16(), src0 + (size_t)ub * (C / 8), (size_t)8 * (C / 8), min(16, (B - ub + 7) >> 3), tag, dst, 1024, t, jx + 1, 20);
+      poll_tile(N16(), src0 + (size_t)ub * (C / 8), (size_t)8 * (C / 8), min(16, (B - ub + 7) >> 3), tag, dst, 1024,
+                p.flagx + (size_t)jx * NCTA + 4 * (8 * rank + (pc >> 1)), (unsigned)(t + NP), !(p.poll_all & 2), t, jx + 1, 20);
       trace(t, jx + 1, 21);
       fence_proxy_async();
       mbar_arrive(bar(B_XFULL));
-      ++nX;
     };
     for (int t = -NP; t < g.max_steps; ++t) {
+      if (t >= 0 && p.nA > 0) {
+        // look-backs of the adaptive blocks for this step: k = -round(-d[t] * dil) with the reference's rounding
+        // (qpnet.py:476-483, 613-624); k == 0 (python index 0) and anything beyond the FIFO select the oldest entry (C4)
+        asm volatile("bar.sync 1, 128;\n" ::: "memory");         // every PX thread is done with the previous step's table
+        const int u = i128;
+        if (u < B) {
+          for (int a = 0; a < p.nA; ++a) {
+            const int dl = p.dil[p.nF + a], dep = p.depth[p.nF + a];
+            int k = g.d_is_f64 ? -gen_index_f64(__ldg((const double*)g.d + (long long)u * ldd + t), dl)
+                               : -gen_index_f32(__ldg((const float*)g.d + (long long)u * ldd + t), dl);
+            if (k <= 0 || k > dep) k = dep;
+            sK[a * UB + u] = (unsigned short)k;
+          }
+        }
+        asm volatile("bar.sync 1, 128;\n" ::: "memory");
+      }
       stage_xp(1, t);
       for (int j = 1; j <= L - 2; ++j) {
         stage_xp(j + 1, t);
         if (j >= 2) stage_x(j - 1, t);
       }
     }
+    asm volatile("cp.async.wait_all;\n" ::: "memory");
   } else if (warp == 16) {
     // ======================================================================================= MMA issuer (one thread)
     if (lane == 0) {
-      const uint32_t idesc32 = umma_idesc(128, 32), idesc16 = umma_idesc(128, 16);
       const uint32_t sZ = sbase + SM_Z, sX = sbase + SM_X, sXP = sbase + SM_XP;
-      int nW = 0, nTf = 0, nTc = 0, nU = 0, nZ = 0, nX = 0, nXP = 0;
-      auto wchunk = [&]() -> uint32_t {   // next weight chunk of the schedule (same order as the loader)
-        const int slot = nW % DW;
-        mbar_wait(bar(B_WFULL + slot), (unsigned)(nW / DW) & 1u);
-        return sbase + SM_W + slot * WCH_B;
-      };
-      auto wdone = [&]() { umma_commit(bar(B_WFREE + nW % DW)); ++nW; };
-      auto mma8 = [&](uint32_t dcol, uint32_t a_base, uint32_t b_base, bool fresh) {
+      // D[128 x N] (+)= A[128 x 128] B[N x 128]^T: two 64-wide K-blocks of four K = 16 steps
+      auto mma = [&](int N, uint32_t dcol, uint32_t a_base, uint32_t b_base, uint32_t b_kblock, bool fresh) {
         fence_proxy_async();   // generic-proxy stores of the pollers -> tcgen05 operand reads (async proxy)
         tc_fence_after();
+        const uint32_t idesc = umma_idesc(128, N);
 #pragma unroll
         for (int kb = 0; kb < 2; ++kb) {
-          const uint64_t ad = umma_desc(a_base + kb * ABLK), bd = umma_desc(b_base + kb * (WCH_B / 2));
+          const uint64_t ad = umma_desc(a_base + kb * ABLK), bd = umma_desc(b_base + kb * b_kblock);
 #pragma unroll
-          for (int ks = 0; ks < 4; ++ks) umma(tmem + dcol, ad + 2 * ks, bd + 2 * ks, idesc32, (fresh && kb == 0 && ks == 0) ? 0u : 1u);
+          for (int ks = 0; ks < 4; ++ks) umma(tmem + dcol, ad + 2 * ks, bd + 2 * ks, idesc, (fresh && kb == 0 && ks == 0) ? 0u : 1u);
         }
-      };
-      auto t_fresh_buf = [&]() -> int {   // TMEM buffer of the next T tile to initialise; its previous contents must have been read
-        const int b = nTf & 1;
-        if (nTf >= 2) mbar_wait(bar(B_TFREE + b), (unsigned)((nTf >> 1) - 1) & 1u);
-        return b;
-      };
-      auto u_buf = [&]() -> int {
-        const int b = nU & 1;
-        if (nU >= 2) mbar_wait(bar(B_UFREE + b), (unsigned)((nU >> 1) - 1) & 1u);
-        return b;
       };
       for (int t = -NP; t < g.max_steps; ++t) {
-        {   // phase 0: T_1 <- Wp_1 x_1(t-k)
-          const int b = t_fresh_buf();
-          const uint32_t wv = wchunk();
-          mbar_wait(bar(B_XPFULL), (unsigned)nXP & 1u);
-          mma8(TC_T + 32 * b, sXP, wv, true);
-          wdone(); umma_commit(bar(B_XPFREE)); ++nXP; ++nTf;
+        {   // phase 0: P_1 (buffer 0) <- Wp_1 x_1(t-k)
+          waitb(B_PFREE + 0); waitb(B_WPW_FULL + 0); waitb(B_XPFULL);
+          mma(32, TC_P, sXP, sbase + SM_W + ZPC_B + WCH_B, WCH_B / 2, true);
+          umma_commit(bar(B_WPW_FREE + 0)); umma_commit(bar(B_XPFREE)); umma_commit(bar(B_PFULL + 0));
         }
         for (int j = 1; j < L; ++j) {
-          {   // T_j += G_j z_{j-1}: the tile is complete
-            const int b = nTc & 1;
-            const uint32_t wv = wchunk();
-            mbar_wait(bar(B_ZFULL), (unsigned)nZ & 1u);
-            trace(t, j, 0);
-            mma8(TC_T + 32 * b, sZ, wv, false);
-            wdone(); umma_commit(bar(B_TFULL + b)); ++nTc;
-            trace(t, j, 1);
-          }
-          {   // U_j <- [R ; K]_{j-1} z_{j-1}
-            const int b = u_buf();
-            const uint32_t wv = wchunk();
-            mma8(TC_U + 32 * b, sZ, wv, true);
-            wdone(); umma_commit(bar(B_UFULL + b)); ++nU;
-          }
-          if (j + 1 <= L - 1) {
-            const int b = t_fresh_buf();
-            {   // T_{j+1} <- H_{j+1} z_{j-1}
-              const uint32_t wv = wchunk();
-              mma8(TC_T + 32 * b, sZ, wv, true);
-              wdone(); umma_commit(bar(B_ZFREE)); ++nZ; ++nTf;
-            }
-            trace(t, j, 7);
-            if (j >= 2) {   // += Wc_{j+1} x_{j-1}
-              const uint32_t wv = wchunk();
-              mbar_wait(bar(B_XFULL), (unsigned)nX & 1u);
+          const int b = j & 1;
+          const uint32_t grp = sbase + SM_W + b * WGRP_B, dbuf = TC_BUF * b;
+          const bool pre = j <= L - 2;                    // this phase also builds P_{j+1}
+          waitb(B_ZPW_FULL + b); waitb(B_CFREE + b); waitb(B_UFREE + b);
+          if (pre) waitb(B_PFREE + b);
+          waitb(B_ZFULL);
+          trace(t, j, 0);
+          // [C_j | U_j | P_{j+1}] <- [G_j ; [R;K]_{j-1} ; H_{j+1}] z_{j-1}
+          mma(pre ? 96 : 64, dbuf, sZ, grp, ZPC_B / 2, true);
+          umma_commit(bar(B_ZPW_FREE + b)); umma_commit(bar(B_ZFREE)); umma_commit(bar(B_CFULL + b)); umma_commit(bar(B_UFULL + b));
+          trace(t, j, 1);
+          if (pre) {
+            if (j >= 2) {   // P_{j+1} += Wc_{j+1} x_{j-1}
+              waitb(B_WCW_FULL + b); waitb(B_XFULL);
               trace(t, j, 8);
-              mma8(TC_T + 32 * b, sX, wv, false);
-              wdone(); umma_commit(bar(B_XFREE)); ++nX;
+              mma(32, dbuf + TC_P, sX, grp + ZPC_B, WCH_B / 2, false);
+              umma_commit(bar(B_WCW_FREE + b)); umma_commit(bar(B_XFREE));
             }
-            {   // += Wp_{j+1} x_{j+1}(t-k)
-              const uint32_t wv = wchunk();
-              mbar_wait(bar(B_XPFULL), (unsigned)nXP & 1u);
-              trace(t, j, 9);
-              mma8(TC_T + 32 * b, sXP, wv, false);
-              wdone(); umma_commit(bar(B_XPFREE)); ++nXP;
-              trace(t, j, 10);
-            }
-          } else {
-            umma_commit(bar(B_ZFREE)); ++nZ;
+            // P_{j+1} += Wp_{j+1} x_{j+1}(t-k)
+            waitb(B_WPW_FULL + b); waitb(B_XPFULL);
+            trace(t, j, 9);
+            mma(32, dbuf + TC_P, sXP, grp + ZPC_B + WCH_B, WCH_B / 2, false);
+            umma_commit(bar(B_WPW_FREE + b)); umma_commit(bar(B_XPFREE)); umma_commit(bar(B_PFULL + b));
+            trace(t, j, 10);
           }
         }
         {   // phase L: U_L <- [R ; K]_{L-1} z_{L-1} (skip rows; the residual rows of the last block are dead, C7)
-          const int b = u_buf();
-          const uint32_t wv = wchunk();
-          mbar_wait(bar(B_ZFULL), (unsigned)nZ & 1u);
+          const int b = L & 1;
+          const uint32_t grp = sbase + SM_W + b * WGRP_B;
+          waitb(B_ZPW_FULL + b); waitb(B_UFREE + b); waitb(B_ZFULL);
           trace(t, L, 0);
-          mma8(TC_U + 32 * b, sZ, wv, true);
-          wdone(); umma_commit(bar(B_UFULL + b)); umma_commit(bar(B_ZFREE)); ++nU; ++nZ;
+          mma(32, TC_BUF * b + TC_U, sZ, grp + 4096, ZPC_B / 2, true);   // rows 32-63 of the chunk: atom 4 of each K-block
+          umma_commit(bar(B_ZPW_FREE + b)); umma_commit(bar(B_ZFREE)); umma_commit(bar(B_UFULL + b));
         }
         if (t >= 0) {
           for (int hd = 0; hd < 2; ++hd) {   // head layers: 16 rows (8 live) x K-share 64, resident weights
-            mbar_wait(bar(B_ZFULL), (unsigned)nZ & 1u);
+            waitb(B_ZFULL);
             fence_proxy_async();
             tc_fence_after();
+            const uint32_t idesc16 = umma_idesc(128, 16);
             const uint64_t ad = umma_desc(sZ), bd = umma_desc(sbase + SM_WH + hd * HCH_B);
 #pragma unroll
             for (int ks = 0; ks < 4; ++ks) umma(tmem + TC_H + 16 * hd, ad + 2 * ks, bd + 2 * ks, idesc16, ks ? 1u : 0u);
-            umma_commit(bar(B_HFULL + hd)); umma_commit(bar(B_ZFREE)); ++nZ;
+            umma_commit(bar(B_HFULL + hd)); umma_commit(bar(B_ZFREE));
           }
         }
       }
@@ -1019,26 +1072,22 @@ __global__ void __launch_bounds__(NT, 1) f3_gen_kernel(Plan p, GenArgsDev g) {
     // ======================================================================================= weight loader (one thread)
     if (lane == 0) {
       const uint64_t pol_keep = l2_policy_evict_last();
-      int nW = 0;
-      auto load = [&](int kind, int l) {
-        const int slot = nW % DW;
-        if (nW >= DW) mbar_wait(bar(B_WFREE + slot), (unsigned)(nW / DW - 1) & 1u);
-        mbar_expect_tx(bar(B_WFULL + slot), WCH_B);
-        bulk_g2s(sbase + SM_W + slot * WCH_B, p.W + (((size_t)kind * L + l) * NCTA + s) * WCH_E, WCH_B, bar(B_WFULL + slot), pol_keep);
-        ++nW;
+      auto load = [&](int free_bar, int full_bar, uint32_t dst, const __nv_bfloat16* src, unsigned bytes) {
+        waitb(free_bar);
+        mbar_expect_tx(bar(full_bar), bytes);
+        bulk_g2s(dst, src, bytes, bar(full_bar), pol_keep);
       };
+      const __nv_bfloat16* const Wc = p.Wcp + (size_t)s * WCH_E;                        // + j * NCTA * WCH_E
+      const __nv_bfloat16* const Wp = p.Wcp + ((size_t)L * NCTA + s) * WCH_E;
       for (int t = -NP; t < g.max_steps; ++t) {
-        load(K_WP, 1);
-        for (int j = 1; j < L; ++j) {
-          load(K_G, j);
-          load(K_RK, j - 1);
-          if (j + 1 <= L - 1) {
-            load(K_H, j + 1);
-            if (j >= 2) load(K_WC, j + 1);
-            load(K_WP, j + 1);
-          }
+        load(B_WPW_FREE + 0, B_WPW_FULL + 0, sbase + SM_W + ZPC_B + WCH_B, Wp + (size_t)1 * NCTA * WCH_E, WCH_B);
+        for (int j = 1; j <= L; ++j) {
+          const int b = j & 1;
+          const uint32_t grp = sbase + SM_W + b * WGRP_B;
+          load(B_ZPW_FREE + b, B_ZPW_FULL + b, grp, p.Wzp + ((size_t)(j - 1) * NCTA + s) * ZPC_E, ZPC_B);
+          if (j >= 2 && j <= L - 2) load(B_WCW_FREE + b, B_WCW_FULL + b, grp + ZPC_B, Wc + (size_t)(j + 1) * NCTA * WCH_E, WCH_B);
+          if (j <= L - 2) load(B_WPW_FREE + b, B_WPW_FULL + b, grp + ZPC_B + WCH_B, Wp + (size_t)(j + 1) * NCTA * WCH_E, WCH_B);
         }
-        load(K_RK, L - 1);
       }
     }
     __syncwarp();
@@ -1135,11 +1184,13 @@ int f3_generate(const QpArch* arch, const float* const* tensors_host, const QpGe
   f3::Plan p;
   size_t need = f3::make_plan(arch, a->B, a->F, a->M, ws, ws_bytes, &p);
   if (need > ws_bytes) return set_error(QP_EWORKSPACE, "generate: workspace %zu < %zu bytes", ws_bytes, need);
-  const int smem = f3::SM_BG + p.L * 256 + 1024;
+  const int smem = f3::SM_END + 1024;
+  for (int l = 0; l < p.L; ++l) QP_REQUIRE(p.depth[l] < 65536, "generate: look-back %d of block %d does not fit the 16-bit table", p.depth[l], l);
   QP_REQUIRE(smem <= 227 * 1024, "generate: %d bytes of shared memory needed", smem);
   const bool tr = getenv("QPNET_GEN_TRACE_STEP") != nullptr;
   if (tr) p.trace_step0 = atoi(getenv("QPNET_GEN_TRACE_STEP"));
   if (const char* e = getenv("QPNET_F3_POLL_ALL")) p.poll_all = atoi(e);
+  if (const char* e = getenv("QPNET_F3_BACKOFF")) p.backoff_ns = atoi(e);
   auto kern = tr ? f3::f3_gen_kernel<true> : f3::f3_gen_kernel<false>;
   QP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   cudaLaunchConfig_t cfg = {};
@@ -1157,8 +1208,10 @@ int f3_generate(const QpArch* arch, const float* const* tensors_host, const QpGe
   QP_CUDA(cudaMemsetAsync(p.status, 0, 256, st));
   QP_CUDA(cudaMemsetAsync(p.tagged_begin, 0xFF, p.tagged_bytes, st));   // every word starts with a stale tag
   QP_CUDA(cudaMemsetAsync(p.trace, 0, sizeof(long long) * 8 * (p.L + 4) * f3::TRACE_EVENTS, st));
+  QP_CUDA(cudaMemsetAsync(p.gtrace, 0, sizeof(long long) * f3::NCTA * (p.L + 4) * 4, st));
   if (int e = upload_tensor_table(arch, tensors_host, p.tab, st)) return e;
   TensorMap tm = tensor_map(arch);
+  QP_CUDA(cudaMemsetAsync(p.Wzp, 0, sizeof(__nv_bfloat16) * (size_t)p.L * f3::NCTA * f3::ZPC_E, st));
   f3::pack_kernel<<<148 * 8, 256, 0, st>>>(tm, p, p.tab);
   QP_LAUNCH_CHECK();
   f3::fold_kernel<<<dim3(f3::NCL * 4, p.L, 2), 256, 0, st>>>(tm, p, p.tab);
@@ -1190,7 +1243,8 @@ bool f3_supported(const QpArch* arch, int B) { return f3::supported(arch, B); }
 int f3_trace_copy(const QpArch* arch, int B, int M, void* ws, size_t ws_bytes, long long* out_host, int n, cudaStream_t st) {
   f3::Plan p;
   f3::make_plan(arch, B, 1, M, ws, ws_bytes, &p);
-  int total = 8 * (p.L + 4) * f3::TRACE_EVENTS;
+  // the per-phase clock64 trace of CTA 0, followed by the %globaltimer trace of every CTA (contiguous in the workspace)
+  int total = 8 * (p.L + 4) * f3::TRACE_EVENTS + f3::NCTA * (p.L + 4) * 4;
   if (n > total) n = total;
   QP_CUDA(cudaMemcpyAsync(out_host, p.trace, sizeof(long long) * n, cudaMemcpyDeviceToHost, st));
   QP_CUDA(cudaStreamSynchronize(st));

@@ -2,9 +2,10 @@
 
 The reference's ``decode_generator`` (qpnet_decode.py:123-209) reads one hdf5 file per utterance, scales F0, computes the
 dilated factors and z-scores the features on the host in fp64, pads to a batch and uploads; its ``_decode`` loop
-(311-320) µ-law-decodes every result on the host and writes a 16-bit WAV.  Here the same arithmetic runs on the device in
-two launches per batch (``qp_feat_prepare``, ``qp_mulaw_decode_pcm16``); hdf5 / file-list handling stays with the caller,
-who passes the raw (T_i, D) feature matrices and the scaler statistics.
+(311-320) µ-law-decodes every result on the host and writes a 16-bit WAV.  Here the same arithmetic runs on the device:
+``qp_feat_prepare`` in front, and the generator itself writes the 16-bit PCM as its output stage
+(``QpGenerateArgs.out_pcm``; ``qp_mulaw_decode_pcm16`` is the standalone form); hdf5 / file-list handling stays with the
+caller, who passes the raw (T_i, D) feature matrices and the scaler statistics.
 """
 from __future__ import annotations
 
@@ -51,19 +52,28 @@ def prepare_batch(feats, mean, scale, fs, dense_factor=8, upsampling_factor=110,
 def decode(model, feats, mean, scale, fs=22050, dense_factor=8, batch_size=32, f0_factor=1.0, f0_dim_index=1,
            extra_memory=False, mode="sampling", ids=None):
     """Generate every utterance of ``feats`` (list of raw (T_i, D) matrices).  Returns ``{id: int16 PCM ndarray}``
-    (ids default to the list positions), the arrays the reference writes with ``wavfile.write`` (qpnet_decode.py:315-319)."""
+    (ids default to the list positions), the arrays the reference writes with ``wavfile.write`` (qpnet_decode.py:315-319).
+
+    Everything between the raw features and the PCM stays on the device: ``qp_feat_prepare`` (front end), the
+    generator, whose output stage writes the 16-bit PCM next to the symbols (``QpGenerateArgs.out_pcm``), and ONE
+    device-to-host copy per batch.  Every utterance draws from the Philox stream of its position in ``feats``
+    (``utt_ids``), so the noise of an utterance does not depend on the batch it lands in and no two utterances of a
+    corpus share a stream (the reference's global torch RNG advances across batches, qpnet.py:508-510)."""
+    from . import _lib
     ids = list(range(len(feats))) if ids is None else list(ids)
     dev = next(model.parameters()).device
+    qmode = {"sampling": _lib.QP_MODE_SAMPLING, "argmax": _lib.QP_MODE_ARGMAX}[mode]
     out = {}
     for group in batch_lists([f.shape[0] for f in feats], batch_size):
         x, h, n_list, d = prepare_batch([feats[i] for i in group], mean, scale, fs, dense_factor,
                                         model.upsampling_factor, f0_factor, f0_dim_index, extra_memory, dev)
-        n_orig = list(n_list)
-        samples = model.batch_fast_generate(x, h, n_list, d, None, mode, extra_memory)
-        order = np.argsort(np.array(n_orig), kind="stable")       # results come back in finish order (qpnet.py:527-557)
-        for r, k in zip(samples, order):
-            pcm = ops.mulaw_decode_pcm16(torch.from_numpy(r.astype(np.int32)).to(dev), model.n_quantize)
-            out[ids[group[k]]] = pcm.cpu().numpy()
+        B, max_n = len(group), max(n_list)
+        pcm = torch.zeros((B, max_n), dtype=torch.int16, device=dev)
+        model.generate_device(x[:, -1].to(dev).contiguous(), h, d, torch.tensor(n_list, dtype=torch.int32, device=dev), max_n,
+                              qmode, n_host=n_list, utt_ids=torch.tensor(group, dtype=torch.int32, device=dev), pcm_out=pcm)
+        host = pcm.cpu().numpy()                                   # the only device -> host copy of the batch
+        for k, n in enumerate(n_list):
+            out[ids[group[k]]] = host[k, :n].copy()
     return out
 
 

@@ -227,16 +227,22 @@ class QPNet(nn.Module):
     # ------------------------------------------------------------------ device-resident core
     @torch.no_grad()
     def generate_device(self, seed, h, d, n_dev, max_n, qmode=_lib.QP_MODE_SAMPLING, uniforms=None, force=None,
-                        return_logits=False, check_status=True, n_host=None):
+                        return_logits=False, check_status=True, n_host=None, utt_ids=None, pcm_out=None):
         """Generation with every input already resident in HBM: seed (B,) int64, h (B,A,F) fp32,
         d (B,F*U) fp64 (numpy flavour of the reference) or fp32 (extra_memory flavour), n_dev (B,)
-        int32.  Returns (symbols (B, max_n) int32 on the device, logits or None).
+        int32.  Returns (symbols (B, max_n) int32 on the device, logits or None).  ``pcm_out``: optional (B, >= max_n)
+        int16 device tensor the generator fills with the decoded waveform (mu-law decode * 32768, clipped: the output
+        stage of qpnet_decode.py:315-318); ``utt_ids`` (B,) int: caller-side utterance indices keying the Philox stream
+        (default: the position in this call).
 
         The tcgen05 cluster generator runs up to 128 utterances per launch.  A larger batch of the SI default widths is
         dealt to launches of 128, longest first, so every launch retires at its own last step (the reference's decoder
         sorts by length for the same reason, qpnet_decode.py:257-259); ``utt_ids`` keeps every utterance on the Philox
         stream of its caller-side index, so the symbols do not depend on the grouping."""
         B = h.shape[0]
+        if pcm_out is not None and (pcm_out.dtype != torch.int16 or not pcm_out.is_cuda or pcm_out.shape[0] != B
+                                    or pcm_out.shape[1] < max_n or not pcm_out.is_contiguous()):
+            raise ValueError("pcm_out must be a contiguous (B, >= max_n) int16 CUDA tensor")
         if B > self.GROUP and self._folded_ok:
             dev = h.device
             n_host = list(n_host) if n_host is not None else n_dev.cpu().tolist()
@@ -248,19 +254,25 @@ class QPNet(nn.Module):
                 ids = order[c:c + self.GROUP]
                 idx = torch.tensor(ids, dtype=torch.int64, device=dev)
                 sub_max = max(n_host[b] for b in ids)
+                sub_pcm = None if pcm_out is None else torch.zeros((len(ids), max(sub_max, 1)), dtype=torch.int16, device=dev)
                 o, lg = self._generate_launch(seed[idx], h[idx], d[idx], n_dev[idx], sub_max, qmode,
                                               None if uniforms is None else uniforms.to(dev)[idx],
                                               None if force is None else force.to(dev)[idx], return_logits, check_status,
-                                              idx.to(torch.int32))
+                                              idx.to(torch.int32) if utt_ids is None else utt_ids.to(dev)[idx].to(torch.int32),
+                                              sub_pcm)
                 launches += self.last_launches
                 out[idx, :o.shape[1]] = o
+                if pcm_out is not None:
+                    pcm_out[idx, :sub_pcm.shape[1]] = sub_pcm
                 if return_logits:
                     logits[idx, :sub_max] = lg
             self.last_launches = launches
             return out, logits
-        return self._generate_launch(seed, h, d, n_dev, max_n, qmode, uniforms, force, return_logits, check_status, None)
+        return self._generate_launch(seed, h, d, n_dev, max_n, qmode, uniforms, force, return_logits, check_status, utt_ids,
+                                     pcm_out)
 
-    def _generate_launch(self, seed, h, d, n_dev, max_n, qmode, uniforms, force, return_logits, check_status, utt_ids):
+    def _generate_launch(self, seed, h, d, n_dev, max_n, qmode, uniforms, force, return_logits, check_status, utt_ids,
+                         pcm_out=None):
         """One qp_generate call (<= 128 utterances on the tcgen05 cluster kernel, any number on the generic one)."""
         params = self._tensors()
         dev = params[0].device
@@ -291,6 +303,8 @@ class QPNet(nn.Module):
         if utt_ids is not None:
             utt_ids = utt_ids.to(dev).contiguous().to(torch.int32)
             a.utt_ids = utt_ids.data_ptr()
+        if pcm_out is not None:
+            a.out_pcm, a.ld_out_pcm = pcm_out.data_ptr(), ops._ld(pcm_out)
         logits = None
         if return_logits:
             logits = torch.zeros((B, max_n, self.n_quantize), dtype=torch.float32, device=dev)

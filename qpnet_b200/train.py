@@ -113,8 +113,11 @@ class FlatAdam:
     hand-written backward returns, ``qpnet.flat_layout``), so ``state_dict()`` / ``load_state_dict()`` of the model keep
     working and the step is a single element-wise pass instead of 216 tensor updates.  ``state_dict()`` /
     ``load_state_dict()`` speak torch.optim.Adam's format, so the reference's checkpoints resume here and ours resume
-    there (qpnet_train.py:346-352, 481-489).  Construct it AFTER ``model.cuda()``: moving the model re-allocates its
-    parameters and drops the flat buffer."""
+    there (qpnet_train.py:346-352, 481-489).  One step counter serves the whole model (torch counts per tensor that has
+    seen a gradient; identical as long as every live tensor gets its gradient from the first step on, which the
+    hand-written backward guarantees -- the dead last ``resA_1x1`` only ever sees zeros, and a zero gradient on zero
+    moments is a zero update).  Construct it AFTER ``model.cuda()``: moving the model re-allocates its parameters and
+    drops the flat buffer."""
 
     def __init__(self, params, lr: float = 1e-4, betas=(0.9, 0.999), eps: float = 1e-8):
         from .qpnet import flat_layout

@@ -390,9 +390,11 @@ def test_generator_is_deterministic_and_batch_independent(dev):
         assert np.array_equal(solo[0], r)
 
 
-def test_generator_large_batch_is_dealt_to_launches_of_128(dev):
+def test_generator_large_batch_is_dealt_to_launches_of_128(dev, monkeypatch):
     """More than 128 utterances of the SI default widths: dealt to launches of 128, longest first (host wrapper).  Every
-    utterance must come out exactly as in a solo call -- same Philox stream (utt_ids), same arithmetic."""
+    utterance must come out exactly as in a solo call -- same Philox stream (utt_ids), same arithmetic (the kernel is
+    pinned: by default a solo call runs on the mma.sync kernel, whose bf16 rounding differs from the tcgen05 one)."""
+    monkeypatch.setenv("QPNET_GEN_KERNEL", "f3")
     a = orc.Arch()
     p = orc.init_params(a, 8, 0.05)
     m = _model({}, p, dev)
@@ -731,8 +733,11 @@ def test_flat_adam_matches_torch_adam_and_resumes_reference_checkpoint(dev, tmp_
     assert ck.load_checkpoint(os.path.join(gold, "checkpoint-7.pkl"), r1, t1) == 7
     assert ck.load_checkpoint(os.path.join(gold, "checkpoint-7.pkl"), r2, t2) == 7
     assert t2.steps == int(t1.state_dict()["state"][0]["step"])
-    for q1, q2 in zip(r1.parameters(), r2.parameters()):
+    have_state = set(torch.load(os.path.join(gold, "checkpoint-7.pkl"), weights_only=False)["optimizer"]["state"])
+    for i, (q1, q2) in enumerate(zip(r1.parameters(), r2.parameters())):
         assert torch.equal(q1, q2)
+        if i not in have_state:     # the dead last residual projection never has a gradient (C7): torch keeps no state for it
+            continue                # (FlatAdam counts ONE step for the whole model, torch one per tensor that saw a gradient)
         g = torch.randn(q1.shape, generator=gen).to(dev) * 1e-2
         q1.grad, q2.grad = g.clone(), g.clone()
     t1.step()

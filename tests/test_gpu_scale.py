@@ -237,3 +237,51 @@ def test_training_step_bf16_tensor_cores_adam_update(dev):
     for _ in range(5):
         loss = tr.step(x.to(dev), h.to(dev), d.to(dev), t.to(dev), bl)
     assert float(loss) < l0
+
+
+@pytest.mark.parametrize("kernel,B", [("f3", 40), ("fold2", 5), ("generic", 5)])
+def test_generator_pcm16_output_stage(dev, monkeypatch, kernel, B):
+    """The generator's PCM output stage (QpGenerateArgs.out_pcm; qpnet_decode.py:315-318: decode_mu_law * 32768, clipped,
+    int16): equal, sample for sample, to the oracle's write-out of the symbols the same launch produced -- on the tcgen05
+    kernel (in-kernel table) and on the kernels the C ABI post-processes."""
+    a = orc.Arch()
+    p = orc.init_params(a, 51, 0.05)
+    frames = 1
+    x, h, d, _ = _forced_case(a, B, frames, 1.0, 1, 1900)
+    n = frames * a.U - 1
+    monkeypatch.setenv("QPNET_GEN_KERNEL", kernel)
+    m = _model({}, p, dev)
+    m.philox_seed = 3
+    pcm = torch.zeros((B, n), dtype=torch.int16, device=dev)
+    seed = torch.full((B,), a.Q // 2, dtype=torch.int64, device=dev)
+    sym, _ = m.generate_device(seed, h.to(dev), torch.from_numpy(d).to(dev), torch.full((B,), n, dtype=torch.int32, device=dev), n,
+                               pcm_out=pcm)
+    sym, pcm = sym.cpu().numpy(), pcm.cpu().numpy()
+    assert sym.min() >= 0 and sym.max() < a.Q and len(np.unique(sym)) > 16
+    for b in range(B):
+        np.testing.assert_array_equal(pcm[b], orc.decode_pcm16(sym[b, :n].astype(np.int64)))
+
+
+def test_deep_preset_full_width_on_tcgen05_generator(dev, monkeypatch):
+    """`Rd10Rr3Ed4Er1` (param_model.py:65-71: 30 fixed blocks with dilations up to 512 + 4 adaptive ones) at FULL width
+    (512 / 256 channels) on the tcgen05 generator (any depth up to QP_MAX_LAYERS; past-tap rings up to 1024 slots for the
+    fixed blocks): per-step logits under forced symbols against the oracle.  The 0.06 bar of the 16-block model scaled
+    by sqrt(34 / 16) like the other deep-preset tests; 620 steps read the 512-deep fixed rings back."""
+    torch.set_num_threads(os.cpu_count() or 1)
+    kw = dict(dilationF_depth=10, dilationF_repeat=3, dilationA_depth=4, dilationA_repeat=1)
+    a = orc.Arch(**kw)
+    assert len(a.dilF) == 30 and max(a.dilF) == 512
+    p = orc.init_params(a, 19, 0.05)
+    B, frames, steps = 3, 6, 620
+    x, h, d, forced = _forced_case(a, B, frames, 1.0, steps, 2100)
+    lg = []
+    with torch.no_grad():
+        orc.generate(a, p, x, h, [steps] * B, d, mode="argmax", force=forced, logits_out=lg, max_steps=steps)
+    want = torch.stack(lg, dim=1)
+    monkeypatch.setenv("QPNET_GEN_KERNEL", "f3")
+    m = _model(kw, p, dev)
+    from qpnet_b200 import _lib
+    res, got = m.batch_fast_generate(x, h, [steps] * B, d, None, "argmax", False, force=forced, return_logits=True)
+    err = (got.cpu() - want).abs().amax(dim=(0, 2))
+    print(f"deep preset, full width, f3: max |dlogit| = {float(err.max()):.4f} (steps 0-99 {float(err[:100].max()):.4f}, last 100 {float(err[-100:].max()):.4f})")
+    assert float(err.max()) < 0.06 * (34 / 16) ** 0.5, float(err.max())

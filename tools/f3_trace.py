@@ -49,14 +49,18 @@ def main():
         torch.cuda.synchronize()
         print(f"kernel ms {e0.elapsed_time(e1):.2f}  us/step {e0.elapsed_time(e1) * 1e3 / (max(n_list) + 16):.2f}")
     nphase, nev = L + 4, 24
-    n = 8 * nphase * nev
+    n_g = 128 * nphase * 4
+    n = 8 * nphase * nev + n_g
     buf = (C.c_longlong * n)()
     fn = _lib.lib.qp_debug_gen_trace
     fn.restype = C.c_int
     fn.argtypes = [C.POINTER(_lib.QpArch), C.c_int32, C.c_int32, C.c_void_p, C.c_size_t, C.POINTER(C.c_longlong), C.c_int32, C.c_void_p]
     ws = m._last_ws
     fn(m._arch, args.utts, ops.max_ceil(d64), ws.data_ptr(), ws.numel(), buf, n, None)
-    tr = np.array(buf, dtype=np.int64).reshape(8, nphase, nev)
+    allbuf = np.array(buf, dtype=np.int64)
+    tr = allbuf[:8 * nphase * nev].reshape(8, nphase, nev)
+    gt = allbuf[8 * nphase * nev:].reshape(128, nphase, 4).astype(np.float64)
+    gt[gt == 0] = np.nan
     labels = ["pub(j-1)->staged", "staged->mma", "mma issue", "commit->TMEM seen", "ld+send", "send->arrived", "finish+publish"]
     acc = np.zeros(7)
     cnt = 0
@@ -74,9 +78,9 @@ def main():
         if st <= 2:
             print(f"final+heads+sampling+block0: {tr[st + 1, 0, 5] - tr[st, L - 1, 5]} cycles")
     # full timeline of two phases of one step, relative to the moment the MMA thread saw z_{j-1}
-    names = {0: "MMA z seen", 1: "MMA gate committed", 7: "MMA RK+H issued", 8: "MMA x tile seen", 9: "MMA past tile seen", 10: "MMA phase issued",
+    names = {0: "MMA z seen", 1: "MMA z-products committed", 8: "MMA x tile seen", 9: "MMA past tile seen", 10: "MMA phase issued",
              2: "ET tile in TMEM", 3: "ET sent", 4: "ET arrived", 5: "ET z published", 11: "PZ z buffer free", 12: "PZ first piece fresh", 6: "PZ z staged",
-             13: "EU tile in TMEM", 14: "EU sent", 15: "EU arrived", 16: "EU x published", 17: "PX past buffer free", 18: "PX past staged",
+             13: "EU tile in TMEM", 14: "EU sent", 15: "EU arrived", 16: "EU x published", 17: "PX past buffer free", 18: "PX past copies issued",
              19: "PX x buffer free", 20: "PX first x piece fresh", 21: "PX x staged"}
     for j in (5, 6, 13):
         e = tr[2, j]
@@ -86,6 +90,15 @@ def main():
             print(f"    {tstamp - base:8d}  {names[ev]}")
     acc /= cnt
     print("mean over blocks 1..L-1 of 6 steps: " + "  ".join(f"{lab} {v:.0f}" for lab, v in zip(labels, acc)) + f"  | phase {acc.sum():.0f}")
+    # every CTA on the global clock (ns), one step: how far apart do the CTAs publish / see a complete tile?
+    print(f"--- step {args.step + 2} on %globaltimer (ns; 1 ns ~ 1.9 cycles): per phase over all CTAs")
+    t0 = np.nanmin(gt[:, 1, 1])
+    for j in range(1, L):
+        pub, stg, arr, xpub = gt[:, j, 0], gt[:, j, 1], gt[:, j, 2], gt[:, j, 3]
+        nxt = gt[:, j + 1, 1] if j + 1 < L + 1 else stg
+        print(f"blk{j:02d} staged {np.nanmin(stg) - t0:8.0f} .. {np.nanmax(stg) - t0:8.0f} | arrived {np.nanmin(arr) - t0:8.0f} .. {np.nanmax(arr) - t0:8.0f} | "
+              f"z published {np.nanmin(pub) - t0:8.0f} .. {np.nanmax(pub) - t0:8.0f} (slowest CTA {int(np.nanargmax(pub))}) | x published {np.nanmin(xpub) - t0:8.0f} .. {np.nanmax(xpub) - t0:8.0f} | "
+              f"next staged - last published {np.nanmin(nxt) - np.nanmax(pub):6.0f} .. {np.nanmax(nxt) - np.nanmax(pub):6.0f}")
     tot = np.mean([tr[st + 1, 0, 5] - tr[st, 0, 5] for st in range(1, 7)])
     tail = np.mean([tr[st + 1, 0, 5] - tr[st, L - 1, 5] for st in range(1, 7)])
     print(f"step total (mean) {tot:.0f} cycles; after the last gate (final skip, heads, sampling, block 0): {tail:.0f}")
