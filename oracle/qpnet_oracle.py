@@ -324,9 +324,16 @@ def generate(a: Arch, p, seed_x, h, n_samples_list, d, mode="sampling", uniforms
     k == 0 selecting the OLDEST entry (python index 0, caveat C4).
     ``force``: optional (B, steps) symbols fed back instead of the drawn ones
     (teacher-forced generator check).  ``uniforms``: (B, steps) for mode="sampling".
+    Runs on the device the parameters live on (CPU for parity; bench.py also times this port with
+    CUDA tensors as the "reference's own eager-PyTorch GPU path on this box" row).
     """
     B = len(n_samples_list)
-    h = torch.as_tensor(h, dtype=torch.float32)
+    dev = p["causal.conv.weight"].device
+    h = torch.as_tensor(h, dtype=torch.float32).to(dev)
+    if uniforms is not None:
+        uniforms = torch.as_tensor(uniforms).to(dev)
+    if force is not None:
+        force = torch.as_tensor(force).to(dev)
     d_np = np.asarray(d, dtype=np.float64 if f64_index else np.float32)
     T = max(n_samples_list) if max_steps is None else max_steps
     M = int(np.nanmax(np.ceil(d_np)))                        # qpnet.py:347-350
@@ -337,7 +344,7 @@ def generate(a: Arch, p, seed_x, h, n_samples_list, d, mode="sampling", uniforms
     dils = list(a.dilF) + list(a.dilA)
     depth = list(a.dilF) + [dl * M for dl in a.dilA]         # look-back bound per layer input
     # ---- priming: constant signal ------------------------------------------------------
-    sym = torch.full((B, 2), half, dtype=torch.int64)
+    sym = torch.full((B, 2), half, dtype=torch.int64, device=dev)
     x0 = torch.stack([_embed(p, sym[b])[0] for b in range(B)])        # (B, C)
     hist = []                                                # hist[l]: list of (B, C), newest last
     cur = x0
@@ -348,9 +355,9 @@ def generate(a: Arch, p, seed_x, h, n_samples_list, d, mode="sampling", uniforms
         _, _, res = _gate(p, kind, i, cur, cur, h0)
         cur = res + cur
     # ---- sample loop -------------------------------------------------------------------
-    prev = torch.full((B,), half, dtype=torch.int64)
-    new = torch.as_tensor(seed_x, dtype=torch.int64).reshape(B, -1)[:, -1].clone()
-    out = torch.zeros((B, T), dtype=torch.int64)
+    prev = torch.full((B,), half, dtype=torch.int64, device=dev)
+    new = torch.as_tensor(seed_x, dtype=torch.int64).reshape(B, -1)[:, -1].clone().to(dev)
+    out = torch.zeros((B, T), dtype=torch.int64, device=dev)
     for i in range(T):
         pair = torch.stack([prev, new], dim=1)
         cur = torch.stack([_embed(p, pair[b])[0] for b in range(B)])
@@ -387,6 +394,7 @@ def generate(a: Arch, p, seed_x, h, n_samples_list, d, mode="sampling", uniforms
         out[:, i] = s
         prev = new
         new = s if force is None else torch.as_tensor(force[:, i], dtype=torch.int64)
+    out = out.cpu()
     return [out[b, : min(n_samples_list[b], T)].numpy() for b in range(B)]
 
 

@@ -34,7 +34,7 @@ def main():
     for _ in range(args.reps):
         t0 = torch.cuda.Event(enable_timing=True); t1 = torch.cuda.Event(enable_timing=True)
         t0.record()
-        out, _ = m.generate_device(seed, hd, d64, n_dev, max(n_list))
+        out, _ = m.generate_device(seed, hd, d64, n_dev, max(n_list), n_host=n_list)
         t1.record()
         torch.cuda.synchronize()
         print("ms", t0.elapsed_time(t1), "us/step", t0.elapsed_time(t1) * 1e3 / (max(n_list) + 1), "sym[0,:8]", out[0, :8].tolist())
