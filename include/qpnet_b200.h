@@ -142,6 +142,16 @@ int qp_backward(const QpArch* arch, const float* const* tensors_host, const int6
                 int32_t M, const float* dlogits, float* const* grads_host, void* ws,
                 size_t ws_bytes, uint32_t flags, void* stream);
 
+/* The same backward in stages, for data-parallel callers that overlap the gradient all-reduce with the rest of the
+ * backward (the reference gets this exchange implicitly from nn.DataParallel's reduce_add, qpnet_train.py:416-423):
+ * stage 0 = the two head layers, stage s in [1, L] = residual block L - s (last block first), stage L + 1 = causal layer
+ * and upsampler.  Run [stage_begin, stage_end) in ascending, non-overlapping ranges starting at 0; when a call returns,
+ * the launches that write the gradients of its stages are enqueued on `stream` (record an event, reduce, carry on). */
+int qp_backward_range(const QpArch* arch, const float* const* tensors_host, const int64_t* x,
+                      const float* h, const float* d, int32_t B, int32_t T, int32_t F, int32_t bl,
+                      int32_t M, const float* dlogits, float* const* grads_host, void* ws,
+                      size_t ws_bytes, uint32_t flags, int32_t stage_begin, int32_t stage_end, void* stream);
+
 /* fused softmax cross-entropy over (rows, Q) logits (qpnet_train.py:426-430,526):
  * loss_sum[0] += sum_r -log softmax(logits[r])[target[r]];  dlogits = (p - onehot)*scale.
  * A target outside [0, Q) (the reference asserts it away, qpnet_train.py:524) turns the loss into NaN. */

@@ -57,6 +57,8 @@ SIGNATURES = {
                              _U32, _P]),
     "qp_backward": (C.c_int, [C.POINTER(QpArch), C.POINTER(_P), _P, _P, _P, _I32, _I32, _I32, _I32, _I32, _P,
                               C.POINTER(_P), _P, _SZ, _U32, _P]),
+    "qp_backward_range": (C.c_int, [C.POINTER(QpArch), C.POINTER(_P), _P, _P, _P, _I32, _I32, _I32, _I32, _I32, _P,
+                                    C.POINTER(_P), _P, _SZ, _U32, _I32, _I32, _P]),
     "qp_cross_entropy": (C.c_int, [_P, _P, _I64, _I32, _F32, _P, _P, _P]),
     "qp_adam_step": (C.c_int, [_P, _P, _P, _P, _I64, _F64, _F64, _F64, _F64, _I32, _F64, _P]),
     "qp_generate_workspace_bytes": (_SZ, [C.POINTER(QpArch), _I32, _I32]),

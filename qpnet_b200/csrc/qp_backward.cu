@@ -87,22 +87,26 @@ int bwd_tc_mask() {
 }
 
 // tc: TF32 tensor-core contractions (the backward of the bf16 training path); false: exact fp32 SIMT
+// Stages: 0 = the two head layers (+ the buffers the blocks accumulate into), 1 .. L = residual block L - stage (last
+// block first), L + 1 = causal layer and upsampler.  [s_begin, s_end) selects a range: a data-parallel caller runs the
+// backward in a few ranges and starts all-reducing the gradients of a finished range while the next one computes; every
+// stage leaves its gradients in the reference's tensors.
 int tf_backward_f32(const QpArch* arch, const float* const* tensors, const int64_t* x, const float* h,
-                    const TfPlan& p, const float* dlogits, float* const* grads, bool tc, cudaStream_t st) {
+                    const TfPlan& p, const float* dlogits, float* const* grads, bool tc, cudaStream_t st, int s_begin, int s_end) {
   const PackedDims& pd = p.pd;
   const TensorMap tm = tensor_map(arch);
   const int C = pd.C, S = pd.S, Q = pd.Q, A = pd.A, B = p.B, L0 = p.L0, bl = p.bl, L = pd.L;
   const int ntens = tm.count();
   for (int i = 0; i < ntens; ++i)
     if (!grads[i]) return set_error(QP_EINVAL, "backward: gradient tensor %d is NULL", i);
-  QP_CUDA(cudaMemcpyAsync((void*)p.gtab, grads, sizeof(float*) * ntens, cudaMemcpyHostToDevice, st));
+  if (s_begin == 0) QP_CUDA(cudaMemcpyAsync((void*)p.gtab, grads, sizeof(float*) * ntens, cudaMemcpyHostToDevice, st));
   // bf16 operands on tcgen05 for the residual blocks (the head stays on the TF32 kernels: 2 % of the work)
   const int mask = (tc && p.ones_col >= 0) ? bwd_tc_mask() : 0;
   const bool tc_w = mask & 1, tc_dz = mask & 2, tc_dx = mask & 4;
   const int Kgp = p.Kgp;
 
   // ---- head -------------------------------------------------------------------------
-  {
+  if (s_begin <= 0 && s_end > 0) {
     WgradArgs w = {};
     w.p[0] = mk(dlogits, (int64_t)bl * Q, Q, nullptr, 0, bl, Q); w.np = 1;
     w.q[0] = mk(p.H1, (int64_t)bl * S, S, nullptr, 0, bl, S, 1); w.nq = 1;
@@ -125,23 +129,25 @@ int tf_backward_f32(const QpArch* arch, const float* const* tensors, const int64
     g1.B = B; g1.n_rows = bl; g1.N = S; g1.out = p.dskip; g1.out_bstride = (int64_t)bl * S; g1.ldo = S;
     g1.mask = p.skipsum; g1.mask_bstride = (int64_t)bl * S; g1.ldmask = S;
     if (int e = launch_gemm<EPI_PLAIN>(g1, st, tc)) return e;
-  }
-  QP_CUDA(cudaMemsetAsync(p.dHup, 0, sizeof(float) * (size_t)B * L0 * A, st));
-  if (mask) {
-    QP_CUDA(cudaMemsetAsync(p.dbskip, 0, sizeof(float) * S, st));
-    if (int e = tc::f32_to_bf16_colsum(p.dskip, (long long)B * bl, S, p.dskip_bf, p.dbskip, st)) return e;
-  }
-  if (tc_w) {   // the tcgen05 weight-gradient kernel accumulates its row splits into zeroed outputs
-    QP_CUDA(cudaMemsetAsync(p.dW.Wg, 0, sizeof(float) * pd.wg_elems() * L, st));
-    QP_CUDA(cudaMemsetAsync(p.dW.bg, 0, sizeof(float) * (size_t)2 * C * L, st));
-    QP_CUDA(cudaMemsetAsync(p.dW.Wrs, 0, sizeof(float) * pd.wrs_elems() * L, st));
-    QP_CUDA(cudaMemsetAsync(p.dW.brs, 0, sizeof(float) * (size_t)(C + S) * L, st));
+    QP_CUDA(cudaMemsetAsync(p.dHup, 0, sizeof(float) * (size_t)B * L0 * A, st));
+    if (mask) {
+      QP_CUDA(cudaMemsetAsync(p.dbskip, 0, sizeof(float) * S, st));
+      if (int e = tc::f32_to_bf16_colsum(p.dskip, (long long)B * bl, S, p.dskip_bf, p.dbskip, st)) return e;
+    }
+    if (tc_w) {   // the tcgen05 weight-gradient kernel accumulates its row splits into zeroed outputs
+      QP_CUDA(cudaMemsetAsync(p.dW.Wg, 0, sizeof(float) * pd.wg_elems() * L, st));
+      QP_CUDA(cudaMemsetAsync(p.dW.bg, 0, sizeof(float) * (size_t)2 * C * L, st));
+      QP_CUDA(cudaMemsetAsync(p.dW.Wrs, 0, sizeof(float) * pd.wrs_elems() * L, st));
+      QP_CUDA(cudaMemsetAsync(p.dW.brs, 0, sizeof(float) * (size_t)(C + S) * L, st));
+    }
   }
 
   // ---- residual blocks, last to first -----------------------------------------------
-  const float* dXnext = nullptr;
   float* pong[2] = {p.dXa, p.dXb};
   for (int l = L - 1; l >= 0; --l) {
+    const int stage = L - l;
+    if (stage < s_begin || stage >= s_end) continue;
+    const float* dXnext = l == L - 1 ? nullptr : pong[(l + 1) & 1];   // dX of the block above (this block's output gradient)
     const int Lin = p.Lin[l], sh = p.shift[l], n = Lin - sh;
     const int* rowmap = l >= pd.nF ? p.pastrow[l - pd.nF] : nullptr;
     float* Wrs = p.W.Wrs + pd.wrs_elems() * l;
@@ -228,7 +234,7 @@ int tf_backward_f32(const QpArch* arch, const float* const* tensors, const int64
         g.resid = dXnext; g.resid_bstride = (long long)n * C;
         g.dh = p.dHup; g.dh_bstride = (long long)L0 * A; g.dh_off = L0 - n;
         if (int e = tc::gemm_dx(g, st)) return e;
-        dXnext = dX;
+        if (int e = unpack_grads_layer_f32(arch, p.gtab, p.dW, l, st)) return e;
         continue;
       }
       GemmArgs g = {};
@@ -239,10 +245,12 @@ int tf_backward_f32(const QpArch* arch, const float* const* tensors, const int64
       g.resid = dXnext; g.resid_bstride = (int64_t)n * C; g.ldresid = C;
       g.dh = p.dHup; g.dh_bstride = (int64_t)L0 * A; g.dh_off = L0 - n;
       if (int e = launch_gemm<EPI_DX>(g, st, tc)) return e;
-      dXnext = dX;
+      if (int e = unpack_grads_layer_f32(arch, p.gtab, p.dW, l, st)) return e;
     }
   }
   // ---- front end ----------------------------------------------------------------------
+  if (L + 1 < s_begin || L + 1 >= s_end) return QP_OK;
+  const float* dXnext = pong[0];                                      // dX of block 0 = gradient of the causal layer's output
   QP_CUDA(cudaMemsetAsync(p.dW.E0, 0, sizeof(float) * (size_t)Q * C, st));
   QP_CUDA(cudaMemsetAsync(p.dW.E1, 0, sizeof(float) * (size_t)Q * C, st));
   embed_grad_kernel<<<dim3(L0, B), 128, 0, st>>>(x, p.T, L0, C, Q, dXnext, p.dW.E0, p.dW.E1);
@@ -257,7 +265,7 @@ int tf_backward_f32(const QpArch* arch, const float* const* tensors, const int64
   QP_CUDA(cudaMemsetAsync(grads[tm.up_b()], 0, sizeof(float), st));
   upsample_grad_kernel<<<pd.U, 64, 0, st>>>(p.dHup, h, B, A, p.F, pd.U, L0, grads[tm.up_w()], grads[tm.up_b()]);
   QP_LAUNCH_CHECK();
-  return unpack_grads_f32(arch, p.gtab, p.dW, st);
+  return unpack_grads_front_f32(arch, p.gtab, p.dW, st);
 }
 
 }  // namespace qp
@@ -277,7 +285,26 @@ int qp_backward(const QpArch* arch, const float* const* tensors_host, const int6
   TfPlan p;
   size_t need = make_tf_plan(arch, B, T, F, bl, M, flags, ws, ws_bytes, &p);
   if (need > ws_bytes) return set_error(QP_EWORKSPACE, "backward: workspace %zu < %zu bytes", ws_bytes, need);
-  return tf_backward_f32(arch, tensors_host, x, h, p, dlogits, grads_host, (flags & QP_F_BF16) != 0, (cudaStream_t)stream);
+  return tf_backward_f32(arch, tensors_host, x, h, p, dlogits, grads_host, (flags & QP_F_BF16) != 0, (cudaStream_t)stream, 0,
+                         arch->n_fixed + arch->n_adaptive + 2);
+}
+
+int qp_backward_range(const QpArch* arch, const float* const* tensors_host, const int64_t* x, const float* h, const float* d,
+                      int32_t B, int32_t T, int32_t F, int32_t bl, int32_t M, const float* dlogits, float* const* grads_host,
+                      void* ws, size_t ws_bytes, uint32_t flags, int32_t stage_begin, int32_t stage_end, void* stream) {
+  if (int e = check_device()) return e;
+  if (int e = check_arch(arch)) return e;
+  QP_REQUIRE(tensors_host && x && h && d && dlogits && grads_host && ws, "backward: NULL pointer");
+  QP_REQUIRE(flags & QP_F_SAVE, "backward: the forward pass must have run with QP_F_SAVE");
+  const int n_stages = arch->n_fixed + arch->n_adaptive + 2;
+  QP_REQUIRE(stage_begin >= 0 && stage_begin < stage_end && stage_end <= n_stages, "backward: stage range [%d, %d) outside [0, %d)",
+             stage_begin, stage_end, n_stages);
+  reset_launch_count();
+  TfPlan p;
+  size_t need = make_tf_plan(arch, B, T, F, bl, M, flags, ws, ws_bytes, &p);
+  if (need > ws_bytes) return set_error(QP_EWORKSPACE, "backward: workspace %zu < %zu bytes", ws_bytes, need);
+  return tf_backward_f32(arch, tensors_host, x, h, p, dlogits, grads_host, (flags & QP_F_BF16) != 0, (cudaStream_t)stream,
+                         stage_begin, stage_end);
 }
 
 }  // extern "C"

@@ -17,10 +17,11 @@ int upload_tensor_table(const QpArch* arch, const float* const* tensors_host, co
 // One thread per element of Wg (all layers).  GRAD=false: params -> packed.
 // GRAD=true: packed grads -> param grads (aux pad columns are skipped).
 template <bool GRAD>
-__global__ void pack_wg_kernel(TensorMap tm, PackedDims pd, const float* const* __restrict__ tab, float* __restrict__ Wg) {
-  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void pack_wg_kernel(TensorMap tm, PackedDims pd, const float* const* __restrict__ tab, float* __restrict__ Wg,
+                               size_t i_begin, size_t i_end) {
+  size_t i = i_begin + (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   size_t per = pd.wg_elems();
-  if (i >= per * pd.L) return;
+  if (i >= i_end) return;
   int l = (int)(i / per);
   size_t r = i % per;
   int row = (int)(r / pd.Kg), k = (int)(r % pd.Kg);
@@ -100,11 +101,74 @@ __global__ void pack_small_kernel(TensorMap tm, PackedDims pd, const float* cons
   }
 }
 
+// packed gradients of ONE residual block -> the reference's tensors (gate biases, [res | skip] weights and biases)
+__global__ void unpack_small_layer_kernel(TensorMap tm, PackedDims pd, const float* const* __restrict__ tab, PackedF32 P, int l) {
+  const int C = pd.C, S = pd.S;
+  const size_t n_bg = (size_t)2 * C, n_wrs = (size_t)(C + S) * C, n_brs = (size_t)(C + S);
+  const bool fixed = l < pd.nF;
+  const int j = fixed ? l : l - pd.nF;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_bg + n_wrs + n_brs; i += (size_t)gridDim.x * blockDim.x) {
+    if (i < n_bg) {
+      const int row = (int)i, c = row >> 1, g = row & 1;
+      const float v = P.bg[(size_t)l * 2 * C + i];
+      if (fixed) { ((float*)tab[tm.dilF_b(g, j)])[c] = v; ((float*)tab[tm.auxF_b(g, j)])[c] = v; }
+      else { ((float*)tab[tm.dilA_bC(g, j)])[c] = v; ((float*)tab[tm.dilA_bP(g, j)])[c] = v; ((float*)tab[tm.auxA_b(g, j)])[c] = v; }
+      continue;
+    }
+    size_t k = i - n_bg;
+    if (k < n_wrs) {
+      const int row = (int)(k / C), col = (int)(k % C);
+      float* q;
+      if (fixed) q = row < C ? (float*)tab[tm.resF_w(j)] + (size_t)row * C + col : (float*)tab[tm.skipF_w(j)] + (size_t)(row - C) * C + col;
+      else q = row < C ? (float*)tab[tm.resA_w(j)] + (size_t)row * C + col : (float*)tab[tm.skipA_w(j)] + (size_t)(row - C) * C + col;
+      *q = P.Wrs[(size_t)l * n_wrs + k];
+      continue;
+    }
+    k -= n_wrs;
+    const int row = (int)k;
+    float* q;
+    if (fixed) q = row < C ? (float*)tab[tm.resF_b(j)] + row : (float*)tab[tm.skipF_b(j)] + (row - C);
+    else q = row < C ? (float*)tab[tm.resA_b(j)] + row : (float*)tab[tm.skipA_b(j)] + (row - C);
+    *q = P.brs[(size_t)l * n_brs + k];
+  }
+}
+
+// packed causal-layer table gradients (E0, E1) -> causal.conv.weight (C, Q, 2)
+__global__ void unpack_front_kernel(TensorMap tm, PackedDims pd, const float* const* __restrict__ tab, PackedF32 P) {
+  const int C = pd.C, Q = pd.Q;
+  const size_t n_e = (size_t)Q * C;
+  for (size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x; k < 2 * n_e; k += (size_t)gridDim.x * blockDim.x) {
+    const int tap = k >= n_e;
+    const size_t r = tap ? k - n_e : k;
+    const int q = (int)(r / C), c = (int)(r % C);
+    ((float*)tab[tm.causal_w()])[((size_t)c * Q + q) * 2 + tap] = (tap ? P.E1 : P.E0)[r];
+  }
+}
+
+int unpack_grads_layer_f32(const QpArch* arch, float* const* dev_grad_table, PackedF32 g, int l, cudaStream_t stream) {
+  TensorMap tm = tensor_map(arch);
+  PackedDims pd = packed_dims(arch);
+  const size_t per = pd.wg_elems();
+  pack_wg_kernel<true><<<(unsigned)((per + 255) / 256), 256, 0, stream>>>(tm, pd, (const float* const*)dev_grad_table, g.Wg, per * l, per * (l + 1));
+  QP_LAUNCH_CHECK();
+  unpack_small_layer_kernel<<<148, 256, 0, stream>>>(tm, pd, (const float* const*)dev_grad_table, g, l);
+  QP_LAUNCH_CHECK();
+  return QP_OK;
+}
+
+int unpack_grads_front_f32(const QpArch* arch, float* const* dev_grad_table, PackedF32 g, cudaStream_t stream) {
+  TensorMap tm = tensor_map(arch);
+  PackedDims pd = packed_dims(arch);
+  unpack_front_kernel<<<148, 256, 0, stream>>>(tm, pd, (const float* const*)dev_grad_table, g);
+  QP_LAUNCH_CHECK();
+  return QP_OK;
+}
+
 int pack_f32(const QpArch* arch, const float* const* dev_table, PackedF32 out, cudaStream_t stream) {
   TensorMap tm = tensor_map(arch);
   PackedDims pd = packed_dims(arch);
   size_t n = pd.wg_elems() * pd.L;
-  pack_wg_kernel<false><<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(tm, pd, dev_table, out.Wg);
+  pack_wg_kernel<false><<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(tm, pd, dev_table, out.Wg, 0, n);
   QP_LAUNCH_CHECK();
   pack_small_kernel<false><<<148 * 4, 256, 0, stream>>>(tm, pd, dev_table, out);
   QP_LAUNCH_CHECK();
@@ -115,7 +179,7 @@ int unpack_grads_f32(const QpArch* arch, float* const* dev_grad_table, PackedF32
   TensorMap tm = tensor_map(arch);
   PackedDims pd = packed_dims(arch);
   size_t n = pd.wg_elems() * pd.L;
-  pack_wg_kernel<true><<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(tm, pd, (const float* const*)dev_grad_table, g.Wg);
+  pack_wg_kernel<true><<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(tm, pd, (const float* const*)dev_grad_table, g.Wg, 0, n);
   QP_LAUNCH_CHECK();
   pack_small_kernel<true><<<148 * 4, 256, 0, stream>>>(tm, pd, (const float* const*)dev_grad_table, g);
   QP_LAUNCH_CHECK();

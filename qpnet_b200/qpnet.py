@@ -77,17 +77,18 @@ def _stream():
     return torch.cuda.current_stream().cuda_stream
 
 
-def flat_layout(tensors):
-    """Element offsets of ``tensors`` inside one flat buffer, each piece starting on a 16-byte boundary."""
-    offs, off = [], 0
-    for t in tensors:
-        offs.append(off)
-        off += (t.numel() + 3) // 4 * 4
+def flat_layout(tensors, order=None):
+    """Element offsets of ``tensors`` (indexed like ``tensors``) inside one flat buffer, each piece starting on a 16-byte
+    boundary.  ``order``: the sequence in which the tensors are laid out (default: as given)."""
+    offs, off = [0] * len(tensors), 0
+    for i in (range(len(tensors)) if order is None else order):
+        offs[i] = off
+        off += (tensors[i].numel() + 3) // 4 * 4
     return offs, off
 
 
-def flat_grad_views(tensors):
-    offs, total = flat_layout(tensors)
+def flat_grad_views(tensors, order=None):
+    offs, total = flat_layout(tensors, order)
     flat = torch.zeros(total, dtype=torch.float32, device=tensors[0].device)
     return flat, [flat[o:o + t.numel()].view(t.shape) for o, t in zip(offs, tensors)]
 
@@ -128,12 +129,20 @@ class _TeacherForced(torch.autograd.Function):
         dlogits = dlogits.contiguous().float()
         # every gradient is a view of ONE flat fp32 buffer (16-byte aligned pieces): autograd adopts the views as
         # p.grad, and the data-parallel bucket all-reduces the buffer in place instead of copying 216 tensors twice
-        flat, grads = flat_grad_views(tensors)
-        ctx.model._flat_grad = flat
-        check(lib.qp_backward(ctx.model._arch, _lib.ptr_array(tensors), x.data_ptr(), h.data_ptr(), d.data_ptr(),
-                              B, T, F, bl, M, dlogits.data_ptr(), _lib.ptr_array(grads), ctx.ws.data_ptr(), ctx.nbytes,
-                              ctx.flags, _stream()))
-        ctx.model.last_launches += lib.qp_last_launch_count()
+        # The buffer is laid out in the order the backward FINISHES the tensors (head, blocks last to first, causal layer:
+        # QPNet.flat_order), so a range of backward stages is a contiguous piece of it.
+        model = ctx.model
+        flat, grads = flat_grad_views(tensors, model.flat_order)
+        model._flat_grad = flat
+        sync = model.grad_sync                       # data-parallel hook (train.OverlappedReducer) or None
+        ranges = sync.stage_ranges() if sync is not None else [(0, model.n_backward_stages)]
+        for k, (s0, s1) in enumerate(ranges):
+            check(lib.qp_backward_range(model._arch, _lib.ptr_array(tensors), x.data_ptr(), h.data_ptr(), d.data_ptr(),
+                                        B, T, F, bl, M, dlogits.data_ptr(), _lib.ptr_array(grads), ctx.ws.data_ptr(),
+                                        ctx.nbytes, ctx.flags, s0, s1, _stream()))
+            model.last_launches += lib.qp_last_launch_count()
+            if sync is not None:
+                sync.range_done(k, flat)             # the gradients of stages [s0, s1) are final once the stream gets here
         ctx.ws = None
         return (None, None, None, None, None, None, None, None, *grads)
 
@@ -197,8 +206,43 @@ class QPNet(nn.Module):
                            and len(self.dilationsF) >= 1 and self.dilationsF[0] == 1
                            and 4 <= len(self.dilationsF) + len(self.dilationsA) <= 64)
         self.philox_seed = 100      # qpnet_decode.py:58 default --seed
+        # backward stages (qp_backward_range): 0 head, 1..L blocks last to first, L+1 causal layer + upsampler; the flat
+        # gradient / parameter / Adam-moment buffers are laid out in that order
+        self.n_backward_stages = nF + nA + 2
+        self.grad_sync = None       # set by train.Trainer when the gradient all-reduce overlaps the backward
+        self._stage_of_param = self._param_stages()
+        self.flat_order = sorted(range(len(self._stage_of_param)), key=lambda i: (self._stage_of_param[i], i))
 
     # ------------------------------------------------------------------ helpers
+    def _param_stages(self):
+        """Backward stage that finishes the gradient of every parameter (state_dict order)."""
+        nF, nA = len(self.dilationsF), len(self.dilationsA)
+        L = nF + nA
+        stages = []
+        for name, _ in self.named_parameters():
+            parts = name.split(".")
+            if parts[0].startswith("conv_post"):
+                stages.append(0)
+            elif parts[0] in ("causal", "upsampling"):
+                stages.append(L + 1)
+            else:
+                i = int(parts[1])
+                layer = i if parts[0].endswith("F") or "F_" in parts[0] else nF + i
+                stages.append(L - layer)
+        return stages
+
+    def flat_stage_offsets(self):
+        """Element range [lo, hi) of every backward stage inside the flat gradient buffer."""
+        params = list(self.parameters())
+        offs, total = flat_layout(params, self.flat_order)
+        lo = [total] * self.n_backward_stages
+        hi = [0] * self.n_backward_stages
+        for i, p in enumerate(params):
+            s = self._stage_of_param[i]
+            lo[s] = min(lo[s], offs[i])
+            hi[s] = max(hi[s], offs[i] + (p.numel() + 3) // 4 * 4)
+        return list(zip(lo, hi)), total
+
     def _tensors(self):
         ts = list(self.parameters())
         for t in ts:

@@ -48,9 +48,10 @@ class GradBucket:
     a single all-reduce.  Parameters that never receive a gradient (the dead last ``resA_1x1``, SURVEY.md
     caveat C7) contribute zeros, so every rank reduces the same number of elements."""
 
-    def __init__(self, params, group=None):
+    def __init__(self, params, group=None, order=None):
         self.params = [p for p in params if p.requires_grad]
         self.group = group
+        self.order = order          # layout order of the flat gradient buffer (QPNet.flat_order)
         self.numel = sum(p.numel() for p in self.params)
         dev = self.params[0].device
         self.flat = torch.zeros(self.numel, dtype=torch.float32, device=dev)
@@ -76,7 +77,7 @@ class GradBucket:
         if flat is None or flat.dtype != torch.float32:
             return False
         from .qpnet import flat_layout
-        offs, total = flat_layout(self.params)
+        offs, total = flat_layout(self.params, self.order)
         if flat.numel() != total:
             return False
         base = flat.data_ptr()
@@ -119,13 +120,13 @@ class FlatAdam:
     moments is a zero update).  Construct it AFTER ``model.cuda()``: moving the model re-allocates its parameters and
     drops the flat buffer."""
 
-    def __init__(self, params, lr: float = 1e-4, betas=(0.9, 0.999), eps: float = 1e-8):
+    def __init__(self, params, lr: float = 1e-4, betas=(0.9, 0.999), eps: float = 1e-8, order=None):
         from .qpnet import flat_layout
         self.params = list(params)
         if not self.params or not all(p.is_cuda and p.dtype == torch.float32 for p in self.params):
             raise RuntimeError("FlatAdam needs float32 parameters on a CUDA (sm_100a) device; there is no CPU path")
         self.lr, self.betas, self.eps = float(lr), (float(betas[0]), float(betas[1])), float(eps)
-        self.offsets, self.numel = flat_layout(self.params)
+        self.offsets, self.numel = flat_layout(self.params, order)     # order: QPNet.flat_order, the layout of the flat gradients
         dev = self.params[0].device
         self.flat = torch.zeros(self.numel, dtype=torch.float32, device=dev)
         for p, o in zip(self.params, self.offsets):
@@ -208,6 +209,69 @@ class FlatAdam:
         self.steps = steps
 
 
+class OverlappedReducer:
+    """Gradient all-reduce overlapped with the backward (the reference's DataParallel reduces after the whole backward,
+    qpnet_train.py:416-423).
+
+    The hand-written backward runs in stage ranges (``qp_backward_range``: head, blocks last to first, causal layer) and
+    returns every gradient as a view of ONE flat buffer laid out in that order, so the gradients of a finished range are
+    a contiguous piece.  After each range an event is recorded on the compute stream and the piece is all-reduced
+    (average) on a side stream while the next range computes; only the last, smallest piece is exposed.  Buckets shrink
+    towards the end of the backward (24 MB, then 12 MB, then 6 MB) for that reason."""
+
+    def __init__(self, model, group=None, limits_mb=(24.0, 12.0, 6.0)):
+        self.model, self.group = model, group
+        stage_offs, total = model.flat_stage_offsets()
+        self.total = total
+        self.buckets = []                       # (stage_begin, stage_end, lo, hi)
+        s0, lo = 0, stage_offs[0][0]
+        for s, (a, b) in enumerate(stage_offs):
+            frac = b / max(total, 1)
+            limit = limits_mb[0] if frac < 0.5 else (limits_mb[1] if frac < 0.85 else limits_mb[2])
+            last = s == len(stage_offs) - 1
+            if (b - lo) * 4 >= limit * (1 << 20) or last:
+                self.buckets.append((s0, s + 1, lo, b))
+                s0, lo = s + 1, b
+        self.works = []
+        self.comm = None
+
+    @property
+    def world(self) -> int:
+        return dist.get_world_size(self.group) if dist.is_available() and dist.is_initialized() else 1
+
+    def stage_ranges(self):
+        return [(b[0], b[1]) for b in self.buckets]
+
+    def range_done(self, k, flat):
+        """Called by the backward right after the launches of bucket k were enqueued."""
+        w = self.world
+        if w == 1:
+            return
+        _, _, lo, hi = self.buckets[k]
+        piece = flat[lo:hi]
+        nccl = flat.is_cuda
+        op = dist.ReduceOp.AVG if nccl else dist.ReduceOp.SUM          # gloo (CPU tests) has no AVG
+        if nccl:
+            if self.comm is None:
+                self.comm = torch.cuda.Stream(device=flat.device)
+            ev = torch.cuda.Event()
+            ev.record()
+            self.comm.wait_event(ev)
+            with torch.cuda.stream(self.comm):
+                work = dist.all_reduce(piece, op=op, group=self.group, async_op=True)
+        else:
+            work = dist.all_reduce(piece, op=op, group=self.group, async_op=True)
+        self.works.append((work, piece, None if nccl else w))
+
+    def finish(self):
+        """The compute stream waits for every piece; afterwards the flat buffer holds the mean gradient."""
+        for work, piece, div in self.works:
+            work.wait()
+            if div:
+                piece.div_(div)
+        self.works = []
+
+
 class Trainer:
     """One SI-QPNet optimisation step per call (qpnet_train.py:517-531), data parallel when
     ``torch.distributed`` is initialised."""
@@ -220,8 +284,10 @@ class Trainer:
         if os.environ.get("QPNET_TORCH_ADAM", "0") == "1":
             self.optimizer = torch.optim.Adam(params, lr=lr, fused=True)
         else:
-            self.optimizer = FlatAdam(params, lr=lr)
-        self.bucket = GradBucket(list(model.parameters()), group)
+            self.optimizer = FlatAdam(params, lr=lr, order=model.flat_order)
+        self.bucket = GradBucket(list(model.parameters()), group, order=model.flat_order)
+        # gradient all-reduce overlapped with the backward (QPNET_OVERLAP_ALLREDUCE=0: one all-reduce after the backward)
+        self.reducer = OverlappedReducer(model, group) if os.environ.get("QPNET_OVERLAP_ALLREDUCE", "1") != "0" else None
 
     def step(self, x, h, d, t, bl: int):
         """x (B, T) long, h (B, A, T/U), d (B, T) fp32, t (B, >= bl) long targets -> mean CE loss (0-dim tensor)."""
@@ -230,12 +296,67 @@ class Trainer:
         self.optimizer.zero_grad(set_to_none=True)
         logits = model(x, h, d, blt)                                      # (B, bl, Q), autograd-attached
         loss, dlogits = ops.cross_entropy(logits.detach(), t[:, -bl:])    # fused softmax-CE + gradient
-        logits.backward(dlogits)
+        overlap = self.reducer is not None and self.bucket.world > 1
+        model.grad_sync = self.reducer if overlap else None
+        try:
+            logits.backward(dlogits)
+        finally:
+            model.grad_sync = None
         flat = getattr(model, "_flat_grad", None)
-        if self.bucket.world > 1:
+        if overlap:
+            self.reducer.finish()
+        elif self.bucket.world > 1:
             self.bucket.allreduce_mean(flat)
         if isinstance(self.optimizer, FlatAdam):
             self.optimizer.step(flat)
         else:
             self.optimizer.step()
         return loss.reshape(())
+
+
+class Adapter(Trainer):
+    """SD adaptation (reference: ``src/bin/qpnet_update.py:444-532``): the SI training step, started from a pretrained
+    checkpoint.  ``pretrain``: a reference-format checkpoint whose ``"model"`` entry initialises the weights, iterations
+    restart at 0 (qpnet_update.py:456-464); ``resume``: an adaptation checkpoint restoring model, Adam state and the
+    iteration counter (445-455).  The step itself is ``Trainer.step``."""
+
+    def __init__(self, model, pretrain=None, resume=None, lr: float = 1e-4, group=None):
+        from . import checkpoint as ck
+        if (pretrain is None) == (resume is None):
+            raise ValueError("pass exactly one of pretrain= (start adapting) or resume= (continue adapting)")
+        if pretrain is not None:
+            ck.load_checkpoint(pretrain, model)           # weights only: the optimizer starts fresh
+        super().__init__(model, lr=lr, group=group)       # (the parameters are re-seated into the flat buffer here)
+        self.iterations = 0
+        if resume is not None:
+            self.iterations = ck.load_checkpoint(resume, model, self.optimizer)
+
+    def step(self, x, h, d, t, bl: int):
+        loss = super().step(x, h, d, t, bl)
+        self.iterations += 1
+        return loss
+
+    def save(self, checkpoint_dir):
+        from . import checkpoint as ck
+        return ck.save_checkpoint(checkpoint_dir, self.model, self.optimizer, self.iterations)
+
+
+@torch.no_grad()
+def validation_loss(model, batches, n_quantize=None):
+    """Held-out loss of one checkpoint (reference: ``src/bin/qpnet_validate.py:408-437``): the mean over the batches of
+    ``CE(model(x, h, d, b)[:, -bl:], t[:, -bl:])`` -- ``float(loss / (i + 1))``, the value the reference stores in
+    ``validation_result.yml`` under the checkpoint's name.  ``batches`` yields ``(x, h, t, d, b)`` like the reference's
+    generators (e.g. ``segmenter.TrainSegmenter.stream``).  The forward keeps nothing for a backward (the reference's
+    script leaves autograd on; the loss is the same).  Returns ``(mean, [batch losses])``."""
+    Q = n_quantize or model.n_quantize
+    losses = []
+    for x, h, t, d, b in batches:
+        assert torch.all(b == b[0])                                   # qpnet_validate.py:422
+        bl = int(b[0])
+        assert int(t.max()) < Q                                       # qpnet_validate.py:425
+        logits = model(x, h, d, b)
+        loss, _ = ops.cross_entropy(logits, t[:, -bl:], want_grad=False)
+        losses.append(float(loss))
+    if not losses:
+        raise ValueError("no validation batches")
+    return float(sum(losses) / len(losses)), losses

@@ -749,3 +749,52 @@ def test_flat_adam_matches_torch_adam_and_resumes_reference_checkpoint(dev, tmp_
     fresh = torch.optim.Adam(QPNet(**kw).parameters(), lr=1e-4)
     fresh.load_state_dict(again["optimizer"])           # torch accepts what FlatAdam wrote
     assert float(fresh.state_dict()["state"][0]["step"]) == 8.0
+
+
+# ------------------------------------------------------------------ SD adaptation / validation loops
+@pytest.mark.gpu
+def test_adaptation_and_validation_loops_vs_oracle(dev, tmp_path):
+    """qpnet_update.py:444-532 / qpnet_validate.py:408-437 around the hand-written forward: the validation loss of a
+    checkpoint equals the oracle's CE on the same batches (fp32 path, 2e-5); an Adapter started from that checkpoint
+    (pretrain=) takes the same first step as a Trainer on the same weights, lowers the loss, saves a reference-format
+    checkpoint, and resume= restores weights, Adam state and the iteration counter."""
+    from qpnet_b200 import checkpoint as ck
+    from qpnet_b200.train import Adapter, Trainer, validation_loss
+    kw, a, p, x, h, d, t, bl = cases.forward_inputs("small_s2_b1")
+    m0 = _model(kw, p, dev)
+    path = ck.save_checkpoint(str(tmp_path / "si"), m0, torch.optim.Adam(m0.parameters(), lr=1e-4), 200000)
+    # validation: two batches (the second with other targets) against the oracle
+    t2 = torch.roll(t, 5, dims=1)
+    b = torch.tensor([bl], device=dev)
+    batches = [(x.to(dev), h.to(dev), t.to(dev), d.to(dev), b), (x.to(dev), h.to(dev), t2.to(dev), d.to(dev), b)]
+    mv = _model(kw, orc.init_params(a, 99, 0.1), dev)
+    ck.load_checkpoint(path, mv)
+    mean, losses = validation_loss(mv, batches)
+    with torch.no_grad():
+        want = orc.forward(a, p, x, h, d, bl)
+        w1 = float(torch.nn.functional.cross_entropy(want.reshape(-1, a.Q), t.reshape(-1)))
+        w2 = float(torch.nn.functional.cross_entropy(want.reshape(-1, a.Q), t2.reshape(-1)))
+    assert abs(losses[0] - w1) < 2e-5 and abs(losses[1] - w2) < 2e-5 and abs(mean - (w1 + w2) / 2) < 2e-5
+    # adaptation from the SI checkpoint
+    ma = _model(kw, orc.init_params(a, 98, 0.1), dev)
+    ad = Adapter(ma, pretrain=path, lr=1e-4)
+    assert ad.iterations == 0 and all(torch.equal(q1, q2) for q1, q2 in zip(ma.parameters(), m0.parameters()))
+    tr = Trainer(m0, lr=1e-4)
+    l_ad = float(ad.step(x.to(dev), h.to(dev), d.to(dev), t.to(dev), bl))
+    l_tr = float(tr.step(x.to(dev), h.to(dev), d.to(dev), t.to(dev), bl))
+    assert abs(l_ad - l_tr) < 1e-6 and abs(l_ad - w1) < 2e-5
+    for q1, q2 in zip(ma.parameters(), m0.parameters()):
+        torch.testing.assert_close(q1, q2, rtol=0, atol=1e-7)
+    for _ in range(4):
+        last = float(ad.step(x.to(dev), h.to(dev), d.to(dev), t.to(dev), bl))
+    assert last < l_ad and ad.iterations == 5
+    saved = ad.save(str(tmp_path / "sd"))
+    assert os.path.basename(saved) == "checkpoint-5.pkl"
+    mr = _model(kw, orc.init_params(a, 97, 0.1), dev)
+    ar = Adapter(mr, resume=saved)
+    assert ar.iterations == 5 and ar.optimizer.steps == 5
+    assert all(torch.equal(q1, q2) for q1, q2 in zip(mr.parameters(), ma.parameters()))
+    l1, l2 = float(ad.step(x.to(dev), h.to(dev), d.to(dev), t.to(dev), bl)), float(ar.step(x.to(dev), h.to(dev), d.to(dev), t.to(dev), bl))
+    assert abs(l1 - l2) < 1e-6
+    for q1, q2 in zip(mr.parameters(), ma.parameters()):
+        torch.testing.assert_close(q1, q2, rtol=0, atol=1e-7)

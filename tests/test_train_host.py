@@ -102,3 +102,46 @@ def test_segmenter_length_arithmetic_matches_oracle():
     bl, h_bs, x_bs = segment_lengths(976, 29900, 30000, 110)
     assert 976 + bl <= 30000 and (976 + bl) % 110 == 0 and x_bs == h_bs * 110 + 1
 
+
+
+def _reducer_worker(rank, world, port, out):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from qpnet_b200.qpnet import QPNet, flat_grad_views
+    from qpnet_b200.train import OverlappedReducer
+    m = QPNet(n_resch=16, n_skipch=8)          # parameters on the CPU: only the host-side layout / bucket logic runs here
+    params = list(m.parameters())
+    red = OverlappedReducer(m, limits_mb=(0.02, 0.01, 0.005))
+    ranges = red.stage_ranges()
+    ok = ranges[0][0] == 0 and ranges[-1][1] == m.n_backward_stages and all(a[1] == b[0] for a, b in zip(ranges, ranges[1:]))
+    ok = ok and len(ranges) >= 3 and red.buckets[0][2] == 0 and red.buckets[-1][3] == red.total
+    ok = ok and all(a[3] == b[2] for a, b in zip(red.buckets, red.buckets[1:]))          # contiguous pieces of the flat buffer
+    # emulate the staged backward: every stage writes the gradients of ITS parameters, then its bucket is reduced
+    flat, views = flat_grad_views(params, m.flat_order)
+    for k, (s0, s1) in enumerate(ranges):
+        for i, v in enumerate(views):
+            if s0 <= m._stage_of_param[i] < s1:
+                v.fill_(float((rank + 1) * (i + 1)))
+        lo, hi = red.buckets[k][2], red.buckets[k][3]
+        inside = [i for i, v in enumerate(views) if lo <= (v.data_ptr() - flat.data_ptr()) // 4 < hi]
+        ok = ok and sorted(inside) == sorted(i for i in range(len(views)) if s0 <= m._stage_of_param[i] < s1)
+        red.range_done(k, flat)
+    red.finish()
+    mean = (1 + world) / 2.0
+    ok = ok and all(torch.allclose(v, torch.full_like(v, mean * (i + 1))) for i, v in enumerate(views))
+    out[rank] = bool(ok)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_overlapped_reducer_world2_gloo():
+    """The bucketed gradient all-reduce that overlaps the staged backward (train.OverlappedReducer): stage ranges cover the
+    backward, every bucket is one contiguous piece of the flat gradient buffer holding exactly the parameters its stages
+    finish, and after the last bucket every rank holds the mean."""
+    world = 2
+    port = 31500 + (os.getpid() % 2000)
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_reducer_worker, args=(world, port, out), nprocs=world, join=True)
+    assert dict(out) == {0: True, 1: True}
