@@ -21,9 +21,9 @@
 //   st.async to the rank that FINISHES those utterances (rank q finishes utterances [32q, 32q+32) of the cluster's rows)
 //   -> sum of the four partial tiles + bias + aux + tables -> z_j = sigmoid * tanh -> published.  U_j = [R ; K]_{j-1}
 //   z_{j-1} (residual and skip rows) goes the same way through its own warps and publishes x_j.
-// * Past taps (the reference's FIFOs, qpnet.py:388-393, 431-437): x_j(t) is published into a ring xr[j][t mod R_j] of
-//   bf16 vectors that serves BOTH as the exchange buffer of the current step and, k steps later, as the past tap
-//   x_j(t-k) (k = dil for fixed blocks, -round(-d[t] * dil) for adaptive ones with the reference's rounding,
+// * Past taps (the reference's FIFOs, qpnet.py:388-393, 431-437): x_j(t) is published twice, into the exchange buffer the
+//   current step's consumers poll and into a ring xr[j][t mod R_j] of bf16 vectors that serves, k steps later, as the past
+//   tap x_j(t-k) (k = dil for fixed blocks, -round(-d[t] * dil) for adaptive ones with the reference's rounding,
 //   qpnet.py:616-617 / 621-622; k == 0 -> oldest entry, caveat C4).  1 KB per utterance, block and step instead of the
 //   16 KB of un-reduced partial products qp_generate_fold2.cu keeps.
 // * The aux 1x1 (qpnet.py:663-664 / 632-633) is evaluated at FRAME rate: h_up[:, t] = h[:, t / U] * w[t % U] + b
@@ -113,6 +113,7 @@ struct Plan {
   float* Paux;            // [NCTA][L][32 utt][32 rows]  V h_f of the finishing CTA's utterances, per frame
   uint32_t* xr[MAXL];     // [1 << rlog][UB][C / 2]  x_l(t) ring, tagged words
   uint32_t* vz;           // [L][UB][C / 2]
+  uint32_t* vx;           // [L][UB][C / 2]  x_l of the current step (the ring copy serves the past taps)
   uint32_t* v256;         // [2][UB][S / 2]   0: relu(skip sum), 1: relu(head-1)
   uint32_t* vlog;         // [UB][Q]  fp32 logits
   uint32_t* vsym;         // [UB][32] fed-back symbol, one line per utterance
@@ -165,6 +166,7 @@ size_t make_plan(const QpArch* a, int B, int F, int M, void* base, size_t cap, P
     p->xr[l] = l >= 1 ? ar.take<uint32_t>(((size_t)1 << p->rlog[l]) * UB * (C / 2)) : nullptr;
   }
   p->vz = ar.take<uint32_t>((size_t)L * UB * (C / 2));
+  p->vx = ar.take<uint32_t>((size_t)L * UB * (C / 2));
   p->v256 = ar.take<uint32_t>((size_t)2 * UB * (S / 2));
   p->vlog = ar.take<uint32_t>((size_t)UB * Q);
   p->vsym = ar.take<uint32_t>((size_t)UB * 32);
@@ -533,7 +535,9 @@ __global__ void __launch_bounds__(NT, 1) f3_gen_kernel(Plan p, GenArgsDev g) {
   };
   // slot and tag of x_l at step t (real steps: ring position; priming passes: slot 0, pass parity)
   auto x_slot = [&](int l, int t) -> int { return t < 0 ? 0 : (t & ((1 << p.rlog[l]) - 1)); };
-  auto x_tag = [&](int l, int t) -> unsigned { return t < 0 ? ((unsigned)(t + NP) & 1u) : ((unsigned)(t >> p.rlog[l]) & 1u); };
+  // every exchange word of a step carries the step's parity (independent of the batch: an utterance's symbols must not
+  // depend on its batch-mates)
+  auto x_tag = [&](int l, int t) -> unsigned { return (unsigned)(t + NP) & 1u; };
   // Stage this thread's pieces i < nl of a tagged vector (piece i at src + i * sstep) at dst + i * dstep.  The thread first
   // spins on `flags` (the step counters of the four CTAs of the producing cluster, one 16-byte load) until the live ranks
   // show `want`; then it loads the pieces and verifies every tag (a flag may overtake its data: then it simply re-loads).
@@ -861,7 +865,8 @@ __global__ void __launch_bounds__(NT, 1) f3_gen_kernel(Plan p, GenArgsDev g) {
             const unsigned o0 = __shfl_down_sync(0xffffffffu, w0, 1), o1 = __shfl_down_sync(0xffffffffu, w1, 1);
             if (!(q & 1) && live) {
               const uint4 piece = make_uint4(w0, w1, o0, o1);
-              uint32_t* dstp = p.xr[j] + (size_t)fu * (C / 2) + 8 * c + 4 * (q >> 1);
+              st_strong_v4(p.vx + ((size_t)j * UB + fu) * (C / 2) + 8 * c + 4 * (q >> 1), piece);   // this step's consumers poll here
+              uint32_t* dstp = p.xr[j] + (size_t)fu * (C / 2) + 8 * c + 4 * (q >> 1);                 // the past taps of later steps read here
               if (t == -1) {   // the last priming pass fills the whole ring with the constant
                 const int R = 1 << p.rlog[j];
                 for (int sl = 0; sl < R; ++sl) st_strong_v4(dstp + (size_t)sl * UB * (C / 2), piece);
@@ -964,7 +969,7 @@ __global__ void __launch_bounds__(NT, 1) f3_gen_kernel(Plan p, GenArgsDev g) {
       waitb(B_XFREE);
       unsigned char* dst = sm + SM_X + tile_off;
       const unsigned tag = x_tag(jx, t);
-      const uint4* src0 = (const uint4*)(p.xr[jx] + (size_t)x_slot(jx, t) * UB * (C / 2)) + rank * 16 + pc;
+      const uint4* src0 = (const uint4*)(p.vx + (size_t)jx * UB * (C / 2)) + rank * 16 + pc;
       trace(t, jx + 1, 19);
       poll_tile(N16(), src0 + (size_t)ub * (C / 8), (size_t)8 * (C / 8), min(16, (B - ub + 7) >> 3), tag, dst, 1024,
                 p.flagx + (size_t)jx * NCTA + 4 * (8 * rank + (pc >> 1)), (unsigned)(t + NP), !(p.poll_all & 2), t, jx + 1, 20);
