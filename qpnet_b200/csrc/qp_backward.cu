@@ -5,6 +5,8 @@
 // QPNET_BWD_TC = 0 fallback of every contraction.  Consumes the workspace a QP_F_SAVE forward filled.
 #include <stdlib.h>
 
+#include <algorithm>
+
 #include "qp_gemm_f32.cuh"
 #include "qp_tc.cuh"
 #include "qp_tf_plan.cuh"
@@ -234,7 +236,6 @@ int tf_backward_f32(const QpArch* arch, const float* const* tensors, const int64
         g.resid = dXnext; g.resid_bstride = (long long)n * C;
         g.dh = p.dHup; g.dh_bstride = (long long)L0 * A; g.dh_off = L0 - n;
         if (int e = tc::gemm_dx(g, st)) return e;
-        if (int e = unpack_grads_layer_f32(arch, p.gtab, p.dW, l, st)) return e;
         continue;
       }
       GemmArgs g = {};
@@ -245,8 +246,11 @@ int tf_backward_f32(const QpArch* arch, const float* const* tensors, const int64
       g.resid = dXnext; g.resid_bstride = (int64_t)n * C; g.ldresid = C;
       g.dh = p.dHup; g.dh_bstride = (int64_t)L0 * A; g.dh_off = L0 - n;
       if (int e = launch_gemm<EPI_DX>(g, st, tc)) return e;
-      if (int e = unpack_grads_layer_f32(arch, p.gtab, p.dW, l, st)) return e;
     }
+  }
+  {   // the blocks of this range leave their gradients in the reference's tensors: blocks [L - s_end + 1, L - s_begin] clipped
+    const int l_lo = std::max(0, L - (s_end - 1)), l_hi = std::min(L - 1, L - std::max(s_begin, 1));
+    if (int e = unpack_grads_layers_f32(arch, p.gtab, p.dW, l_lo, l_hi + 1, st)) return e;
   }
   // ---- front end ----------------------------------------------------------------------
   if (L + 1 < s_begin || L + 1 >= s_end) return QP_OK;

@@ -125,7 +125,6 @@ struct Plan {
   long long* trace; int trace_step0, trace_nsteps;
   long long* gtrace;      // [NCTA][L + 4][4] %globaltimer of one step, every CTA: 0 z published, 1 z staged, 2 partial rows arrived, 3 x published
   int poll_all;           // (tuning) bit 0 / bit 1: poll the z / x pieces themselves from the start instead of waiting for the producers' flags
-  int backoff_ns;         // (tuning) sleep between two polling rounds
 };
 
 static int log2_above(int v) { int q = 0; while ((1 << q) <= v) ++q; return q; }
@@ -180,7 +179,6 @@ size_t make_plan(const QpArch* a, int B, int F, int M, void* base, size_t cap, P
   p->gtrace = ar.take<long long>((size_t)NCTA * (L + 4) * 4);
   p->trace_step0 = -1000000; p->trace_nsteps = 8;
   p->poll_all = 3;     // measured (profiles/r02g_*): polling the pieces themselves beats flag-then-load at 32 and at 128 utterances
-  p->backoff_ns = 0;
   return align_up(ar.off, 256);
 }
 
@@ -473,7 +471,7 @@ __global__ void __launch_bounds__(NT, 1) f3_gen_kernel(Plan p, GenArgsDev g) {
   const int rank = (int)cluster_rank();                       // == s % CL
   const int nlive = (B + 31) >> 5;                            // ranks that finish at least one live utterance
   const int half = Q / 2;
-  const bool use_flags = p.poll_all != 3;                     // producers publish step counters only when a consumer waits for them
+  const bool use_flags = (p.poll_all & 3) != 3;                     // producers publish step counters only when a consumer waits for them
   float* const sBh = (float*)(sm + SM_BH);
   unsigned short* const sK = (unsigned short*)(sm + SM_K);
   auto bar = [&](int i) -> uint32_t { return sbase + SM_BAR + 8 * i; };
@@ -516,10 +514,11 @@ __global__ void __launch_bounds__(NT, 1) f3_gen_kernel(Plan p, GenArgsDev g) {
     }
   };
   // the watchdog: a word or barrier that never arrives is a bug, not a schedule; record it and stop the grid
-  auto spin_check = [&](unsigned& spins, long long& t0) {
-    if ((++spins & 1023u) != 0) return;
-    if (t0 == 0) { t0 = clock64(); return; }
-    if (*((volatile int32_t*)p.status) != 0 || clock64() - t0 > GEN_TIMEOUT_CYCLES) {
+  // (a polling round is at least an L2 round trip or an mbarrier try_wait time-out, a few hundred cycles: 2^23 rounds
+  // are seconds, far beyond any schedule; counting rounds keeps the hot loops free of clock reads and 64-bit state)
+  auto spin_check = [&](unsigned& spins, long long&) {
+    if ((++spins & 0xFFFFu) != 0) return;
+    if (*((volatile int32_t*)p.status) != 0 || spins >= (1u << 23)) {
       atomicExch(p.status, QP_ETIMEOUT);
       __threadfence_system();
       __trap();
@@ -552,19 +551,24 @@ __global__ void __launch_bounds__(NT, 1) f3_gen_kernel(Plan p, GenArgsDev g) {
       spin_check(spins, t0);
     }
     if (tr_ev >= 0) trace(tr_t, tr_ph, tr_ev);
-    uint4 v[N];
+    // cp.async copies the pieces global (L2) -> shared without holding registers for 16 loads in flight; the tags are
+    // then checked on the staged copy, and a round with a stale piece is simply repeated
+    const uint32_t dst_s = smem_u32(dst);
     while (true) {
 #pragma unroll
-      for (int i = 0; i < N; ++i) if (i < nl) v[i] = ld_strong_v4(src + (size_t)i * sstep);
-      bool ok = true;
+      for (int i = 0; i < N; ++i) if (i < nl) cp_async16_s(dst_s + i * dstep, src + (size_t)i * sstep);
+      asm volatile("cp.async.wait_all;\n" ::: "memory");
+      unsigned bad = 0;
 #pragma unroll
-      for (int i = 0; i < N; ++i) if (i < nl) ok = ok && fresh4(v[i], tag);
-      if (ok) break;
+      for (int i = 0; i < N; ++i)
+        if (i < nl) {
+          uint4 x;
+          asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];\n" : "=r"(x.x), "=r"(x.y), "=r"(x.z), "=r"(x.w) : "r"(dst_s + i * dstep) : "memory");
+          bad |= (x.x ^ tag) | (x.y ^ tag) | (x.z ^ tag) | (x.w ^ tag);
+        }
+      if (!(bad & 1u)) break;
       spin_check(spins, t0);
-      if (p.backoff_ns) __nanosleep(p.backoff_ns);
     }
-#pragma unroll
-    for (int i = 0; i < N; ++i) if (i < nl) *(uint4*)(dst + i * dstep) = v[i];
   };
   using N16 = std::integral_constant<int, 16>;
   using N8 = std::integral_constant<int, 8>;
@@ -1195,7 +1199,6 @@ int f3_generate(const QpArch* arch, const float* const* tensors_host, const QpGe
   const bool tr = getenv("QPNET_GEN_TRACE_STEP") != nullptr;
   if (tr) p.trace_step0 = atoi(getenv("QPNET_GEN_TRACE_STEP"));
   if (const char* e = getenv("QPNET_F3_POLL_ALL")) p.poll_all = atoi(e);
-  if (const char* e = getenv("QPNET_F3_BACKOFF")) p.backoff_ns = atoi(e);
   auto kern = tr ? f3::f3_gen_kernel<true> : f3::f3_gen_kernel<false>;
   QP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   cudaLaunchConfig_t cfg = {};

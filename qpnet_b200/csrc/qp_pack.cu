@@ -101,13 +101,18 @@ __global__ void pack_small_kernel(TensorMap tm, PackedDims pd, const float* cons
   }
 }
 
-// packed gradients of ONE residual block -> the reference's tensors (gate biases, [res | skip] weights and biases)
-__global__ void unpack_small_layer_kernel(TensorMap tm, PackedDims pd, const float* const* __restrict__ tab, PackedF32 P, int l) {
+// packed gradients of the residual blocks [l_begin, l_end) -> the reference's tensors (gate biases, [res | skip] weights
+// and biases)
+__global__ void unpack_small_layer_kernel(TensorMap tm, PackedDims pd, const float* const* __restrict__ tab, PackedF32 P, int l_begin,
+                                          int l_end) {
   const int C = pd.C, S = pd.S;
   const size_t n_bg = (size_t)2 * C, n_wrs = (size_t)(C + S) * C, n_brs = (size_t)(C + S);
-  const bool fixed = l < pd.nF;
-  const int j = fixed ? l : l - pd.nF;
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_bg + n_wrs + n_brs; i += (size_t)gridDim.x * blockDim.x) {
+  const size_t per = n_bg + n_wrs + n_brs;
+  for (size_t ii = (size_t)blockIdx.x * blockDim.x + threadIdx.x; ii < per * (l_end - l_begin); ii += (size_t)gridDim.x * blockDim.x) {
+    const int l = l_begin + (int)(ii / per);
+    const size_t i = ii % per;
+    const bool fixed = l < pd.nF;
+    const int j = fixed ? l : l - pd.nF;
     if (i < n_bg) {
       const int row = (int)i, c = row >> 1, g = row & 1;
       const float v = P.bg[(size_t)l * 2 * C + i];
@@ -145,13 +150,14 @@ __global__ void unpack_front_kernel(TensorMap tm, PackedDims pd, const float* co
   }
 }
 
-int unpack_grads_layer_f32(const QpArch* arch, float* const* dev_grad_table, PackedF32 g, int l, cudaStream_t stream) {
+int unpack_grads_layers_f32(const QpArch* arch, float* const* dev_grad_table, PackedF32 g, int l_begin, int l_end, cudaStream_t stream) {
+  if (l_end <= l_begin) return QP_OK;
   TensorMap tm = tensor_map(arch);
   PackedDims pd = packed_dims(arch);
-  const size_t per = pd.wg_elems();
-  pack_wg_kernel<true><<<(unsigned)((per + 255) / 256), 256, 0, stream>>>(tm, pd, (const float* const*)dev_grad_table, g.Wg, per * l, per * (l + 1));
+  const size_t per = pd.wg_elems(), n = per * (l_end - l_begin);
+  pack_wg_kernel<true><<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(tm, pd, (const float* const*)dev_grad_table, g.Wg, per * l_begin, per * l_end);
   QP_LAUNCH_CHECK();
-  unpack_small_layer_kernel<<<148, 256, 0, stream>>>(tm, pd, (const float* const*)dev_grad_table, g, l);
+  unpack_small_layer_kernel<<<148 * 2, 256, 0, stream>>>(tm, pd, (const float* const*)dev_grad_table, g, l_begin, l_end);
   QP_LAUNCH_CHECK();
   return QP_OK;
 }

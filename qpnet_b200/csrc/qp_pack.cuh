@@ -51,9 +51,9 @@ int upload_tensor_table(const QpArch* arch, const float* const* tensors_host, co
 int pack_f32(const QpArch* arch, const float* const* dev_table, PackedF32 out, cudaStream_t stream);
 // scatter packed gradients back into the reference's tensors (overwrites)
 int unpack_grads_f32(const QpArch* arch, float* const* dev_grad_table, PackedF32 grads, cudaStream_t stream);
-// the same for ONE residual block / for the causal layer: the backward hands finished gradients out block by block, so a
+// the same for the residual blocks [l_begin, l_end) / for the causal layer: the backward hands finished gradients out block by block, so a
 // data-parallel caller can start reducing them while the rest of the backward runs
-int unpack_grads_layer_f32(const QpArch* arch, float* const* dev_grad_table, PackedF32 grads, int l, cudaStream_t stream);
+int unpack_grads_layers_f32(const QpArch* arch, float* const* dev_grad_table, PackedF32 grads, int l_begin, int l_end, cudaStream_t stream);
 int unpack_grads_front_f32(const QpArch* arch, float* const* dev_grad_table, PackedF32 grads, cudaStream_t stream);
 
 }  // namespace qp
