@@ -438,6 +438,20 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&r)[8]) {
 }
 __device__ __forceinline__ float4 ldcg4(const float* p) { return __ldcg((const float4*)p); }
 
+// two 16-column loads in flight, one wait
+__device__ __forceinline__ void tmem_ld16x2(uint32_t ta, uint32_t (&a)[16], uint32_t tb, uint32_t (&b)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
+      : "=r"(a[0]), "=r"(a[1]), "=r"(a[2]), "=r"(a[3]), "=r"(a[4]), "=r"(a[5]), "=r"(a[6]), "=r"(a[7]), "=r"(a[8]),
+        "=r"(a[9]), "=r"(a[10]), "=r"(a[11]), "=r"(a[12]), "=r"(a[13]), "=r"(a[14]), "=r"(a[15])
+      : "r"(ta) : "memory");
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
+      : "=r"(b[0]), "=r"(b[1]), "=r"(b[2]), "=r"(b[3]), "=r"(b[4]), "=r"(b[5]), "=r"(b[6]), "=r"(b[7]), "=r"(b[8]),
+        "=r"(b[9]), "=r"(b[10]), "=r"(b[11]), "=r"(b[12]), "=r"(b[13]), "=r"(b[14]), "=r"(b[15])
+      : "r"(tb) : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+}
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
@@ -692,8 +706,7 @@ __global__ void __launch_bounds__(NT, 1) f3_gen_kernel(Plan p, GenArgsDev g) {
 #pragma unroll
           for (int hh = 0; hh < 2; ++hh) {
             uint32_t cv[16], pv[16];
-            tmem_ld16(trow + TC_BUF * b + TC_C + 16 * hh, cv);
-            tmem_ld16(trow + TC_BUF * pb_ + TC_P + 16 * hh, pv);
+            tmem_ld16x2(trow + TC_BUF * b + TC_C + 16 * hh, cv, trow + TC_BUF * pb_ + TC_P + 16 * hh, pv);
 #pragma unroll
             for (int i = 0; i < 8; ++i)
               hw[8 * hh + i] = pack_h2(__uint_as_float(cv[2 * i]) + __uint_as_float(pv[2 * i]),
@@ -1035,10 +1048,12 @@ __global__ void __launch_bounds__(NT, 1) f3_gen_kernel(Plan p, GenArgsDev g) {
           if (pre) waitb(B_PFREE + b);
           waitb(B_ZFULL);
           trace(t, j, 0);
-          // [C_j | U_j | P_{j+1}] <- [G_j ; [R;K]_{j-1} ; H_{j+1}] z_{j-1}
-          mma(pre ? 96 : 64, dbuf, sZ, grp, ZPC_B / 2, true);
-          umma_commit(bar(B_ZPW_FREE + b)); umma_commit(bar(B_ZFREE)); umma_commit(bar(B_CFULL + b)); umma_commit(bar(B_UFULL + b));
+          // C_j <- G_j z_{j-1} first (the tile the critical path waits for), then [U_j | P_{j+1}] <- [[R;K]_{j-1} ; H_{j+1}] z_{j-1}
+          mma(32, dbuf + TC_C, sZ, grp, ZPC_B / 2, true);
+          umma_commit(bar(B_CFULL + b));
           trace(t, j, 1);
+          mma(pre ? 64 : 32, dbuf + TC_U, sZ, grp + 4096, ZPC_B / 2, true);   // rows 32.. of the chunk: atom 4 of each K-block
+          umma_commit(bar(B_ZPW_FREE + b)); umma_commit(bar(B_ZFREE)); umma_commit(bar(B_UFULL + b));
           if (pre) {
             if (j >= 2) {   // P_{j+1} += Wc_{j+1} x_{j-1}
               waitb(B_WCW_FULL + b); waitb(B_XFULL);
