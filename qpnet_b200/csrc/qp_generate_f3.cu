@@ -31,9 +31,9 @@
 //   finishing threads, b (V 1) is folded into the bias.  Block 0 reads the causal layer, a function of the last three
 //   symbols: three table lookups and no exchange at all; blocks 1 and 2 reach x_0 through two more tables.
 // * Exchange words carry a 1-bit epoch tag (LSB of the low bf16 / of the fp32 logit), so a consumer never needs a fence: it
-//   polls the data itself and verifies the tags of what it loaded.  (QPNET_F3_POLL_ALL selects a flag-then-load variant,
-//   where a consumer first spins on the step counters its four producer CTAs write after their pieces: less polling
-//   traffic, one more round trip; measured slower, profiles/r02g_*.)
+//   polls the data itself -- cp.async straight into the swizzled A tile, no registers held for the loads in flight -- and
+//   verifies the tags of the staged copy.  (A flag-then-load variant, where a consumer first spins on step counters its
+//   producers write after their pieces, moved less data and was slower: one more round trip, profiles/r02g_*.)
 // * Warp roles (19 warps, no CTA-wide barrier inside the time loop; everything meets through mbarriers):
 //     0-3   ET   T tiles: tcgen05.ld -> partial rows -> finishers of z_j, the two head layers
 //     4-7   EU   U tiles: partial rows -> fp32 residual / skip state, x_j and relu(skip sum) published
@@ -117,14 +117,10 @@ struct Plan {
   uint32_t* v256;         // [2][UB][S / 2]   0: relu(skip sum), 1: relu(head-1)
   uint32_t* vlog;         // [UB][Q]  fp32 logits
   uint32_t* vsym;         // [UB][32] fed-back symbol, one line per utterance
-  uint32_t* flagz;        // [L][NCTA]  step counter of the z_l pieces CTA s has published (readiness hint; the data carries the tag)
-  uint32_t* flagx;        // [L][NCTA]  same for x_l
-  uint32_t* flagh;        // [2][NCTA]  same for the two 256-vectors of the head
   int16_t* pcm_lut;       // [Q] decode_mu_law(symbol) * 32768 clipped to int16 (qpnet_decode.py:315-318)
   void* tagged_begin; size_t tagged_bytes;
   long long* trace; int trace_step0, trace_nsteps;
   long long* gtrace;      // [NCTA][L + 4][4] %globaltimer of one step, every CTA: 0 z published, 1 z staged, 2 partial rows arrived, 3 x published
-  int poll_all;           // (tuning) bit 0 / bit 1: poll the z / x pieces themselves from the start instead of waiting for the producers' flags
 };
 
 static int log2_above(int v) { int q = 0; while ((1 << q) <= v) ++q; return q; }
@@ -169,16 +165,12 @@ size_t make_plan(const QpArch* a, int B, int F, int M, void* base, size_t cap, P
   p->v256 = ar.take<uint32_t>((size_t)2 * UB * (S / 2));
   p->vlog = ar.take<uint32_t>((size_t)UB * Q);
   p->vsym = ar.take<uint32_t>((size_t)UB * 32);
-  p->flagz = ar.take<uint32_t>((size_t)L * NCTA);
-  p->flagx = ar.take<uint32_t>((size_t)L * NCTA);
-  p->flagh = ar.take<uint32_t>((size_t)2 * NCTA);
   ar.off = align_up(ar.off, 256);
   p->tagged_begin = base ? (char*)base + t0 : nullptr;
   p->tagged_bytes = ar.off - t0;
   p->trace = ar.take<long long>((size_t)8 * (L + 4) * TRACE_EVENTS);
   p->gtrace = ar.take<long long>((size_t)NCTA * (L + 4) * 4);
   p->trace_step0 = -1000000; p->trace_nsteps = 8;
-  p->poll_all = 3;     // measured (profiles/r02g_*): polling the pieces themselves beats flag-then-load at 32 and at 128 utterances
   return align_up(ar.off, 256);
 }
 
@@ -485,7 +477,6 @@ __global__ void __launch_bounds__(NT, 1) f3_gen_kernel(Plan p, GenArgsDev g) {
   const int rank = (int)cluster_rank();                       // == s % CL
   const int nlive = (B + 31) >> 5;                            // ranks that finish at least one live utterance
   const int half = Q / 2;
-  const bool use_flags = (p.poll_all & 3) != 3;                     // producers publish step counters only when a consumer waits for them
   float* const sBh = (float*)(sm + SM_BH);
   unsigned short* const sK = (unsigned short*)(sm + SM_K);
   auto bar = [&](int i) -> uint32_t { return sbase + SM_BAR + 8 * i; };
@@ -555,15 +546,10 @@ __global__ void __launch_bounds__(NT, 1) f3_gen_kernel(Plan p, GenArgsDev g) {
   // spins on `flags` (the step counters of the four CTAs of the producing cluster, one 16-byte load) until the live ranks
   // show `want`; then it loads the pieces and verifies every tag (a flag may overtake its data: then it simply re-loads).
   auto poll_tile = [&](auto nconst, const uint4* src, size_t sstep, int nl, unsigned tag, unsigned char* dst, int dstep,
-                       const uint32_t* flags, unsigned want, bool use_flags, int tr_t, int tr_ph, int tr_ev) {
+                       int tr_t, int tr_ph, int tr_ev) {
     constexpr int N = decltype(nconst)::value;
     if (nl <= 0) return;
     unsigned spins = 0; long long t0 = 0;
-    while (use_flags) {
-      const uint4 f = ld_strong_v4(flags);
-      if (f.x == want && (nlive < 2 || f.y == want) && (nlive < 3 || f.z == want) && (nlive < 4 || f.w == want)) break;
-      spin_check(spins, t0);
-    }
     if (tr_ev >= 0) trace(tr_t, tr_ph, tr_ev);
     // cp.async copies the pieces global (L2) -> shared without holding registers for 16 loads in flight; the tags are
     // then checked on the staged copy, and a round with a stale piece is simply repeated
@@ -670,10 +656,6 @@ __global__ void __launch_bounds__(NT, 1) f3_gen_kernel(Plan p, GenArgsDev g) {
         pre[4] = a1.x + b1.x + c1.x + fmaf(wt, pb.x, g1.x); pre[5] = a1.y + b1.y + c1.y + fmaf(wt, pb.y, g1.y);
         pre[6] = a1.z + b1.z + c1.z + fmaf(wt, pb.z, g1.z); pre[7] = a1.w + b1.w + c1.w + fmaf(wt, pb.w, g1.w);
         gate4(0, pre, tagz);
-        if (use_flags) {
-          asm volatile("bar.sync 2, 128;\n" ::: "memory");   // every finishing thread has issued its pieces
-          if (tid == 0) st_strong_u32(p.flagz + s, (unsigned)(t + NP));
-        }
       }
       trace(t, 0, 5);
       // ---- blocks 1 .. L-1
@@ -738,10 +720,6 @@ __global__ void __launch_bounds__(NT, 1) f3_gen_kernel(Plan p, GenArgsDev g) {
             pre[4] += f2.x; pre[5] += f2.y; pre[6] += f3.x; pre[7] += f3.y;
           }
           gate4(j, pre, tagz);
-          if (use_flags) {
-            asm volatile("bar.sync 2, 128;\n" ::: "memory");
-            if (tid == 0) st_strong_u32(p.flagz + (size_t)j * NCTA + s, (unsigned)(t + NP));
-          }
           gtrace(t, j, 0);
         }
         trace(t, j, 5);
@@ -779,10 +757,6 @@ __global__ void __launch_bounds__(NT, 1) f3_gen_kernel(Plan p, GenArgsDev g) {
               const unsigned w1 = __shfl_down_sync(0xffffffffu, w0, 1), w2 = __shfl_down_sync(0xffffffffu, w0, 2),
                              w3 = __shfl_down_sync(0xffffffffu, w0, 3);
               if (q == 0 && live) st_strong_v4(p.v256 + ((size_t)UB + fu) * (S / 2) + 4 * c, make_uint4(w0, w1, w2, w3));
-              if (use_flags) {
-                asm volatile("bar.sync 2, 128;\n" ::: "memory");
-                if (tid == 0) st_strong_u32(p.flagh + NCTA + s, (unsigned)t);
-              }
             } else if (live) {
               st_strong_v2(p.vlog + (size_t)fu * Q + 8 * c + 2 * q, (__float_as_uint(s0) & ~1u) | par_t, (__float_as_uint(s1) & ~1u) | par_t);
             }
@@ -891,20 +865,12 @@ __global__ void __launch_bounds__(NT, 1) f3_gen_kernel(Plan p, GenArgsDev g) {
                 st_strong_v4(dstp + (size_t)x_slot(j, t) * UB * (C / 2), piece);
               }
             }
-            if (use_flags) {
-              asm volatile("bar.sync 3, 128;\n" ::: "memory");   // every finishing thread has issued its pieces
-              if (t128 == 0) st_strong_u32(p.flagx + (size_t)j * NCTA + s, (unsigned)(t + NP));
-            }
           } else if (t >= 0) {   // relu(sum of the skip outputs) (qpnet.py:505, 566-567) rows 8c + 2q, +1
             const unsigned par_t = (unsigned)t & 1u;
             const unsigned w0 = pack_tagged(fmaxf(sk0, 0.f), fmaxf(sk1, 0.f), par_t);
             const unsigned w1 = __shfl_down_sync(0xffffffffu, w0, 1), w2 = __shfl_down_sync(0xffffffffu, w0, 2),
                            w3 = __shfl_down_sync(0xffffffffu, w0, 3);
             if (q == 0 && live) st_strong_v4(p.v256 + (size_t)fu * (S / 2) + 4 * c, make_uint4(w0, w1, w2, w3));
-            if (use_flags) {
-              asm volatile("bar.sync 3, 128;\n" ::: "memory");
-              if (t128 == 0) st_strong_u32(p.flagh + s, (unsigned)t);
-            }
           }
         }
         trace(t, j, 16);
@@ -926,8 +892,7 @@ __global__ void __launch_bounds__(NT, 1) f3_gen_kernel(Plan p, GenArgsDev g) {
         const uint4* src = (const uint4*)(p.vz + ((size_t)(j - 1) * UB + ub) * (C / 2)) + rank * 16 + pc;
         unsigned char* dst = sZ + (pc >> 3) * ABLK + ub * 128 + (((pc & 7) ^ ub) << 4);
         trace(t, j, 11);
-        poll_tile(N16(), src, (size_t)8 * (C / 8), min(16, (B - ub + 7) >> 3), tagz, dst, 1024,
-                  p.flagz + (size_t)(j - 1) * NCTA + 4 * (8 * rank + (pc >> 1)), (unsigned)(t + NP), !(p.poll_all & 1), t, j, 12);
+        poll_tile(N16(), src, (size_t)8 * (C / 8), min(16, (B - ub + 7) >> 3), tagz, dst, 1024, t, j, 12);
         trace(t, j, 6);
         gtrace(t, j, 1);
         done();
@@ -940,8 +905,7 @@ __global__ void __launch_bounds__(NT, 1) f3_gen_kernel(Plan p, GenArgsDev g) {
           const int pc = i128 & 7, ub = i128 >> 3;
           const uint4* src = (const uint4*)(p.v256 + ((size_t)hd * UB + ub) * (S / 2)) + rank * 8 + pc;
           unsigned char* dst = sZ + (ub >> 3) * 1024 + (ub & 7) * 128 + ((pc ^ (ub & 7)) << 4);
-          poll_tile(N8(), src, (size_t)16 * (S / 8), min(8, (B - ub + 15) >> 4), par_t, dst, 2048,
-                    p.flagh + (size_t)hd * NCTA + 4 * (8 * rank + pc), (unsigned)t, !(p.poll_all & 1), t, 0, -1);
+          poll_tile(N8(), src, (size_t)16 * (S / 8), min(8, (B - ub + 15) >> 4), par_t, dst, 2048, t, 0, -1);
           done();
         }
       }
@@ -988,8 +952,7 @@ __global__ void __launch_bounds__(NT, 1) f3_gen_kernel(Plan p, GenArgsDev g) {
       const unsigned tag = x_tag(jx, t);
       const uint4* src0 = (const uint4*)(p.vx + (size_t)jx * UB * (C / 2)) + rank * 16 + pc;
       trace(t, jx + 1, 19);
-      poll_tile(N16(), src0 + (size_t)ub * (C / 8), (size_t)8 * (C / 8), min(16, (B - ub + 7) >> 3), tag, dst, 1024,
-                p.flagx + (size_t)jx * NCTA + 4 * (8 * rank + (pc >> 1)), (unsigned)(t + NP), !(p.poll_all & 2), t, jx + 1, 20);
+      poll_tile(N16(), src0 + (size_t)ub * (C / 8), (size_t)8 * (C / 8), min(16, (B - ub + 7) >> 3), tag, dst, 1024, t, jx + 1, 20);
       trace(t, jx + 1, 21);
       fence_proxy_async();
       mbar_arrive(bar(B_XFULL));
@@ -1213,7 +1176,6 @@ int f3_generate(const QpArch* arch, const float* const* tensors_host, const QpGe
   QP_REQUIRE(smem <= 227 * 1024, "generate: %d bytes of shared memory needed", smem);
   const bool tr = getenv("QPNET_GEN_TRACE_STEP") != nullptr;
   if (tr) p.trace_step0 = atoi(getenv("QPNET_GEN_TRACE_STEP"));
-  if (const char* e = getenv("QPNET_F3_POLL_ALL")) p.poll_all = atoi(e);
   auto kern = tr ? f3::f3_gen_kernel<true> : f3::f3_gen_kernel<false>;
   QP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   cudaLaunchConfig_t cfg = {};

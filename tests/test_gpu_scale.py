@@ -287,3 +287,25 @@ def test_deep_preset_full_width_on_tcgen05_generator(dev, monkeypatch):
     err = (got.cpu() - want).abs().amax(dim=(0, 2))
     print(f"deep preset, full width, f3: max |dlogit| = {float(err.max()):.4f} (steps 0-99 {float(err[:100].max()):.4f}, last 100 {float(err[-100:].max()):.4f})")
     assert float(err.max()) < 0.10, float(err.max())
+
+
+@pytest.mark.parametrize("kernel", ["f3", "fold2"])
+def test_generator_wide_aux_vs_oracle(dev, monkeypatch, kernel):
+    """n_aux = 44 (more than the 40-float staging pitch the mma.sync kernel used in round 1, below its 48-channel limit):
+    per-step logits under forced symbols against the oracle on both cluster kernels -- the aux rows of neighbouring
+    utterances must not alias."""
+    kw = dict(n_aux=44)
+    a = orc.Arch(**kw)
+    p = orc.init_params(a, 53, 0.05)
+    B, frames, steps = 5, 2, 130
+    x, h, d, forced = _forced_case(a, B, frames, 1.0, steps, 2300)
+    lg = []
+    with torch.no_grad():
+        orc.generate(a, p, x, h, [steps] * B, d, mode="argmax", force=forced, logits_out=lg, max_steps=steps)
+    want = torch.stack(lg, dim=1)
+    monkeypatch.setenv("QPNET_GEN_KERNEL", kernel)
+    m = _model(kw, p, dev)
+    res, got = m.batch_fast_generate(x, h, [steps] * B, d, None, "argmax", False, force=forced, return_logits=True)
+    err = float((got.cpu() - want).abs().max())
+    print(f"n_aux 44, kernel {kernel}: max |dlogit| = {err:.4f}")
+    assert err < 0.06, err
