@@ -519,11 +519,21 @@ __global__ void __launch_bounds__(NT, 1) f3_gen_kernel(Plan p, GenArgsDev g) {
     }
   };
   // the watchdog: a word or barrier that never arrives is a bug, not a schedule; record it and stop the grid
-  // (a polling round is at least an L2 round trip or an mbarrier try_wait time-out, a few hundred cycles: 2^23 rounds
-  // are seconds, far beyond any schedule; counting rounds keeps the hot loops free of clock reads and 64-bit state)
+  // Rounds are counted instead of timed (no clock reads or 64-bit state in the hot loops): a polling round is at least an
+  // L2 round trip (~1 k cycles: 2^23 rounds are seconds), an mbarrier try_wait round can be as short as ~100 cycles
+  // (2^26 rounds are seconds too) -- far beyond any schedule; tools that slow the kernel down by orders of magnitude
+  // (compute-sanitizer) trip it.
   auto spin_check = [&](unsigned& spins, long long&) {
     if ((++spins & 0xFFFFu) != 0) return;
     if (*((volatile int32_t*)p.status) != 0 || spins >= (1u << 23)) {
+      atomicExch(p.status, QP_ETIMEOUT);
+      __threadfence_system();
+      __trap();
+    }
+  };
+  auto spin_check_bar = [&](unsigned& spins) {
+    if ((++spins & 0xFFFFu) != 0) return;
+    if (*((volatile int32_t*)p.status) != 0 || spins >= (1u << 26)) {
       atomicExch(p.status, QP_ETIMEOUT);
       __threadfence_system();
       __trap();
@@ -533,8 +543,8 @@ __global__ void __launch_bounds__(NT, 1) f3_gen_kernel(Plan p, GenArgsDev g) {
   auto waitb = [&](int i) {
     const uint32_t b = bar(i);
     const unsigned parity = (unsigned)(par >> i) & 1u;
-    unsigned spins = 0; long long t0 = 0;
-    while (!mbar_try(b, parity)) spin_check(spins, t0);
+    unsigned spins = 0;
+    while (!mbar_try(b, parity)) spin_check_bar(spins);
     par ^= 1ull << i;
   };
   // slot and tag of x_l at step t (real steps: ring position; priming passes: slot 0, pass parity)
