@@ -13,7 +13,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libqpnet_b200.so")
-SOURCES = ["qp_util.cu", "qp_pack.cu", "qp_forward.cu", "qp_backward.cu", "qp_generate.cu", "qp_generate_fold2.cu", "qp_generate_f3.cu", "qp_tc.cu", "qp_optim.cu"]
+SOURCES = ["qp_util.cu", "qp_pack.cu", "qp_forward.cu", "qp_backward.cu", "qp_generate.cu", "qp_generate_fold2.cu", "qp_generate_f3.cu", "qp_generate_f3x2.cu", "qp_tc.cu", "qp_optim.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "--use_fast_math=false", "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=default"]
 

@@ -793,8 +793,8 @@ __global__ void __launch_bounds__(GEN_THREADS, 1) gen_kernel(GenPlan p, GenArgsD
 }  // namespace qp
 
 namespace qp {
-// generators for the SI default widths: qp_generate_fold2.cu (mma.sync, <= 32 utterances) and qp_generate_f3.cu
-// (tcgen05, <= 128 utterances per launch)
+// generators for the SI default widths: qp_generate_fold2.cu (mma.sync, <= 32 utterances), qp_generate_f3.cu
+// (tcgen05, <= 128 utterances per launch) and qp_generate_f3x2.cu (tcgen05, two groups of 128: 129..256 utterances)
 int f2_generate(const QpArch* arch, const float* const* tensors_host, const QpGenerateArgs* a, void* ws, size_t ws_bytes,
                 cudaStream_t st);
 size_t f2_workspace_bytes(const QpArch* arch, int B, int M);
@@ -805,17 +805,24 @@ int f3_generate(const QpArch* arch, const float* const* tensors_host, const QpGe
 size_t f3_workspace_bytes(const QpArch* arch, int B, int M);
 bool f3_supported(const QpArch* arch, int B);
 int f3_trace_copy(const QpArch* arch, int B, int M, void* ws, size_t ws_bytes, long long* out_host, int n, cudaStream_t st);
+int f3x2_generate(const QpArch* arch, const float* const* tensors_host, const QpGenerateArgs* a, void* ws, size_t ws_bytes,
+                  cudaStream_t st);
+size_t f3x2_workspace_bytes(const QpArch* arch, int B, int M);
+bool f3x2_supported(const QpArch* arch, int B);
+int f3x2_trace_copy(const QpArch* arch, int B, int M, void* ws, size_t ws_bytes, long long* out_host, int n, cudaStream_t st);
 int pcm16_rows(const int32_t* sym, long long ld, int B, int n_steps, int n_quantize, int16_t* out, long long ld_out, cudaStream_t st);   // qp_util.cu
-static thread_local int g_last_kernel = 0;   // 4: tcgen05 folded (f3), 3: two-level folded mma.sync (fold2), 0: generic
-// QPNET_GEN_KERNEL = f3 | fold2 | generic selects the generator (debugging / A-B timing).  Default: the mma.sync kernel
-// up to 32 utterances (44 us per sample step), the tcgen05 kernel above (86 us at 32, 123 us at 128 utterances:
-// profiles/r02e_*), the generic kernel for everything else
+static thread_local int g_last_kernel = 0;   // 5: tcgen05, two groups (f3x2), 4: tcgen05 (f3), 3: two-level folded mma.sync (fold2), 0: generic
+// QPNET_GEN_KERNEL = f3x2 | f3 | fold2 | generic selects the generator (debugging / A-B timing).  Default: the mma.sync
+// kernel up to 32 utterances (44 us per sample step), the tcgen05 kernel up to 128 (80 us at 128), its two-group variant
+// up to 256 (131 us at 256; profiles/r02x_*), the generic kernel for everything else
 static int wanted_kernel(const QpArch* arch, int B) {
   const char* e = getenv("QPNET_GEN_KERNEL");
-  int want = (B <= 32 && f2_supported(arch, B)) ? 3 : 4;
+  int want = (B <= 32 && f2_supported(arch, B)) ? 3 : (B <= 128 ? 4 : 5);
   if (e && strcmp(e, "generic") == 0) want = 0;
   else if (e && strcmp(e, "fold2") == 0) want = 3;
-  else if (e && strcmp(e, "f3") == 0) want = 4;
+  else if (e && strcmp(e, "f3") == 0) want = B <= 128 ? 4 : 5;   // "the tcgen05 kernel": the variant that takes this many utterances
+  else if (e && strcmp(e, "f3x2") == 0) want = 5;
+  if (want == 5 && !f3x2_supported(arch, B)) want = 4;
   if (want == 4 && !f3_supported(arch, B)) want = 3;
   if (want == 3 && !f2_supported(arch, B)) want = 0;
   return want;
@@ -854,6 +861,7 @@ size_t qp_generate_workspace_bytes(const QpArch* arch, int32_t B, int32_t M) {
   size_t n = make_gen_plan(arch, B, 1, M, nullptr, 0, &p);
   if (f2_supported(arch, B)) n = std::max(n, f2_workspace_bytes(arch, B, M));
   if (f3_supported(arch, B)) n = std::max(n, f3_workspace_bytes(arch, B, M));
+  if (wanted_kernel(arch, B) == 5) n = std::max(n, f3x2_workspace_bytes(arch, B, M));   // its rings are sized for 256 utterances
   return n;
 }
 
@@ -865,7 +873,7 @@ int qp_generate(const QpArch* arch, const float* const* tensors_host, const QpGe
   int r = generate_symbols(arch, tensors_host, a, ws, ws_bytes, stream);
   if (r != QP_OK) return r;
   // PCM output stage (qpnet_decode.py:315-318): the tcgen05 generator writes it itself, the others are post-processed
-  if (a->out_pcm && g_last_kernel != 4)
+  if (a->out_pcm && g_last_kernel < 4)
     return pcm16_rows(a->out, a->ld_out, a->B, a->max_steps, arch->n_quantize, a->out_pcm, a->ld_out_pcm, (cudaStream_t)stream);
   return QP_OK;
 }
@@ -879,6 +887,12 @@ static int generate_symbols(const QpArch* arch, const float* const* tensors_host
   cudaStream_t st = (cudaStream_t)stream;
   g_last_kernel = 0;
   int want = wanted_kernel(arch, a->B);
+  if (want == 5) {
+    int r = f3x2_generate(arch, tensors_host, a, ws, ws_bytes, st);
+    if (r != 1) { g_last_kernel = 5; return r; }   // 1: the clusters cannot be co-resident here -> next kernel
+    reset_launch_count();
+    want = f3_supported(arch, a->B) ? 4 : (f2_supported(arch, a->B) ? 3 : 0);
+  }
   if (want == 4) {
     int r = f3_generate(arch, tensors_host, a, ws, ws_bytes, st);
     if (r != 1) { g_last_kernel = 4; return r; }   // 1: the clusters cannot be co-resident here -> next kernel
@@ -946,6 +960,7 @@ int qp_workspace_status(const void* ws, void* stream) {
 // debug only (not part of the public header): copy the per-phase clock64 trace of CTA 0
 int qp_debug_gen_trace(const QpArch* arch, int32_t B, int32_t M, void* ws, size_t ws_bytes, long long* out_host,
                        int32_t n, void* stream) {
+  if (g_last_kernel == 5) return f3x2_trace_copy(arch, B, M, ws, ws_bytes, out_host, n, (cudaStream_t)stream);
   if (g_last_kernel == 4) return f3_trace_copy(arch, B, M, ws, ws_bytes, out_host, n, (cudaStream_t)stream);
   if (g_last_kernel == 3) return f2_trace_copy(arch, B, M, ws, ws_bytes, out_host, n, (cudaStream_t)stream);
   GenPlan p;

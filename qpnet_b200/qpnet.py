@@ -150,7 +150,7 @@ class _TeacherForced(torch.autograd.Function):
 class QPNet(nn.Module):
     """QUASI-PERIODIC WAVENET -- same constructor as qpnet.py:174-178."""
 
-    GROUP = 128     # utterances per launch of the tcgen05 cluster generator (qp_generate_f3.cu)
+    GROUP = 256     # utterances per launch of the tcgen05 cluster generators (qp_generate_f3.cu: 128, qp_generate_f3x2.cu: 256)
 
     def __init__(self, n_quantize=256, n_aux=39, n_resch=512, n_skipch=256,
                  dilationF_depth=4, dilationF_repeat=3, dilationA_depth=4, dilationA_repeat=1,
@@ -279,8 +279,8 @@ class QPNet(nn.Module):
         stage of qpnet_decode.py:315-318); ``utt_ids`` (B,) int: caller-side utterance indices keying the Philox stream
         (default: the position in this call).
 
-        The tcgen05 cluster generator runs up to 128 utterances per launch.  A larger batch of the SI default widths is
-        dealt to launches of 128, longest first, so every launch retires at its own last step (the reference's decoder
+        The tcgen05 cluster generators run up to 256 utterances per launch (two groups of 128 above 128).  A larger batch
+        of the SI default widths is dealt to launches of 256, longest first, so every launch retires at its own last step (the reference's decoder
         sorts by length for the same reason, qpnet_decode.py:257-259); ``utt_ids`` keeps every utterance on the Philox
         stream of its caller-side index, so the symbols do not depend on the grouping."""
         B = h.shape[0]
@@ -317,7 +317,7 @@ class QPNet(nn.Module):
 
     def _generate_launch(self, seed, h, d, n_dev, max_n, qmode, uniforms, force, return_logits, check_status, utt_ids,
                          pcm_out=None):
-        """One qp_generate call (<= 128 utterances on the tcgen05 cluster kernel, any number on the generic one)."""
+        """One qp_generate call (<= 256 utterances on the tcgen05 cluster kernels, any number on the generic one)."""
         params = self._tensors()
         dev = params[0].device
         ops._need_cuda(seed, h, d, n_dev)

@@ -390,15 +390,18 @@ def test_generator_is_deterministic_and_batch_independent(dev):
         assert np.array_equal(solo[0], r)
 
 
-def test_generator_large_batch_is_dealt_to_launches_of_128(dev, monkeypatch):
-    """More than 128 utterances of the SI default widths: dealt to launches of 128, longest first (host wrapper).  Every
-    utterance must come out exactly as in a solo call -- same Philox stream (utt_ids), same arithmetic (the kernel is
-    pinned: by default a solo call runs on the mma.sync kernel, whose bf16 rounding differs from the tcgen05 one)."""
+def test_generator_large_batch_is_dealt_to_launches_of_256(dev, monkeypatch):
+    """More than 256 utterances of the SI default widths: dealt to launches of 256, longest first (host wrapper): here one
+    launch of 256 on the two-group tcgen05 kernel (qp_generate_f3x2.cu) and one of 3 on the single-group one
+    (qp_generate_f3.cu).  Every utterance must come out exactly as in a solo call on the single-group kernel -- same Philox
+    stream (utt_ids), same arithmetic: the two tcgen05 kernels accumulate the same products in the same order, so their
+    symbols are identical (the kernel family is pinned: by default a solo call runs on the mma.sync kernel, whose bf16
+    rounding differs)."""
     monkeypatch.setenv("QPNET_GEN_KERNEL", "f3")
     a = orc.Arch()
     p = orc.init_params(a, 8, 0.05)
     m = _model({}, p, dev)
-    B = 131
+    B = 259
     frames = [1 + (b % 2) for b in range(B)]
     Fm = max(frames)
     h = np.zeros((B, a.A, Fm), np.float32)
@@ -408,13 +411,13 @@ def test_generator_large_batch_is_dealt_to_launches_of_128(dev, monkeypatch):
         hs, f0, n = synth.utterance(frames[b], 900 + b, 1.0, a.A)
         h[b, :, :frames[b]] = hs.T
         d[b, :frames[b] * a.U] = cases.d_from_f0(f0)
-        n_list.append(min(n, 40 + b))
+        n_list.append(min(n, 40 + b // 2))
     x = torch.full((B, 1), a.Q // 2, dtype=torch.long)
     m.philox_seed = 5
     res = m.batch_fast_generate(x, torch.from_numpy(h), list(n_list), d)
     order = np.argsort(np.array(n_list), kind="stable")
     assert [len(r) for r in res] == sorted(n_list)
-    for b in (0, 17, 130):
+    for b in (0, 1, 17, 130, 200, 258):            # 0, 1 ride in the short launch of 3, the others in the two groups of the long one
         pos = list(order).index(b)
         solo = m.batch_fast_generate(x[b:b + 1], torch.from_numpy(h[b:b + 1]), [n_list[b]], d[b:b + 1])
         # a solo call keys Philox with slot 0, the batch with the caller-side index b: compare through generate_device
@@ -483,7 +486,7 @@ def test_generator_utterance_groups_vs_oracle(dev, monkeypatch, kw, B, groups):
 
 @pytest.mark.parametrize("fac", [1.0, 0.5, 1.5])
 def test_generator_full_model_every_kernel_vs_oracle(dev, monkeypatch, fac):
-    """SI default architecture on every generator kernel (QPNET_GEN_KERNEL = f3 | fold2 | generic), with the
+    """SI default architecture on every generator kernel (QPNET_GEN_KERNEL = f3 | f3x2 | fold2 | generic), with the
     F0 contour scaled x0.5 / x1.5 (BASELINE configs[2]: longest and shortest pitch-dependent look-backs, ring depth up to
     8 * ceil(max d)).  Teacher-forced per-step logits against the CPU oracle, 0.06 absolute; the steps run past the
     look-back of the first adaptive blocks so the rings are read back, not only primed."""
@@ -504,7 +507,7 @@ def test_generator_full_model_every_kernel_vs_oracle(dev, monkeypatch, fac):
                      max_steps=steps)
     want = torch.stack(lg, dim=1)
     m = _model({}, p, dev)
-    for kernel in ("f3", "fold2", "generic"):
+    for kernel in ("f3", "f3x2", "fold2", "generic"):
         monkeypatch.setenv("QPNET_GEN_KERNEL", kernel)
         res, got = m.batch_fast_generate(x, torch.from_numpy(h), [steps] * B, d, None, "argmax", False, force=forced,
                                          return_logits=True)

@@ -132,7 +132,7 @@ def ringwrap_oracle():
     return a, p, x, h, d, forced, steps, torch.stack(lg, dim=1)
 
 
-@pytest.mark.parametrize("kernel", ["f3", "fold2"])
+@pytest.mark.parametrize("kernel", ["f3", "f3x2", "fold2"])
 def test_generator_full_group_ring_wrap_vs_oracle(dev, monkeypatch, ringwrap_oracle, kernel):
     """The benchmarked kernels at the benchmark's batch (32 utterances), lowest pitch (F0 x0.5: look-backs up to
     8 * 123 samples), for 2 300 steps so that every past-tap ring wraps at least twice; per-step logits of every
@@ -150,10 +150,11 @@ def test_generator_full_group_ring_wrap_vs_oracle(dev, monkeypatch, ringwrap_ora
     assert all(len(r) == steps for r in res)
 
 
-@pytest.mark.parametrize("B,fac", [(128, 1.0), (77, 1.5)])
+@pytest.mark.parametrize("B,fac", [(128, 1.0), (77, 1.5), (256, 1.0), (150, 0.5)])
 def test_generator_large_group_vs_oracle(dev, monkeypatch, B, fac):
-    """The tcgen05 generator with a full 128-utterance group (and a ragged one): per-step logits of EVERY utterance
-    under forced symbols against the oracle, 0.06 absolute; 260 steps read the first adaptive rings back."""
+    """The tcgen05 generators with a full 128-utterance group and a ragged one (qp_generate_f3.cu), two full groups and a
+    full + ragged pair (qp_generate_f3x2.cu): per-step logits of EVERY utterance under forced symbols against the oracle,
+    0.06 absolute; 260 steps read the first adaptive rings back."""
     torch.set_num_threads(os.cpu_count() or 1)
     a = orc.Arch()
     p = orc.init_params(a, 43, 0.05)
@@ -239,7 +240,7 @@ def test_training_step_bf16_tensor_cores_adam_update(dev):
     assert float(loss) < l0
 
 
-@pytest.mark.parametrize("kernel,B", [("f3", 40), ("fold2", 5), ("generic", 5)])
+@pytest.mark.parametrize("kernel,B", [("f3", 40), ("f3x2", 140), ("fold2", 5), ("generic", 5)])
 def test_generator_pcm16_output_stage(dev, monkeypatch, kernel, B):
     """The generator's PCM output stage (QpGenerateArgs.out_pcm; qpnet_decode.py:315-318: decode_mu_law * 32768, clipped,
     int16): equal, sample for sample, to the oracle's write-out of the symbols the same launch produced -- on the tcgen05

@@ -1,7 +1,8 @@
 #!/usr/bin/env python3
-"""Per-phase clock64 trace of CTA 0 of the tcgen05 generator (qp_generate_f3.cu, QPNET_GEN_TRACE_STEP).
+"""Per-phase clock64 trace of one CTA of the tcgen05 generators (QPNET_GEN_TRACE_STEP; qp_generate_f3.cu up to 128
+utterances, qp_generate_f3x2.cu above or with --x2: both groups, any CTA through QPNET_GEN_TRACE_CTA).
 
-    python tools/f3_trace.py [--utts 128] [--frames 20] [--step 1000]
+    python tools/f3_trace.py [--utts 128] [--frames 20] [--step 1000] [--x2]
 
 Events per phase j (block j; phase L = final skip): 0 MMA thread sees the staged z_{j-1} tile, 1 gate MMAs committed,
 2 ET thread 0: tile complete in TMEM, 3 partial rows sent, 4 partial rows of the cluster arrived, 5 z_j published,
@@ -24,9 +25,11 @@ def main():
     ap.add_argument("--utts", type=int, default=128)
     ap.add_argument("--frames", type=int, default=20)
     ap.add_argument("--step", type=int, default=1000)
+    ap.add_argument("--x2", action="store_true", help="the two-group kernel also for <= 128 utterances")
     args = ap.parse_args()
     os.environ["QPNET_GEN_TRACE_STEP"] = str(args.step)
-    os.environ["QPNET_GEN_KERNEL"] = "f3"
+    x2 = args.x2 or args.utts > 128
+    os.environ["QPNET_GEN_KERNEL"] = "f3x2" if x2 else "f3"
     import bench
     from qpnet_b200 import _lib, ops
     from qpnet_b200.qpnet import QPNet, initialize
@@ -48,8 +51,8 @@ def main():
         e1.record()
         torch.cuda.synchronize()
         print(f"kernel ms {e0.elapsed_time(e1):.2f}  us/step {e0.elapsed_time(e1) * 1e3 / (max(n_list) + 16):.2f}")
-    nphase, nev = L + 4, 24
-    n_g = 128 * nphase * 4
+    nphase, nev, ngt = L + 4, (64 if x2 else 24), (8 if x2 else 4)
+    n_g = 128 * nphase * ngt
     n = 8 * nphase * nev + n_g
     buf = (C.c_longlong * n)()
     fn = _lib.lib.qp_debug_gen_trace
@@ -59,7 +62,9 @@ def main():
     fn(m._arch, args.utts, ops.max_ceil(d64), ws.data_ptr(), ws.numel(), buf, n, None)
     allbuf = np.array(buf, dtype=np.int64)
     tr = allbuf[:8 * nphase * nev].reshape(8, nphase, nev)
-    gt = allbuf[8 * nphase * nev:].reshape(128, nphase, 4).astype(np.float64)
+    gt2 = allbuf[8 * nphase * nev:].reshape(128, nphase, ngt // 4, 4).astype(np.float64)
+    gt2[gt2 == 0] = np.nan
+    gt = gt2[:, :, 0, :]
     gt[gt == 0] = np.nan
     labels = ["pub(j-1)->staged", "staged->mma", "mma issue", "commit->TMEM seen", "ld+send", "send->arrived", "finish+publish"]
     acc = np.zeros(7)
@@ -82,12 +87,14 @@ def main():
              2: "ET tile in TMEM", 3: "ET sent", 4: "ET arrived", 5: "ET z published", 11: "PZ z buffer free", 12: "PZ first piece fresh", 6: "PZ z staged",
              13: "EU tile in TMEM", 14: "EU sent", 15: "EU arrived", 16: "EU x published", 17: "PX past buffer free", 18: "PX past copies issued",
              19: "PX x buffer free", 20: "PX first x piece fresh", 21: "PX x staged"}
+    names.update({22: "MMA Wc chunk seen", 23: "MMA Wp chunk seen"})
     for j in (5, 6, 13):
         e = tr[2, j]
         base = e[0]
-        print(f"--- timeline of phase {j} (step {args.step + 2}), cycles relative to 'MMA z seen':")
-        for ev, tstamp in sorted(((k, int(e[k])) for k in names if e[k] != 0), key=lambda kv: kv[1]):
-            print(f"    {tstamp - base:8d}  {names[ev]}")
+        print(f"--- timeline of phase {j} (step {args.step + 2}), cycles relative to 'MMA z seen' of group 0:")
+        evs = [(int(e[32 * g + k]), f"g{g} {names[k]}") for g in range(2 if x2 else 1) for k in names if 32 * g + k < nev and e[32 * g + k] != 0]
+        for tstamp, label in sorted(evs):
+            print(f"    {tstamp - base:8d}  {label}")
     acc /= cnt
     print("mean over blocks 1..L-1 of 6 steps: " + "  ".join(f"{lab} {v:.0f}" for lab, v in zip(labels, acc)) + f"  | phase {acc.sum():.0f}")
     # every CTA on the global clock (ns), one step: how far apart do the CTAs publish / see a complete tile?
@@ -99,6 +106,12 @@ def main():
         print(f"blk{j:02d} staged {np.nanmin(stg) - t0:8.0f} .. {np.nanmax(stg) - t0:8.0f} | arrived {np.nanmin(arr) - t0:8.0f} .. {np.nanmax(arr) - t0:8.0f} | "
               f"z published {np.nanmin(pub) - t0:8.0f} .. {np.nanmax(pub) - t0:8.0f} (slowest CTA {int(np.nanargmax(pub))}) | x published {np.nanmin(xpub) - t0:8.0f} .. {np.nanmax(xpub) - t0:8.0f} | "
               f"next staged - last published {np.nanmin(nxt) - np.nanmax(pub):6.0f} .. {np.nanmax(nxt) - np.nanmax(pub):6.0f}")
+    if x2 and not np.all(np.isnan(gt2[:, :, 1, :])):
+        print("--- both groups, z staged (min .. max over CTAs) and z published, ns:")
+        for j in range(1, L):
+            print(f"blk{j:02d} " + " | ".join(f"g{g} staged {np.nanmin(gt2[:, j, g, 1]) - t0:8.0f} .. {np.nanmax(gt2[:, j, g, 1]) - t0:8.0f} published {np.nanmin(gt2[:, j, g, 0]) - t0:8.0f} .. {np.nanmax(gt2[:, j, g, 0]) - t0:8.0f}" for g in range(2)))
+        for cta in (0, 1, 26, 112):
+            print(f"CTA {cta}: " + "  ".join(f"j{j}: g0 {gt2[cta, j, 0, 1] - t0:.0f} g1 {gt2[cta, j, 1, 1] - t0:.0f}" for j in range(3, 8)))
     tot = np.mean([tr[st + 1, 0, 5] - tr[st, 0, 5] for st in range(1, 7)])
     tail = np.mean([tr[st + 1, 0, 5] - tr[st, L - 1, 5] for st in range(1, 7)])
     print(f"step total (mean) {tot:.0f} cycles; after the last gate (final skip, heads, sampling, block 0): {tail:.0f}")
