@@ -4,12 +4,11 @@
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--scaling weak|strong]
 
 Workload (config.workload): batch fast generation of synthetic 5 s utterances (1000 frames -> 109 999 samples each) with
-the SI default model, random-init weights, synthetic WORLD-style aux features and F0 contours, sampling mode, 128
-utterances per GPU -- the per-GPU share of BASELINE.json configs[3] (256 utterances over 2 GPUs), the largest
-single-GPU configuration in `configs`, and the batch at which the tcgen05 generator runs.  A "step" is one full pass of
-the hot path over that batch.  With N > 1 ranks (torchrun) every rank generates its own 128 utterances (utterance
-sharding, no collective: weak scaling); `--scaling strong` shards configs[3]'s 256 utterances over the ranks instead
-(256 / N per GPU).  BASELINE configs[1] (32 utterances on one GPU) is measured in the same run and reported under
+the SI default model, random-init weights, synthetic WORLD-style aux features and F0 contours, sampling mode, 256
+utterances per GPU -- the batch of BASELINE.json configs[3] on one GPU, the largest single-GPU configuration in
+`configs`, and one launch of the two-group tcgen05 generator.  A "step" is one full pass of the hot path over that batch.
+With N > 1 ranks (torchrun) every rank generates its own 256 utterances (utterance sharding, no collective: weak
+scaling); `--scaling strong` shards configs[3]'s 256 utterances over the ranks instead (256 / N per GPU).  BASELINE configs[1] (32 utterances on one GPU) is measured in the same run and reported under
 `configs1_32_utterances`, configs[2] (F0 x0.5 / x1.5) under `configs2_f0_scaled`, configs[0] (the CPU case) under
 `configs0_cpu`, configs[4] (training) under `train`.
 
@@ -41,7 +40,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-UTTS_PER_GPU = 128       # per-GPU share of configs[3] at 2 GPUs; one launch of the tcgen05 generator
+UTTS_PER_GPU = 256       # configs[3]'s batch on one GPU; one launch of the two-group tcgen05 generator
 UTTS_STRONG = 256        # configs[3]: 256 utterances over the box
 FRAMES = 1000            # 5 s at 5 ms shift
 FS = 22050
@@ -211,7 +210,7 @@ def roofline_of(kernel_s, n_utts, max_n, kernel, prime_steps):
 
 KERNEL_NOTE = ("SURVEY.md 8(d) models the step as weight-bandwidth bound (47.25 MB of bf16 weights per step + 31.7 KB of state "
                "per utterance); the step is in fact a chain of L + 3 = 19 dependent cross-SM exchanges (16 blocks, skip, 2 head "
-               "layers) + sampling, each ~5 us at 128 utterances (profiles/r02h_*), so frac is small by construction")
+               "layers) + sampling, each ~4 us per group of 128 utterances (profiles/r02h_*, r02x_*), so frac is small by construction")
 
 
 def workload_config(n_gpus, per_gpu, scaling, frames):
@@ -219,7 +218,7 @@ def workload_config(n_gpus, per_gpu, scaling, frames):
     return {"workload": f"QPNet SI default, batch_fast_generate of {per_gpu} synthetic 5 s utterances per GPU ({frames} frames, "
                         f"{frames * 110 - 1} samples each), mode=sampling, extra_memory=False: "
                         + ("BASELINE configs[3] (256 utterances over the box) sharded over the ranks" if scaling == "strong" else
-                           "the per-GPU share of BASELINE configs[3] at 2 GPUs (the largest single-GPU configuration; "
+                           "the batch of BASELINE configs[3] on every GPU (the largest single-GPU configuration; "
                            "configs[1], 32 utterances, is reported under configs1_32_utterances)"),
             "utterances_per_gpu": per_gpu, "utterances_total": tot,
             "samples_per_utterance": frames * 110 - 1, "parallelism": f"utterance-sharded x{n_gpus}, no collective",
@@ -261,7 +260,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
-                    help="weak: 128 utterances per GPU; strong: BASELINE configs[3], 256 utterances over the ranks")
+                    help="weak: 256 utterances per GPU; strong: BASELINE configs[3], 256 utterances over the ranks")
     ap.add_argument("--frames", type=int, default=FRAMES, help="(debug) frames per utterance")
     ap.add_argument("--utts", type=int, default=0, help="(debug) utterances per GPU")
     ap.add_argument("--ref-sample-steps", type=int, default=40)
@@ -424,9 +423,9 @@ def main():
         return
 
     kernel_s = (sum(dev_ms) / len(dev_ms)) / 1e3       # events bracket pack + generator; the generator is > 99.9 %
-    n_launch = (n_utts + 127) // 128
-    kernel = "qp::f3::f3_gen_kernel" if n_utts > 32 else "qp::f2::f2_gen_kernel"
-    roofline = roofline_of(kernel_s / n_launch, min(n_utts, 128), max_n, kernel, 16)
+    n_launch = (n_utts + 255) // 256
+    kernel = ("qp::f3x2::f3x2_gen_kernel" if n_utts > 128 else "qp::f3::f3_gen_kernel") if n_utts > 32 else "qp::f2::f2_gen_kernel"
+    roofline = roofline_of(kernel_s / n_launch, min(n_utts, 256), max_n, kernel, 16)
     roofline["note"] = KERNEL_NOTE
 
     cpu = None

@@ -1,2 +1,1 @@
-timeout 1500 python -m pytest tests -m gpu -q -k "generator or deep_preset_full or decode" 2>&1 | tail -6
-for u in 256 192 160 128; do QPNET_GEN_KERNEL=f3 timeout 200 python tools/ab_kernels.py --utts $u --frames 60 --kernels f3 --reps 1; done
+for w in 0 1 2 3; do echo "== wpol $w"; QPNET_F3_WPOL=$w QPNET_GEN_KERNEL=f3x2 timeout 200 python tools/ab_kernels.py --utts 256 --frames 60 --kernels f3x2 --reps 1; done

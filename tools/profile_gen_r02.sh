@@ -1,7 +1,7 @@
 #!/bin/bash
 # ncu evidence for the generators, round 2 (run under gpurun, one GPU):
 #   1. launch list of a short bench run (per-launch gpu__time_duration, cold-cache, serialised)
-#   2. per kernel (tcgen05 f3 at 128 utterances, mma.sync fold2 at 32): two light captures (5 and 20 frames) ->
+#   2. per kernel (tcgen05 f3x2 at 256 utterances, f3 at 128, mma.sync fold2 at 32): two light captures (5 and 20 frames) ->
 #      steady-state DRAM traffic per sample step; one --set full capture of the longer run
 # The persistent kernels are launched without the cooperative attribute under the profiler (QPNET_GEN_NOCOOP).
 out=gpurun_out
@@ -9,7 +9,7 @@ tag=${1:-r02}
 export QPNET_GEN_NOCOOP=1
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $out/${tag}_launches_bench.csv \
     python bench.py --steps 1 --warmup 1 --frames 60 --no-cpu-baseline --no-train --no-extras > $out/${tag}_bench_under_ncu.log 2>&1
-for spec in "f3 128 f3_gen_kernel" "fold2 32 f2_gen_kernel"; do
+for spec in "f3x2 256 f3x2_gen_kernel" "f3 128 f3_gen_kernel" "fold2 32 f2_gen_kernel"; do
   set -- $spec
   for f in 5 20; do
     QPNET_GEN_KERNEL=$1 timeout 600 ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,lts__t_sector_hit_rate.pct,gpu__time_duration.sum,sm__inst_executed_pipe_tensor.sum,sm__pipe_tensor_op_hmma_cycles_active.avg.pct_of_peak_sustained_active \
@@ -26,13 +26,16 @@ def load(p):
     d = {}
     for r in csv.reader(open(p)):
         if len(r) > 14 and r[0].isdigit():
-            d[r[12]] = (float(r[14].replace(",", "")), r[13])
+            try:
+                d[r[12]] = (float(r[14].replace(",", "")), r[13])
+            except ValueError:      # "n/a": the metric does not exist on this chip
+                pass
     return d
 def val(x):
     v, u = x
     return v * {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1}.get(u, 1)
 res = {"kernels": {}}
-for name, kern, utts in (("f3", "qp::f3::f3_gen_kernel", 128), ("fold2", "qp::f2::f2_gen_kernel", 32)):
+for name, kern, utts in (("f3x2", "qp::f3x2::f3x2_gen_kernel", 256), ("f3", "qp::f3::f3_gen_kernel", 128), ("fold2", "qp::f2::f2_gen_kernel", 32)):
     try:
         a, b = load(f"gpurun_out/{tag}_traffic_{name}_f5.csv"), load(f"gpurun_out/{tag}_traffic_{name}_f20.csv")
         steps = (20 - 5) * 110
@@ -40,8 +43,8 @@ for name, kern, utts in (("f3", "qp::f3::f3_gen_kernel", 128), ("fold2", "qp::f2
         wr = (val(b["dram__bytes_write.sum"]) - val(a["dram__bytes_write.sum"])) / steps
         res["kernels"][kern] = {"utterances": utts, "dram_bytes_per_step": rd + wr, "dram_read_per_step": rd, "dram_write_per_step": wr,
                                 "l2_sector_hit_rate_pct": b["lts__t_sector_hit_rate.pct"][0],
-                                "kernel_duration_20_frames": list(b["gpu__time_duration.sum"]),
-                                "tensor_pipe_active_pct": b.get("sm__pipe_tensor_op_hmma_cycles_active.avg.pct_of_peak_sustained_active", (None,))[0],
+                                "us_per_step_under_ncu": (val(b["gpu__time_duration.sum"]) - val(a["gpu__time_duration.sum"])) / steps / 1e3,
+                                "tensor_pipe_inst_per_step": (b["sm__inst_executed_pipe_tensor.sum"][0] - a["sm__inst_executed_pipe_tensor.sum"][0]) / steps,
                                 "source": "ncu dram__bytes_read.sum + dram__bytes_write.sum of two captures (tools/profile_gen_r02.sh: 5 and 20 frames), difference per sample step"}
         print(name, res["kernels"][kern])
     except Exception as e:
