@@ -196,6 +196,13 @@ def ncu_traffic_per_step(kernel):
     return None
 
 
+def kernel_of(n_utts):
+    """The generator kernel a launch of n_utts utterances of the SI default model runs on (qp_generate.cu: wanted_kernel)."""
+    if n_utts <= 32:
+        return "qp::f2::f2_gen_kernel"
+    return "qp::f3::f3_gen_kernel" if n_utts <= 128 else "qp::f3x2::f3x2_gen_kernel"
+
+
 def roofline_of(kernel_s, n_utts, max_n, kernel, prime_steps):
     peak, peak_src = peaks()
     steps_per_launch = max_n + prime_steps
@@ -264,7 +271,7 @@ def main():
     ap.add_argument("--frames", type=int, default=FRAMES, help="(debug) frames per utterance")
     ap.add_argument("--utts", type=int, default=0, help="(debug) utterances per GPU")
     ap.add_argument("--ref-sample-steps", type=int, default=40)
-    ap.add_argument("--cpu-sample-steps", type=int, default=60)
+    ap.add_argument("--cpu-sample-steps", type=int, default=240)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip configs[0] / [1] / [2], the eager-GPU port and the sample-match probe")
     ap.add_argument("--no-train", action="store_true", help="skip the train seg/s probe")
@@ -389,7 +396,7 @@ def main():
         extras["configs1_32_utterances"] = {
             "workload": "BASELINE configs[1]: batch fast generation of 32 synthetic 5 s utterances on 1 x B200",
             "value": sum(nl32) / s32, "unit": "samples/s", "real_time_factor": sum(nl32) / s32 / FS, "steps": 2, "warmup": 1,
-            "roofline": roofline_of(s32, 32, max(nl32), "qp::f2::f2_gen_kernel", 16)}
+            "roofline": roofline_of(s32, 32, max(nl32), kernel_of(32), 16)}
         # configs[2]: the F0 contour scaled x0.5 (longest look-backs, ring depth 8 * ceil(max d)) and x1.5 (shortest)
         c2 = {}
         for fac in (0.5, 1.5):
@@ -398,7 +405,7 @@ def main():
             sf = msf[0] / 1e3
             c2[f"f0_x{fac}"] = {"value": sum(nlf) / sf, "unit": "samples/s", "real_time_factor": sum(nlf) / sf / FS,
                                 "utterances": n_utts, "max_dilated_factor": float(np.ceil((FS / f0f / 8).max())), "steps": 1, "warmup": 1,
-                                "roofline": roofline_of(sf, n_utts, max(nlf), "qp::f3::f3_gen_kernel", 16)}
+                                "roofline": roofline_of(sf / ((n_utts + 255) // 256), min(n_utts, 256), max(nlf), kernel_of(min(n_utts, 256)), 16)}
         extras["configs2_f0_scaled"] = c2
         # free-running generation under shared pre-drawn uniforms against the CPU oracle: sample-match rate
         try:
@@ -424,7 +431,7 @@ def main():
 
     kernel_s = (sum(dev_ms) / len(dev_ms)) / 1e3       # events bracket pack + generator; the generator is > 99.9 %
     n_launch = (n_utts + 255) // 256
-    kernel = ("qp::f3x2::f3x2_gen_kernel" if n_utts > 128 else "qp::f3::f3_gen_kernel") if n_utts > 32 else "qp::f2::f2_gen_kernel"
+    kernel = kernel_of(min(n_utts, 256))
     roofline = roofline_of(kernel_s / n_launch, min(n_utts, 256), max_n, kernel, 16)
     roofline["note"] = KERNEL_NOTE
 
