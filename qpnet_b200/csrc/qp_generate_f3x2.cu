@@ -15,6 +15,8 @@
 //     What was tried and measured slower or wrong: a second issuing thread for the x-products and a non-blocking
 //     two-stream scheduler on one thread (both let z-products overtake x-products: run-to-run different symbols through
 //     priming, and no faster once priming was kept in order), starting the groups up to 8 us apart (no effect).
+//   * the z-products of an item are ONE sequence of 8 UMMAs with N = 96 ([C_j | U_j | P_{j+1}]); the single-group kernel
+//     issues C_j separately first.  (256 utterances: 130.1 -> 129.5 us, 192: 123.5 -> 118.8 us per step.)
 //   * a ring slot is stored as the A tiles its readers stage, [4 K-shares][2 K-blocks][256 rows][128 B] with the 16-byte
 //     pieces of a row in SWIZZLE_128B order: the past-tap tile of a block with a fixed look-back is two contiguous 16 KB
 //     cp.async.bulk copies issued by one thread (adaptive blocks gather 16-byte pieces with cp.async, one slot per
@@ -1131,11 +1133,12 @@ __global__ void __launch_bounds__(NT, 1) f3x2_gen_kernel(Plan p, GenArgsDev g) {
             if (pre) waitb(gb(gi, G_PFREE + b));
             waitb(B_ZFULL);
             trace(t, gi, j, 0);
-            // C_j <- G_j z_{j-1} first (the tile the critical path waits for), then [U_j | P_{j+1}] <- [[R;K]_{j-1} ; H_{j+1}] z_{j-1}
-            mma(32, dbuf + TC_C, sZ, sWZ, ZPC_B / 2, true);
+            // [C_j | U_j | P_{j+1}] <- [G_j ; [R;K]_{j-1} ; H_{j+1}] z_{j-1}: ONE sequence of 8 instructions (N = 96).  The
+            // single-group kernel issues C_j on its own first (ready ~300 cycles earlier); here the issuing thread of the
+            // slowest CTAs is what every other CTA waits for, and 8 instructions instead of 16 is worth more
+            mma(pre ? 96 : 64, dbuf + TC_C, sZ, sWZ, ZPC_B / 2, true);
             umma_commit(bar(gb(gi, G_CFULL + b)));
             trace(t, gi, j, 1);
-            mma(pre ? 64 : 32, dbuf + TC_U, sZ, sWZ + 4096, ZPC_B / 2, true);   // rows 32.. of the chunk: atom 4 of each K-block
             umma_commit(bar(B_ZFREE)); umma_commit(bar(gb(gi, G_UFULL + b)));
             if (gi == ng - 1) umma_commit(bar(B_ZPW_FREE));
             // the x-products of this group go between the groups' z-products: the other group's z tile is staged meanwhile
