@@ -25,6 +25,9 @@
 //     never waiting for data; their MMA thread and PX warps are busy ~8k cycles per (phase, group) item -- z-products
 //     1.7k, waiting for the single-buffered Wc / Wp chunks 3.4k (group 0 only), x tile poll 2k, x-products 2k -- and every
 //     other CTA waits for their tiles.  Double-buffered A tiles and weight slots would need ~100 KB more shared memory.
+//     Finer events (profiles/r02ai_*): a UMMA costs the issuing thread ~75 cycles whatever its N, a tcgen05.commit ~110, so
+//     the 24 UMMAs and 7 - 9 commits of an item are ~2.7 k cycles of issue time, the waits for the x and past-tap tiles
+//     ~1.3 - 2 k; the weight chunks' latency plays no role (L2 policy sweep and a persisting-L2 window: no change).
 //
 // tcgen05 generator: QPNet.batch_fast_generate (qpnet.py:314-559) for the SI default widths (n_resch 512, n_skipch 256,
 // n_quantize 256), up to 256 utterances per launch, any number of residual blocks up to QP_MAX_LAYERS.
@@ -103,8 +106,9 @@ constexpr int HCH_E = 16 * KH, HCH_B = HCH_E * 2;     // head chunk: 16 rows (8 
 constexpr int ABLK = UB * 128;                         // bytes of one K-block of an A tile (128 rows x 128 B)
 constexpr int NWARP = 19, NT = NWARP * 32;
 constexpr int MAXA = 8;                                // adaptive blocks (look-back table in shared memory)
-// trace events of CTA 0 (QPNET_GEN_TRACE_STEP), group 0, per phase j.  MMA thread: 0 z tile seen, 1 gate product
-// committed, 8 x tile seen, 9 past-tap tile seen, 10 phase issued.  ET thread 0: 2 tiles in TMEM, 3 partial rows sent,
+// trace events of one CTA (QPNET_GEN_TRACE_STEP, QPNET_GEN_TRACE_CTA), per phase j and group (group g at event + 32 g).
+// MMA thread: 0 z tile seen, 24 z UMMAs issued, 1 / 25 / 26 / 27 after each commit, 22 Wc chunk seen, 8 x tile seen, 28 x
+// UMMAs issued, 29 x buffer committed, 23 Wp chunk seen, 9 past-tap tile seen, 10 phase issued.  ET thread 0: 2 tiles in TMEM, 3 partial rows sent,
 // 4 partial rows of the cluster arrived, 5 z published.  PZ thread 0: 11 z buffer free, 6 z staged.  EU thread 0: 13 U tile
 // in TMEM, 14 sent, 15 arrived, 16 x published.  PX thread 0: 17 past-tap buffer free, 18 past-tap copies issued, 19 x buffer
 // free, 21 x staged
@@ -1137,10 +1141,15 @@ __global__ void __launch_bounds__(NT, 1) f3x2_gen_kernel(Plan p, GenArgsDev g) {
             // single-group kernel issues C_j on its own first (ready ~300 cycles earlier); here the issuing thread of the
             // slowest CTAs is what every other CTA waits for, and 8 instructions instead of 16 is worth more
             mma(pre ? 96 : 64, dbuf + TC_C, sZ, sWZ, ZPC_B / 2, true);
+            trace(t, gi, j, 24);
             umma_commit(bar(gb(gi, G_CFULL + b)));
             trace(t, gi, j, 1);
-            umma_commit(bar(B_ZFREE)); umma_commit(bar(gb(gi, G_UFULL + b)));
+            umma_commit(bar(B_ZFREE));
+            trace(t, gi, j, 25);
+            umma_commit(bar(gb(gi, G_UFULL + b)));
+            trace(t, gi, j, 26);
             if (gi == ng - 1) umma_commit(bar(B_ZPW_FREE));
+            trace(t, gi, j, 27);
             // the x-products of this group go between the groups' z-products: the other group's z tile is staged meanwhile
             if (pre) {
               if (j >= 2) {   // P_{j+1} += Wc_{j+1} x_{j-1}
@@ -1149,7 +1158,9 @@ __global__ void __launch_bounds__(NT, 1) f3x2_gen_kernel(Plan p, GenArgsDev g) {
                 waitb(B_XFULL);
                 trace(t, gi, j, 8);
                 mma(32, dbuf + TC_P, sX, sWC, WCH_B / 2, false);
+                trace(t, gi, j, 28);
                 umma_commit(bar(B_XFREE));
+                trace(t, gi, j, 29);
                 if (gi == ng - 1) umma_commit(bar(B_WCW_FREE));
               }
               // P_{j+1} += Wp_{j+1} x_{j+1}(t-k)

@@ -87,7 +87,7 @@ def main():
              2: "ET tile in TMEM", 3: "ET sent", 4: "ET arrived", 5: "ET z published", 11: "PZ z buffer free", 12: "PZ first piece fresh", 6: "PZ z staged",
              13: "EU tile in TMEM", 14: "EU sent", 15: "EU arrived", 16: "EU x published", 17: "PX past buffer free", 18: "PX past copies issued",
              19: "PX x buffer free", 20: "PX first x piece fresh", 21: "PX x staged"}
-    names.update({22: "MMA Wc chunk seen", 23: "MMA Wp chunk seen"})
+    names.update({22: "MMA Wc chunk seen", 23: "MMA Wp chunk seen", 24: "MMA z UMMAs issued", 25: "MMA commit 2 done", 26: "MMA commit 3 done", 27: "MMA commit 4 done", 28: "MMA x UMMAs issued", 29: "MMA x commit done"})
     for j in (5, 6, 13):
         e = tr[2, j]
         base = e[0]
