@@ -547,8 +547,11 @@ __global__ void __launch_bounds__(NT, 1) f3_gen_kernel(Plan p, GenArgsDev g) {
     while (!mbar_try(b, parity)) spin_check_bar(spins);
     par ^= 1ull << i;
   };
-  // slot and tag of x_l at step t (real steps: ring position; priming passes: slot 0, pass parity)
-  auto x_slot = [&](int l, int t) -> int { return t < 0 ? 0 : (t & ((1 << p.rlog[l]) - 1)); };
+  // slot of x_l at step t (real steps: ring position)
+  // Priming passes alternate between slots 0 and 1 (every ring has at least two): a pass reads what the PREVIOUS pass wrote
+  // (slot (t - 1) & 1) while its own x goes to slot t & 1, so a past-tap copy that is still in flight when block j+1's
+  // finishers write can never see the newer value -- the result does not depend on how far a CTA's copies lag.
+  auto x_slot = [&](int l, int t) -> int { return t < 0 ? (t & 1) : (t & ((1 << p.rlog[l]) - 1)); };
   // every exchange word of a step carries the step's parity (independent of the batch: an utterance's symbols must not
   // depend on its batch-mates)
   auto x_tag = [&](int l, int t) -> unsigned { return (unsigned)(t + NP) & 1u; };
@@ -947,7 +950,7 @@ __global__ void __launch_bounds__(NT, 1) f3_gen_kernel(Plan p, GenArgsDev g) {
           const int u = ub + 8 * i;
           if (u < B) {
             const int k = kt ? (int)kt[u] : dl;
-            const int slot = t >= 0 ? ((t - k) & rmask) : 0;
+            const int slot = t >= 0 ? ((t - k) & rmask) : ((t - 1) & 1);
             cp_async16_s(dst + i * 1024, src + ((size_t)slot * UB + u) * (C / 8));
           }
         }

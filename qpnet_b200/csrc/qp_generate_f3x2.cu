@@ -11,10 +11,10 @@
 //   * per group: TMEM tiles (192 columns each + the head tiles = 448 of 512), cluster receive buffers, exchange buffers,
 //     rings, look-back table.  Shared: the three A-tile buffers, the weight slots (single-buffered), every role's warps.
 //   * the MMA thread issues Z(j,0) P(j,0) Z(j,1) P(j,1) -- a group's x-products between the groups' z-products -- and every
-//     staging role follows the same order.  The order is fixed on purpose: see the comment at the MMA loop (priming).
-//     What was tried and measured slower or wrong: a second issuing thread for the x-products and a non-blocking
-//     two-stream scheduler on one thread (both let z-products overtake x-products: run-to-run different symbols through
-//     priming, and no faster once priming was kept in order), starting the groups up to 8 us apart (no effect).
+//     staging role follows the same order.  What was tried and measured no faster: a second issuing thread for the
+//     x-products and a non-blocking two-stream scheduler on one thread (both let z-products overtake x-products; at the
+//     time a priming pass re-read the ring slot it rewrote one phase later, so a lagging past-tap copy changed the primed
+//     state run to run -- the passes now alternate slots 0 and 1, see x_slot), starting the groups up to 8 us apart.
 //   * the z-products of an item are ONE sequence of 8 UMMAs with N = 96 ([C_j | U_j | P_{j+1}]); the single-group kernel
 //     issues C_j separately first.  (256 utterances: 130.1 -> 129.5 us, 192: 123.5 -> 118.8 us per step.)
 //   * a ring slot is stored as the A tiles its readers stage, [4 K-shares][2 K-blocks][256 rows][128 B] with the 16-byte
@@ -604,7 +604,10 @@ __global__ void __launch_bounds__(NT, 1) f3x2_gen_kernel(Plan p, GenArgsDev g) {
   };
   // slot of x_l(t) in its ring (priming passes: slot 0); every exchange word of a step carries the step's parity
   // (independent of the batch: an utterance's symbols must not depend on its batch-mates)
-  auto x_slot = [&](int l, int t) -> int { return t < 0 ? 0 : (t & ((1 << p.rlog[l]) - 1)); };
+  // Priming passes alternate between slots 0 and 1 (every ring has at least two): a pass reads what the PREVIOUS pass wrote
+  // (slot (t - 1) & 1) while its own x goes to slot t & 1, so a past-tap copy that is still in flight when block j+1's
+  // finishers write can never see the newer value -- the result does not depend on how far a CTA's copies lag.
+  auto x_slot = [&](int l, int t) -> int { return t < 0 ? (t & 1) : (t & ((1 << p.rlog[l]) - 1)); };
   // Stage this thread's pieces i < nl of a tagged vector (piece i at src + i * sstep) at dst + i * dstep: cp.async copies
   // them global (L2) -> shared without holding registers for 16 loads in flight; the tags are then checked on the staged
   // copy, and a round with a stale piece is simply repeated.
@@ -1030,7 +1033,7 @@ __global__ void __launch_bounds__(NT, 1) f3x2_gen_kernel(Plan p, GenArgsDev g) {
         if (jb < p.nF) {
           // fixed look-back: every utterance reads the same slot, the tile is two contiguous 16 KB runs of the ring
           if (i128 == 0) {
-            const uint32_t* src = ring + (size_t)(t >= 0 ? ((t - p.dil[jb]) & rmask) : 0) * UT * (C / 2);
+            const uint32_t* src = ring + (size_t)(t >= 0 ? ((t - p.dil[jb]) & rmask) : ((t - 1) & 1)) * UT * (C / 2);
             mbar_expect_tx(bar(B_XPFULL), 2 * ABLK);
             bulk_g2s_plain(sbase + SM_XP, src, ABLK, bar(B_XPFULL));
             bulk_g2s_plain(sbase + SM_XP + ABLK, src + (size_t)UT * 32, ABLK, bar(B_XPFULL));
@@ -1047,7 +1050,7 @@ __global__ void __launch_bounds__(NT, 1) f3x2_gen_kernel(Plan p, GenArgsDev g) {
           for (int i = 0; i < 16; ++i) {
             const int u = ub + 8 * i;
             if (u < Bg) {
-              const int slot = t >= 0 ? ((t - (int)kt[u]) & rmask) : 0;
+              const int slot = t >= 0 ? ((t - (int)kt[u]) & rmask) : ((t - 1) & 1);
               cp_async16_s(dst + i * 1024, src + (size_t)slot * UT * (C / 2) + u * 32);
             }
           }
@@ -1113,10 +1116,9 @@ __global__ void __launch_bounds__(NT, 1) f3x2_gen_kernel(Plan p, GenArgsDev g) {
           for (int ks = 0; ks < 4; ++ks) umma(tmem + dcol, ad + 2 * ks, bd + 2 * ks, idesc, (fresh && kb == 0 && ks == 0) ? 0u : 1u);
         }
       };
-      // Issue order.  It is fixed, and every role stages and consumes in the same order: the priming passes read the ring
-      // slot the same pass rewrites one phase later (the past tap of block j+1 is staged in phase j, x_{j+1} is written in
-      // phase j+1), so an order in which the x-products could fall behind the next z-products changes what priming
-      // converges through (measured: run-to-run different symbols).
+      // Issue order: fixed, Z(j,0) P(j,0) Z(j,1) P(j,1); every role stages and consumes in the same order.  (Orders in which the
+      // x-products may fall behind the next z-products -- a second issuing thread, a non-blocking scheduler -- were not
+      // faster, and before the priming passes alternated ring slots (x_slot) they changed what priming converged through.)
       for (int t = -NP; t < g.max_steps; ++t) {
         {   // phase 0: P_1 (buffer 0) <- Wp_1 x_1(t-k), both groups on one chunk
           waitb(B_WPW_FULL);
