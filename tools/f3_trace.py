@@ -110,6 +110,18 @@ def main():
         print("--- both groups, z staged (min .. max over CTAs) and z published, ns:")
         for j in range(1, L):
             print(f"blk{j:02d} " + " | ".join(f"g{g} staged {np.nanmin(gt2[:, j, g, 1]) - t0:8.0f} .. {np.nanmax(gt2[:, j, g, 1]) - t0:8.0f} published {np.nanmin(gt2[:, j, g, 0]) - t0:8.0f} .. {np.nanmax(gt2[:, j, g, 0]) - t0:8.0f}" for g in range(2)))
+        # are the CTAs split into camps that serve the groups in opposite phase?  per CTA: when it staged z of block 6 for
+        # each group (relative to the first CTA), and the distance between its two groups
+        j = 6
+        s0, s1 = gt2[:, j, 0, 1] - np.nanmin(gt2[:, j, 0, 1]), gt2[:, j, 1, 1] - np.nanmin(gt2[:, j, 0, 1])
+        bins = np.arange(0, 12001, 1000)
+        print("blk06 z staged, ns after the first CTA: histogram per 1 us bin")
+        print("   group 0:", np.histogram(s0[~np.isnan(s0)], bins)[0].tolist())
+        print("   group 1:", np.histogram(s1[~np.isnan(s1)], bins)[0].tolist())
+        dd = s1 - s0
+        print("   g1 - g0 per CTA: histogram per 1 us bin from -6 us:", np.histogram(dd[~np.isnan(dd)], np.arange(-6000, 6001, 1000))[0].tolist())
+        late = np.argsort(-s0)[:16]
+        print("   the 16 CTAs that stage group 0 last:", [(int(c), int(s0[c])) for c in late])
         for cta in (0, 1, 26, 112):
             print(f"CTA {cta}: " + "  ".join(f"j{j}: g0 {gt2[cta, j, 0, 1] - t0:.0f} g1 {gt2[cta, j, 1, 1] - t0:.0f}" for j in range(3, 8)))
     tot = np.mean([tr[st + 1, 0, 5] - tr[st, 0, 5] for st in range(1, 7)])
