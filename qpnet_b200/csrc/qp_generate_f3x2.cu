@@ -165,6 +165,8 @@ struct Plan {
   int16_t* pcm_lut;       // [Q] decode_mu_law(symbol) * 32768 clipped to int16 (qpnet_decode.py:315-318)
   void* tagged_begin; size_t tagged_bytes;
   long long* trace; int trace_step0, trace_nsteps, trace_cta;
+  int nowait;             // debug (QPNET_F3_NOWAIT): no poll waits for fresh data -- wrong symbols, but the step time is then the CTAs' local
+                          // pipeline alone (profiles/r02ao_*: 107 of 131 us per step at 256 utterances)
   long long* gtrace;      // [NCTA][L + 4][NG][4] %globaltimer of one step, every CTA: 0 z published, 1 z staged, 2 partial rows arrived, 3 x published
 };
 
@@ -627,7 +629,7 @@ __global__ void __launch_bounds__(NT, 1) f3x2_gen_kernel(Plan p, GenArgsDev g) {
           asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];\n" : "=r"(x.x), "=r"(x.y), "=r"(x.z), "=r"(x.w) : "r"(dst_s + i * dstep) : "memory");
           bad |= (x.x ^ tag) | (x.y ^ tag) | (x.z ^ tag) | (x.w ^ tag);
         }
-      if (!(bad & 1u)) break;
+      if (!(bad & 1u) || p.nowait) break;
       spin_check(spins);
     }
   };
@@ -639,7 +641,7 @@ __global__ void __launch_bounds__(NT, 1) f3x2_gen_kernel(Plan p, GenArgsDev g) {
     unsigned spins = 0;
     while (true) {
       const unsigned v = ld_strong_u32(p.vsym + u * 32);
-      if (((v ^ want) & 0x40000000u) == 0) return (int)(v & 0xFFFFu) % Q;
+      if (((v ^ want) & 0x40000000u) == 0 || p.nowait) return (int)(v & 0xFFFFu) % Q;
       spin_check(spins);
     }
   };
@@ -1240,8 +1242,8 @@ __global__ void __launch_bounds__(NT, 1) f3x2_gen_kernel(Plan p, GenArgsDev g) {
           unsigned pend = 3;
           unsigned spins = 0;
           while (pend) {
-            if (pend & 1u) { a = ld_strong_v4(src); if (fresh4(a, par_t)) pend &= ~1u; }
-            if (pend & 2u) { b = ld_strong_v4(src + 1); if (fresh4(b, par_t)) pend &= ~2u; }
+            if (pend & 1u) { a = ld_strong_v4(src); if (fresh4(a, par_t) || p.nowait) pend &= ~1u; }
+            if (pend & 2u) { b = ld_strong_v4(src + 1); if (fresh4(b, par_t) || p.nowait) pend &= ~2u; }
             if (pend) spin_check(spins);
           }
           v[0] = __uint_as_float(a.x); v[1] = __uint_as_float(a.y); v[2] = __uint_as_float(a.z); v[3] = __uint_as_float(a.w);
@@ -1326,6 +1328,7 @@ int f3x2_generate(const QpArch* arch, const float* const* tensors_host, const Qp
   const bool tr = getenv("QPNET_GEN_TRACE_STEP") != nullptr;
   if (tr) p.trace_step0 = atoi(getenv("QPNET_GEN_TRACE_STEP"));
   if (const char* e = getenv("QPNET_GEN_TRACE_CTA")) p.trace_cta = atoi(e);
+  p.nowait = getenv("QPNET_F3_NOWAIT") ? 1 : 0;
   auto kern = tr ? f3x2::f3x2_gen_kernel<true> : f3x2::f3x2_gen_kernel<false>;
   QP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   cudaLaunchConfig_t cfg = {};
