@@ -133,7 +133,7 @@ constexpr int SM_END = SM_BH + 64;
 static_assert(SM_END + 1024 <= 227 * 1024, "shared memory budget");
 // mbarrier indices: shared ones, then per group ([2] = TMEM buffer by phase parity)
 constexpr int B_ZPW_FULL = 0, B_ZPW_FREE = 1, B_WCW_FULL = 2, B_WCW_FREE = 3, B_WPW_FULL = 4, B_WPW_FREE = 5,
-              B_ZFULL = 6, B_ZFREE = 7, B_XFULL = 8, B_XFREE = 9, B_XPFULL = 10, B_XPFREE = 11, B_GROUP0 = 12;
+              B_ZFULL = 6, B_ZFREE = 7, B_XFULL = 8, B_XFREE = 9, B_XPFULL = 10, B_XPFREE = 11, B_ZPOLL = 12, B_XPOLL = 13, B_GROUP0 = 14;
 constexpr int G_CFULL = 0, G_UFULL = 2, G_PFULL = 4, G_CFREE = 6, G_UFREE = 8, G_PFREE = 10, G_HFULL = 12,
               G_RT = 14, G_RU = 16, G_RH = 19, G_COUNT = 21;
 constexpr int B_COUNT = B_GROUP0 + NG * G_COUNT;
@@ -437,6 +437,13 @@ __device__ __forceinline__ void bulk_g2s_plain(unsigned dst, const void* src, un
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n"
                ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
 }
+// named barrier of n threads that also ORs a predicate over them
+__device__ __forceinline__ bool bar_or(int id, int n, bool pred) {
+  unsigned r;
+  asm volatile("{\n .reg .pred p, q;\n setp.ne.u32 p, %1, 0;\n bar.red.or.pred q, %2, %3, p;\n selp.u32 %0, 1, 0, q;\n}\n"
+               : "=r"(r) : "r"((unsigned)pred), "r"(id), "r"(n) : "memory");
+  return r != 0;
+}
 __device__ __forceinline__ void st_strong_v4(void* p, uint4 v) {
   asm volatile("st.relaxed.gpu.global.v4.u32 [%0], {%1,%2,%3,%4};\n" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
@@ -633,6 +640,39 @@ __global__ void __launch_bounds__(NT, 1) f3x2_gen_kernel(Plan p, GenArgsDev g) {
       spin_check(spins);
     }
   };
+  // The exchange buffers vz[l], vx[l] are stored as the A tiles their consumers stage (like the ring slots):
+  // [group][K-share 4][K-block 2][128 rows][128 B], the 16-byte pieces of a row in SWIZZLE_128B order.  Word offset of piece
+  // pw (0..63: 8 channels each) of utterance fu inside one vz[l] / vx[l]:
+  auto xoff = [&](int fu, int pw) -> size_t {
+    const int gi_ = fu / UB, u = fu % UB;
+    return ((size_t)(gi_ * 8 + (pw >> 3)) * UB + u) * 32 + 4 * ((pw ^ u) & 7);
+  };
+  // Poll a whole 32 KB tile (this rank's K-share of one group: contiguous in the exchange buffer) with ONE bulk copy per
+  // round: thread 0 of the role issues it, everyone waits on its mbarrier, checks the tags of its own pieces on the staged
+  // copy and a barrier with an OR reduction decides whether the round is repeated.  (2 048 cp.async of 16 bytes took
+  // ~3 k cycles per round; the tile has to be on its way anyway, and the copy engine moves it in one piece.)
+  auto poll_bulk = [&](const uint32_t* src, uint32_t dst, int pollbar, int named, int i128_, int nrows, unsigned tag) {
+    const int pc_ = i128_ & 15, ub_ = i128_ >> 4;       // this thread checks piece position pc_ of rows ub_ + 8 i
+    const uint32_t mine = dst + (uint32_t)((pc_ >> 3) * ABLK + ub_ * 128 + ((pc_ & 7) << 4));
+    unsigned spins = 0;
+    while (true) {
+      if (i128_ == 0) {
+        mbar_expect_tx(bar(pollbar), 2 * ABLK);
+        bulk_g2s_plain(dst, src, 2 * ABLK, bar(pollbar));
+      }
+      waitb(pollbar);
+      unsigned bad = 0;
+#pragma unroll
+      for (int i = 0; i < 16; ++i)
+        if (ub_ + 8 * i < nrows) {
+          uint4 x;
+          asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];\n" : "=r"(x.x), "=r"(x.y), "=r"(x.z), "=r"(x.w) : "r"(mine + i * 1024) : "memory");
+          bad |= (x.x ^ tag) | (x.y ^ tag) | (x.z ^ tag) | (x.w ^ tag);
+        }
+      if (!bar_or(named, 128, (bad & 1u) != 0) || p.nowait) break;
+      spin_check(spins);
+    }
+  };
   using N16 = std::integral_constant<int, 16>;
   using N8 = std::integral_constant<int, 8>;
   // fed-back symbol of utterance u for step t >= 1
@@ -666,7 +706,7 @@ __global__ void __launch_bounds__(NT, 1) f3x2_gen_kernel(Plan p, GenArgsDev g) {
       const unsigned w0 = pack_tagged(z[0], z[1], tag), w1 = pack_tagged(z[2], z[3], tag);
       const unsigned o0 = __shfl_down_sync(0xffffffffu, w0, 1), o1 = __shfl_down_sync(0xffffffffu, w1, 1);
       if (!(q & 1) && live)
-        st_strong_v4(p.vz + ((size_t)j * UT + fu) * (C / 2) + 8 * c + 4 * (q >> 1), make_uint4(w0, w1, o0, o1));
+        st_strong_v4(p.vz + (size_t)j * UT * (C / 2) + xoff(fu, 2 * c + (q >> 1)), make_uint4(w0, w1, o0, o1));
     };
 
     for (int t = -NP; t < g.max_steps; ++t) {
@@ -949,7 +989,7 @@ __global__ void __launch_bounds__(NT, 1) f3x2_gen_kernel(Plan p, GenArgsDev g) {
               const unsigned o0 = __shfl_down_sync(0xffffffffu, w0, 1), o1 = __shfl_down_sync(0xffffffffu, w1, 1);
               if (!(q & 1) && live) {
                 const uint4 piece = make_uint4(w0, w1, o0, o1);
-                st_strong_v4(p.vx + ((size_t)j * UT + fu) * (C / 2) + 8 * c + 4 * (q >> 1), piece);   // this step's consumers poll here
+                st_strong_v4(p.vx + (size_t)j * UT * (C / 2) + xoff(fu, 2 * c + (q >> 1)), piece);   // this step's consumers poll here
                 // the past taps of later steps read here.  A ring slot is stored as the A tiles its readers stage,
                 // [CL K-shares][2 K-blocks][UT rows][128 B], the 16-byte pieces of a row in SWIZZLE_128B order (piece ^ (row & 7)):
                 // the tile of a block with a fixed look-back is two contiguous 16 KB runs
@@ -986,12 +1026,8 @@ __global__ void __launch_bounds__(NT, 1) f3x2_gen_kernel(Plan p, GenArgsDev g) {
       for (int j = 1; j <= L; ++j) {
         for (int gi = 0; gi < ng; ++gi) {
           waitb(B_ZFREE);
-          // this rank's K-share of z_{j-1}: 16 pieces of 16 bytes per utterance; thread -> piece pc of utterances ub + 8 i
-          const int pc = i128 & 15, ub = i128 >> 4;
-          const uint4* src = (const uint4*)(p.vz + ((size_t)(j - 1) * UT + UB * gi + ub) * (C / 2)) + rank * 16 + pc;
           trace(t, gi, j, 11);
-          poll_tile(N16(), src, (size_t)8 * (C / 8), min(16, (gB(gi) - ub + 7) >> 3), tagz,
-                    sZ + (pc >> 3) * ABLK + ub * 128 + (((pc & 7) ^ ub) << 4), 1024);
+          poll_bulk(p.vz + (size_t)(j - 1) * UT * (C / 2) + (size_t)(gi * 8 + rank * 2) * UB * 32, sZ, B_ZPOLL, 2, i128, gB(gi), tagz);
           trace(t, gi, j, 6);
           gtrace(t, gi, j, 1);
           done();
@@ -1064,10 +1100,8 @@ __global__ void __launch_bounds__(NT, 1) f3x2_gen_kernel(Plan p, GenArgsDev g) {
     // x_jx of the current step (published during the previous phase) -> X tile
     auto stage_x = [&](int jx, int gi, int t) {
       waitb(B_XFREE);
-      const uint4* src0 = (const uint4*)(p.vx + ((size_t)jx * UT + UB * gi) * (C / 2)) + rank * 16 + pc;
       trace(t, gi, jx + 1, 19);
-      poll_tile(N16(), src0 + (size_t)ub * (C / 8), (size_t)8 * (C / 8), min(16, (gB(gi) - ub + 7) >> 3), (unsigned)(t + NP) & 1u,
-                sbase + SM_X + tile_off, 1024);
+      poll_bulk(p.vx + (size_t)jx * UT * (C / 2) + (size_t)(gi * 8 + rank * 2) * UB * 32, sbase + SM_X, B_XPOLL, 3, i128, gB(gi), (unsigned)(t + NP) & 1u);
       trace(t, gi, jx + 1, 21);
       fence_proxy_async();
       mbar_arrive(bar(B_XFULL));
