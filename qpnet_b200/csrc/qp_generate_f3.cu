@@ -91,7 +91,7 @@ static_assert(SM_END + 1024 <= 227 * 1024, "shared memory budget");
 constexpr int B_ZPW_FULL = 0, B_ZPW_FREE = 2, B_WCW_FULL = 4, B_WCW_FREE = 6, B_WPW_FULL = 8, B_WPW_FREE = 10,
               B_ZFULL = 12, B_ZFREE = 13, B_XFULL = 14, B_XFREE = 15, B_XPFULL = 16, B_XPFREE = 17,
               B_CFULL = 18, B_UFULL = 20, B_PFULL = 22, B_CFREE = 24, B_UFREE = 26, B_PFREE = 28, B_HFULL = 30,
-              B_RT = 32, B_RU = 34, B_RH = 37, B_COUNT = 39;
+              B_RT = 32, B_RU = 34, B_RH = 37, B_ZPOLL = 39, B_XPOLL = 40, B_COUNT = 41;
 static_assert(B_COUNT <= 48, "mbarrier area");
 constexpr int TM_COLS = 256;                           // TMEM columns: buffer b at 96 b: [C | U | P] 32 each; head at 192
 constexpr int TC_C = 0, TC_U = 32, TC_P = 64, TC_BUF = 96, TC_H = 192;
@@ -386,6 +386,17 @@ __device__ __forceinline__ void bulk_g2s(unsigned dst, const void* src, unsigned
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;\n"
                ::"r"(dst), "l"(src), "r"(bytes), "r"(bar), "l"(pol) : "memory");
 }
+__device__ __forceinline__ void bulk_g2s_plain(unsigned dst, const void* src, unsigned bytes, unsigned bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n"
+               ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+// named barrier of n threads that also ORs a predicate over them
+__device__ __forceinline__ bool bar_or(int id, int n, bool pred) {
+  unsigned r;
+  asm volatile("{\n .reg .pred p, q;\n setp.ne.u32 p, %1, 0;\n bar.red.or.pred q, %2, %3, p;\n selp.u32 %0, 1, 0, q;\n}\n"
+               : "=r"(r) : "r"((unsigned)pred), "r"(id), "r"(n) : "memory");
+  return r != 0;
+}
 __device__ __forceinline__ void st_strong_v4(void* p, uint4 v) {
   asm volatile("st.relaxed.gpu.global.v4.u32 [%0], {%1,%2,%3,%4};\n" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
@@ -555,36 +566,39 @@ __global__ void __launch_bounds__(NT, 1) f3_gen_kernel(Plan p, GenArgsDev g) {
   // every exchange word of a step carries the step's parity (independent of the batch: an utterance's symbols must not
   // depend on its batch-mates)
   auto x_tag = [&](int l, int t) -> unsigned { return (unsigned)(t + NP) & 1u; };
-  // Stage this thread's pieces i < nl of a tagged vector (piece i at src + i * sstep) at dst + i * dstep.  The thread first
-  // spins on `flags` (the step counters of the four CTAs of the producing cluster, one 16-byte load) until the live ranks
-  // show `want`; then it loads the pieces and verifies every tag (a flag may overtake its data: then it simply re-loads).
-  auto poll_tile = [&](auto nconst, const uint4* src, size_t sstep, int nl, unsigned tag, unsigned char* dst, int dstep,
-                       int tr_t, int tr_ph, int tr_ev) {
-    constexpr int N = decltype(nconst)::value;
-    if (nl <= 0) return;
+  // The exchange buffers vz[l], vx[l] (and the head's v256) are stored as the A tiles their consumers stage:
+  // [K-share 4][K-block 2][128 rows][128 B], the 16-byte pieces of a row in SWIZZLE_128B order.  Word offset of piece pw
+  // (0..63: 8 channels each; 0..31 for the 256-vectors, one K-block per rank) of utterance u inside one vz[l] / vx[l]:
+  auto xoff = [&](int u, int pw) -> size_t { return ((size_t)(pw >> 3) * UB + u) * 32 + 4 * ((pw ^ u) & 7); };
+  // A polling round is ONE bulk copy of this rank's tile (nkb K-blocks of 16 KB, contiguous in the exchange buffer) straight
+  // into the A tile: thread 0 of the role issues it, everyone waits on its mbarrier, verifies the tags of its own pieces on
+  // the staged copy, and a barrier with an OR reduction decides whether the round is repeated.  (2 048 cp.async of 16
+  // bytes per round took ~3 k cycles even when every piece was there.)
+  auto poll_bulk = [&](const uint32_t* src, uint32_t dst, int nkb, int pollbar, int named, int i128_, int nrows, unsigned tag) {
+    // two K-blocks: piece position pc_ (K-block pc_ >> 3) of rows ub_ + 8 i; one K-block: position pc_ of rows ub_ + 16 i
+    const int pc_ = nkb == 2 ? (i128_ & 15) : (i128_ & 7), ub_ = nkb == 2 ? (i128_ >> 4) : (i128_ >> 3);
+    const int rstep = nkb == 2 ? 8 : 16, n_i = nkb == 2 ? 16 : 8;
+    const uint32_t mine = dst + (uint32_t)(nkb == 2 ? (pc_ >> 3) * ABLK + ub_ * 128 + ((pc_ & 7) << 4)
+                                                      : (ub_ >> 3) * 1024 + (ub_ & 7) * 128 + (pc_ << 4));
     unsigned spins = 0; long long t0 = 0;
-    if (tr_ev >= 0) trace(tr_t, tr_ph, tr_ev);
-    // cp.async copies the pieces global (L2) -> shared without holding registers for 16 loads in flight; the tags are
-    // then checked on the staged copy, and a round with a stale piece is simply repeated
-    const uint32_t dst_s = smem_u32(dst);
     while (true) {
-#pragma unroll
-      for (int i = 0; i < N; ++i) if (i < nl) cp_async16_s(dst_s + i * dstep, src + (size_t)i * sstep);
-      asm volatile("cp.async.wait_all;\n" ::: "memory");
+      if (i128_ == 0) {
+        mbar_expect_tx(bar(pollbar), nkb * ABLK);
+        bulk_g2s_plain(dst, src, nkb * ABLK, bar(pollbar));
+      }
+      waitb(pollbar);
       unsigned bad = 0;
 #pragma unroll
-      for (int i = 0; i < N; ++i)
-        if (i < nl) {
+      for (int i = 0; i < 16; ++i)
+        if (i < n_i && ub_ + rstep * i < nrows) {
           uint4 x;
-          asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];\n" : "=r"(x.x), "=r"(x.y), "=r"(x.z), "=r"(x.w) : "r"(dst_s + i * dstep) : "memory");
+          asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];\n" : "=r"(x.x), "=r"(x.y), "=r"(x.z), "=r"(x.w) : "r"(mine + i * (rstep * 128)) : "memory");
           bad |= (x.x ^ tag) | (x.y ^ tag) | (x.z ^ tag) | (x.w ^ tag);
         }
-      if (!(bad & 1u)) break;
+      if (!bar_or(named, 128, (bad & 1u) != 0)) break;
       spin_check(spins, t0);
     }
   };
-  using N16 = std::integral_constant<int, 16>;
-  using N8 = std::integral_constant<int, 8>;
 
   if (warp < 4) {
     // ======================================================================================= ET: C + P tiles, z_j, head
@@ -607,7 +621,7 @@ __global__ void __launch_bounds__(NT, 1) f3_gen_kernel(Plan p, GenArgsDev g) {
       const unsigned w0 = pack_tagged(z[0], z[1], tag), w1 = pack_tagged(z[2], z[3], tag);
       const unsigned o0 = __shfl_down_sync(0xffffffffu, w0, 1), o1 = __shfl_down_sync(0xffffffffu, w1, 1);
       if (!(q & 1) && live)
-        st_strong_v4(p.vz + ((size_t)j * UB + fu) * (C / 2) + 8 * c + 4 * (q >> 1), make_uint4(w0, w1, o0, o1));
+        st_strong_v4(p.vz + (size_t)j * UB * (C / 2) + xoff(fu, 2 * c + (q >> 1)), make_uint4(w0, w1, o0, o1));
     };
 
     for (int t = -NP; t < g.max_steps; ++t) {
@@ -769,7 +783,7 @@ __global__ void __launch_bounds__(NT, 1) f3_gen_kernel(Plan p, GenArgsDev g) {
               const unsigned w0 = pack_tagged(fmaxf(s0, 0.f), fmaxf(s1, 0.f), par_t);
               const unsigned w1 = __shfl_down_sync(0xffffffffu, w0, 1), w2 = __shfl_down_sync(0xffffffffu, w0, 2),
                              w3 = __shfl_down_sync(0xffffffffu, w0, 3);
-              if (q == 0 && live) st_strong_v4(p.v256 + ((size_t)UB + fu) * (S / 2) + 4 * c, make_uint4(w0, w1, w2, w3));
+              if (q == 0 && live) st_strong_v4(p.v256 + (size_t)UB * (S / 2) + xoff(fu, c), make_uint4(w0, w1, w2, w3));
             } else if (live) {
               st_strong_v2(p.vlog + (size_t)fu * Q + 8 * c + 2 * q, (__float_as_uint(s0) & ~1u) | par_t, (__float_as_uint(s1) & ~1u) | par_t);
             }
@@ -869,7 +883,7 @@ __global__ void __launch_bounds__(NT, 1) f3_gen_kernel(Plan p, GenArgsDev g) {
             const unsigned o0 = __shfl_down_sync(0xffffffffu, w0, 1), o1 = __shfl_down_sync(0xffffffffu, w1, 1);
             if (!(q & 1) && live) {
               const uint4 piece = make_uint4(w0, w1, o0, o1);
-              st_strong_v4(p.vx + ((size_t)j * UB + fu) * (C / 2) + 8 * c + 4 * (q >> 1), piece);   // this step's consumers poll here
+              st_strong_v4(p.vx + (size_t)j * UB * (C / 2) + xoff(fu, 2 * c + (q >> 1)), piece);   // this step's consumers poll here
               uint32_t* dstp = p.xr[j] + (size_t)fu * (C / 2) + 8 * c + 4 * (q >> 1);                 // the past taps of later steps read here
               if (t == -1) {   // the last priming pass fills the whole ring with the constant
                 const int R = 1 << p.rlog[j];
@@ -883,7 +897,7 @@ __global__ void __launch_bounds__(NT, 1) f3_gen_kernel(Plan p, GenArgsDev g) {
             const unsigned w0 = pack_tagged(fmaxf(sk0, 0.f), fmaxf(sk1, 0.f), par_t);
             const unsigned w1 = __shfl_down_sync(0xffffffffu, w0, 1), w2 = __shfl_down_sync(0xffffffffu, w0, 2),
                            w3 = __shfl_down_sync(0xffffffffu, w0, 3);
-            if (q == 0 && live) st_strong_v4(p.v256 + (size_t)fu * (S / 2) + 4 * c, make_uint4(w0, w1, w2, w3));
+            if (q == 0 && live) st_strong_v4(p.v256 + xoff(fu, c), make_uint4(w0, w1, w2, w3));
           }
         }
         trace(t, j, 16);
@@ -900,12 +914,8 @@ __global__ void __launch_bounds__(NT, 1) f3_gen_kernel(Plan p, GenArgsDev g) {
       const unsigned tagz = (unsigned)(t + NP) & 1u;
       for (int j = 1; j <= L; ++j) {
         waitb(B_ZFREE);
-        // this rank's K-share of z_{j-1}: 16 pieces of 16 bytes per utterance; thread -> piece pc of utterances ub + 8 i
-        const int pc = i128 & 15, ub = i128 >> 4;
-        const uint4* src = (const uint4*)(p.vz + ((size_t)(j - 1) * UB + ub) * (C / 2)) + rank * 16 + pc;
-        unsigned char* dst = sZ + (pc >> 3) * ABLK + ub * 128 + (((pc & 7) ^ ub) << 4);
         trace(t, j, 11);
-        poll_tile(N16(), src, (size_t)8 * (C / 8), min(16, (B - ub + 7) >> 3), tagz, dst, 1024, t, j, 12);
+        poll_bulk(p.vz + (size_t)(j - 1) * UB * (C / 2) + (size_t)(rank * 2) * UB * 32, smem_u32(sZ), 2, B_ZPOLL, 2, i128, B, tagz);
         trace(t, j, 6);
         gtrace(t, j, 1);
         done();
@@ -914,11 +924,7 @@ __global__ void __launch_bounds__(NT, 1) f3_gen_kernel(Plan p, GenArgsDev g) {
         const unsigned par_t = (unsigned)t & 1u;
         for (int hd = 0; hd < 2; ++hd) {
           waitb(B_ZFREE);
-          // K-share of a 256-vector: 8 pieces per utterance; thread -> piece pc of utterances ub + 16 i
-          const int pc = i128 & 7, ub = i128 >> 3;
-          const uint4* src = (const uint4*)(p.v256 + ((size_t)hd * UB + ub) * (S / 2)) + rank * 8 + pc;
-          unsigned char* dst = sZ + (ub >> 3) * 1024 + (ub & 7) * 128 + ((pc ^ (ub & 7)) << 4);
-          poll_tile(N8(), src, (size_t)16 * (S / 8), min(8, (B - ub + 15) >> 4), par_t, dst, 2048, t, 0, -1);
+          poll_bulk(p.v256 + (size_t)hd * UB * (S / 2) + (size_t)rank * UB * 32, smem_u32(sZ), 1, B_ZPOLL, 2, i128, B, par_t);
           done();
         }
       }
@@ -961,11 +967,9 @@ __global__ void __launch_bounds__(NT, 1) f3_gen_kernel(Plan p, GenArgsDev g) {
     // x_jx of the current step (published during the previous phase) -> X tile
     auto stage_x = [&](int jx, int t) {
       waitb(B_XFREE);
-      unsigned char* dst = sm + SM_X + tile_off;
       const unsigned tag = x_tag(jx, t);
-      const uint4* src0 = (const uint4*)(p.vx + (size_t)jx * UB * (C / 2)) + rank * 16 + pc;
       trace(t, jx + 1, 19);
-      poll_tile(N16(), src0 + (size_t)ub * (C / 8), (size_t)8 * (C / 8), min(16, (B - ub + 7) >> 3), tag, dst, 1024, t, jx + 1, 20);
+      poll_bulk(p.vx + (size_t)jx * UB * (C / 2) + (size_t)(rank * 2) * UB * 32, smem_u32(sm + SM_X), 2, B_XPOLL, 3, i128, B, tag);
       trace(t, jx + 1, 21);
       fence_proxy_async();
       mbar_arrive(bar(B_XFULL));
