@@ -31,14 +31,18 @@
 //   finishing threads, b (V 1) is folded into the bias.  Block 0 reads the causal layer, a function of the last three
 //   symbols: three table lookups and no exchange at all; blocks 1 and 2 reach x_0 through two more tables.
 // * Exchange words carry a 1-bit epoch tag (LSB of the low bf16 / of the fp32 logit), so a consumer never needs a fence: it
-//   polls the data itself -- cp.async straight into the swizzled A tile, no registers held for the loads in flight -- and
-//   verifies the tags of the staged copy.  (A flag-then-load variant, where a consumer first spins on step counters its
-//   producers write after their pieces, moved less data and was slower: one more round trip, profiles/r02g_*.)
+//   polls the data itself.  The exchange buffers (and the ring slots) are stored as the A tiles their consumers stage
+//   ([K-share][K-block][128 rows][128 B], pieces in SWIZZLE_128B order), so a polling round is ONE 32 KB cp.async.bulk
+//   straight into the tile (no registers held, no per-piece instructions); the role's threads then verify the tags of the
+//   staged copy and a barrier with an OR reduction decides whether to repeat the round.  Before, a round was 2 048
+//   cp.async of 16 bytes and took ~3 k cycles even when every piece was there (128 utterances: 80 -> 74 us per step).
+//   (A flag-then-load variant, where a consumer first spins on step counters its producers write after their pieces,
+//   moved less data and was slower: one more round trip, profiles/r02g_*.)
 // * Warp roles (19 warps, no CTA-wide barrier inside the time loop; everything meets through mbarriers):
 //     0-3   ET   T tiles: tcgen05.ld -> partial rows -> finishers of z_j, the two head layers
 //     4-7   EU   U tiles: partial rows -> fp32 residual / skip state, x_j and relu(skip sum) published
-//     8-11  PZ   poll z_{j-1} (and the head's 256-vectors) -> A tile
-//     12-15 PX   poll x_{j-1} -> A tile; gather the past taps x_{j+1}(t-k) -> A tile (cp.async, completion on an mbarrier)
+//     8-11  PZ   poll z_{j-1} (and the head's 256-vectors) -> A tile (bulk copy per round + tag check)
+//     12-15 PX   poll x_{j-1} -> A tile; the past taps x_{j+1}(t-k) -> A tile (one bulk copy; adaptive blocks: cp.async gather)
 //     16    MMA  one thread issues every tcgen05.mma and releases buffers with tcgen05.commit
 //     17    LOAD one thread streams the weight chunks of the next phase (cp.async.bulk, two slot groups, L2 evict_last)
 //     18    SAMP softmax + inverse-CDF / arg-max of utterance blockIdx.x (qpnet.py:507-512), symbol fed back
@@ -111,7 +115,7 @@ struct Plan {
   float* T12;             // [NCL][2][2][Q][32] Wc_1 x_0, Wc_2 x_0: tap 0 = newest symbol (E1 + bias), tap 1 = previous (E0)
   float* Eo;              // [NCL][2][Q][16]    causal-layer rows of the cluster's channels (bias folded into tap 1)
   float* Paux;            // [NCTA][L][32 utt][32 rows]  V h_f of the finishing CTA's utterances, per frame
-  uint32_t* xr[MAXL];     // [1 << rlog][UB][C / 2]  x_l(t) ring, tagged words
+  uint32_t* xr[MAXL];     // [1 << rlog][CL][2][UB][32]  x_l(t) ring, tagged words, a slot laid out as its readers' A tiles
   uint32_t* vz;           // [L][UB][C / 2]
   uint32_t* vx;           // [L][UB][C / 2]  x_l of the current step (the ring copy serves the past taps)
   uint32_t* v256;         // [2][UB][S / 2]   0: relu(skip sum), 1: relu(head-1)
@@ -884,7 +888,7 @@ __global__ void __launch_bounds__(NT, 1) f3_gen_kernel(Plan p, GenArgsDev g) {
             if (!(q & 1) && live) {
               const uint4 piece = make_uint4(w0, w1, o0, o1);
               st_strong_v4(p.vx + (size_t)j * UB * (C / 2) + xoff(fu, 2 * c + (q >> 1)), piece);   // this step's consumers poll here
-              uint32_t* dstp = p.xr[j] + (size_t)fu * (C / 2) + 8 * c + 4 * (q >> 1);                 // the past taps of later steps read here
+              uint32_t* dstp = p.xr[j] + xoff(fu, 2 * c + (q >> 1));   // the past taps of later steps read here: a ring slot is a tile too
               if (t == -1) {   // the last priming pass fills the whole ring with the constant
                 const int R = 1 << p.rlog[j];
                 for (int sl = 0; sl < R; ++sl) st_strong_v4(dstp + (size_t)sl * UB * (C / 2), piece);
@@ -947,20 +951,32 @@ __global__ void __launch_bounds__(NT, 1) f3_gen_kernel(Plan p, GenArgsDev g) {
         fence_proxy_async();
         mbar_arrive(bar(B_XPFULL));
       } else {
-        const int rmask = (1 << p.rlog[jb]) - 1, dl = p.dil[jb];
-        const unsigned short* kt = jb >= p.nF ? sK + (jb - p.nF) * UB : nullptr;   // pitch-dependent look-backs of this step
-        const uint32_t dst = sbase + SM_XP + tile_off;
-        const uint4* src = (const uint4*)p.xr[jb] + rank * 16 + pc;
-#pragma unroll 4
-        for (int i = 0; i < 16; ++i) {
-          const int u = ub + 8 * i;
-          if (u < B) {
-            const int k = kt ? (int)kt[u] : dl;
-            const int slot = t >= 0 ? ((t - k) & rmask) : ((t - 1) & 1);
-            cp_async16_s(dst + i * 1024, src + ((size_t)slot * UB + u) * (C / 8));
+        const uint32_t* ring = p.xr[jb] + (size_t)rank * 2 * UB * 32;    // + slot * UB * (C / 2) + kb * UB * 32 + row * 32
+        const int rmask = (1 << p.rlog[jb]) - 1;
+        if (jb < p.nF) {
+          // fixed look-back: every utterance reads the same slot, this rank's tile is 32 contiguous KB of the ring
+          if (i128 == 0) {
+            const uint32_t* src = ring + (size_t)(t >= 0 ? ((t - p.dil[jb]) & rmask) : ((t - 1) & 1)) * UB * (C / 2);
+            mbar_expect_tx(bar(B_XPFULL), 2 * ABLK);
+            bulk_g2s_plain(sbase + SM_XP, src, 2 * ABLK, bar(B_XPFULL));
+          } else {
+            mbar_arrive(bar(B_XPFULL));
           }
+        } else {
+          // pitch-dependent look-backs of this step: piece by piece, one slot per utterance
+          const unsigned short* kt = sK + (jb - p.nF) * UB;
+          const uint32_t dst = sbase + SM_XP + (uint32_t)((pc >> 3) * ABLK + ub * 128 + ((pc & 7) << 4));
+          const uint32_t* src = ring + (size_t)(pc >> 3) * UB * 32 + 4 * (pc & 7);
+#pragma unroll 4
+          for (int i = 0; i < 16; ++i) {
+            const int u = ub + 8 * i;
+            if (u < B) {
+              const int slot = t >= 0 ? ((t - (int)kt[u]) & rmask) : ((t - 1) & 1);
+              cp_async16_s(dst + i * 1024, src + (size_t)slot * UB * (C / 2) + u * 32);
+            }
+          }
+          cp_async_arrive_noinc(bar(B_XPFULL));
         }
-        cp_async_arrive_noinc(bar(B_XPFULL));
       }
       trace(t, jb - 1, 18);
     };
