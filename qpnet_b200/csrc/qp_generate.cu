@@ -813,8 +813,8 @@ int f3x2_trace_copy(const QpArch* arch, int B, int M, void* ws, size_t ws_bytes,
 int pcm16_rows(const int32_t* sym, long long ld, int B, int n_steps, int n_quantize, int16_t* out, long long ld_out, cudaStream_t st);   // qp_util.cu
 static thread_local int g_last_kernel = 0;   // 5: tcgen05, two groups (f3x2), 4: tcgen05 (f3), 3: two-level folded mma.sync (fold2), 0: generic
 // QPNET_GEN_KERNEL = f3x2 | f3 | fold2 | generic selects the generator (debugging / A-B timing).  Default: the mma.sync
-// kernel up to 32 utterances (44 us per sample step), the tcgen05 kernel up to 128 (80 us at 128), its two-group variant
-// up to 256 (131 us at 256; profiles/r02x_*), the generic kernel for everything else
+// kernel up to 32 utterances (44 us per sample step), the tcgen05 kernel up to 128 (74 us at 128), its two-group variant
+// up to 256 (114 us at 256; profiles/r02x_*), the generic kernel for everything else
 static int wanted_kernel(const QpArch* arch, int B) {
   const char* e = getenv("QPNET_GEN_KERNEL");
   int want = (B <= 32 && f2_supported(arch, B)) ? 3 : (B <= 128 ? 4 : 5);

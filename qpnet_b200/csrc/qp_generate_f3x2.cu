@@ -3,8 +3,8 @@
 // Why a second kernel: a sample step is a chain of L + 3 cross-SM exchanges and ~60 % of a phase is waiting (store -> L2
 // -> polled load, the cluster reduction, skew between CTAs).  Here every role works through the items of a step in the
 // order (phase, group), so one group's tiles are computed while the other group's exchange is in flight; one weight chunk
-// load serves both groups.  256 utterances cost 131 us per sample step against 80 us for 128 in qp_generate_f3.cu
-// (profiles/r02x_*): 1.23 x the throughput per GPU.  Below 129 utterances qp_generate_f3.cu is faster (its weight slots
+// load serves both groups.  256 utterances cost 114 us per sample step against 74 us for 128 in qp_generate_f3.cu
+// (profiles/r02x_*): 1.30 x the throughput per GPU.  Below 129 utterances qp_generate_f3.cu is faster (its weight slots
 // are double-buffered; here the second group's TMEM tiles and receive buffers take that shared memory).
 //
 // What differs from qp_generate_f3.cu (read that file's header first; everything not listed is the same design):
@@ -170,7 +170,7 @@ struct Plan {
   void* tagged_begin; size_t tagged_bytes;
   long long* trace; int trace_step0, trace_nsteps, trace_cta;
   int nowait;             // debug (QPNET_F3_NOWAIT): no poll waits for fresh data -- wrong symbols, but the step time is then the CTAs' local
-                          // pipeline alone (profiles/r02ao_*: 107 of 131 us per step at 256 utterances)
+                          // pipeline alone (profiles/r02ao_*: 107 of 131 us per step at 256 utterances; with the bulk polling rounds 97 of 114)
   long long* gtrace;      // [NCTA][L + 4][NG][4] %globaltimer of one step, every CTA: 0 z published, 1 z staged, 2 partial rows arrived, 3 x published
 };
 
