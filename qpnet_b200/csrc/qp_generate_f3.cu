@@ -587,8 +587,15 @@ __global__ void __launch_bounds__(NT, 1) f3_gen_kernel(Plan p, GenArgsDev g) {
     unsigned spins = 0; long long t0 = 0;
     while (true) {
       if (i128_ == 0) {
-        mbar_expect_tx(bar(pollbar), nkb * ABLK);
-        bulk_g2s_plain(dst, src, nkb * ABLK, bar(pollbar));
+        // a ragged group: only the 8-row atoms that hold utterances (the first ceil(nrows / 8) KB of each K-block)
+        const unsigned kbytes = nrows >= UB ? (unsigned)ABLK : (unsigned)((nrows + 7) >> 3) * 1024u;
+        if (kbytes == (unsigned)ABLK) {
+          mbar_expect_tx(bar(pollbar), nkb * ABLK);
+          bulk_g2s_plain(dst, src, nkb * ABLK, bar(pollbar));
+        } else {
+          mbar_expect_tx(bar(pollbar), nkb * kbytes);
+          for (int kb = 0; kb < nkb; ++kb) bulk_g2s_plain(dst + kb * ABLK, src + (size_t)kb * UB * 32, kbytes, bar(pollbar));
+        }
       }
       waitb(pollbar);
       unsigned bad = 0;

@@ -638,8 +638,16 @@ __global__ void __launch_bounds__(NT, 1) f3x2_gen_kernel(Plan p, GenArgsDev g) {
     unsigned spins = 0;
     while (true) {
       if (i128_ == 0) {
-        mbar_expect_tx(bar(pollbar), 2 * ABLK);
-        bulk_g2s_plain(dst, src, 2 * ABLK, bar(pollbar));
+        // a ragged group: only the 8-row atoms that hold utterances (the first ceil(nrows / 8) KB of each K-block)
+        const unsigned kbytes = nrows >= UB ? (unsigned)ABLK : (unsigned)((nrows + 7) >> 3) * 1024u;
+        if (kbytes == (unsigned)ABLK) {
+          mbar_expect_tx(bar(pollbar), 2 * ABLK);
+          bulk_g2s_plain(dst, src, 2 * ABLK, bar(pollbar));
+        } else {
+          mbar_expect_tx(bar(pollbar), 2 * kbytes);
+          bulk_g2s_plain(dst, src, kbytes, bar(pollbar));
+          bulk_g2s_plain(dst + ABLK, src + (size_t)UB * 32, kbytes, bar(pollbar));
+        }
       }
       waitb(pollbar);
       unsigned bad = 0;
@@ -666,8 +674,9 @@ __global__ void __launch_bounds__(NT, 1) f3x2_gen_kernel(Plan p, GenArgsDev g) {
     unsigned spins = 0;
     while (true) {
       if (i128_ == 0) {
-        mbar_expect_tx(bar(pollbar), ABLK);
-        bulk_g2s_plain(dst, src, ABLK, bar(pollbar));
+        const unsigned kbytes = nrows >= UB ? (unsigned)ABLK : (unsigned)((nrows + 7) >> 3) * 1024u;
+        mbar_expect_tx(bar(pollbar), kbytes);
+        bulk_g2s_plain(dst, src, kbytes, bar(pollbar));
       }
       waitb(pollbar);
       unsigned bad = 0;
