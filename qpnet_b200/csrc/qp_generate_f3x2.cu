@@ -16,7 +16,8 @@
 //     time a priming pass re-read the ring slot it rewrote one phase later, so a lagging past-tap copy changed the primed
 //     state run to run -- the passes now alternate slots 0 and 1, see x_slot), starting the groups up to 8 us apart.
 //   * the z-products of an item are ONE sequence of 8 UMMAs with N = 96 ([C_j | U_j | P_{j+1}]); the single-group kernel
-//     issues C_j separately first.  (256 utterances: 130.1 -> 129.5 us, 192: 123.5 -> 118.8 us per step.)
+//     issues C_j separately first (and is 6 us per step slower with one sequence).  Here, with the bulk polling rounds:
+//     256 utterances 121.3 -> 114.1 us per step, 192 utterances 117.1 -> 107.9.
 //   * a ring slot is stored as the A tiles its readers stage, [4 K-shares][2 K-blocks][256 rows][128 B] with the 16-byte
 //     pieces of a row in SWIZZLE_128B order: the past-tap tile of a block with a fixed look-back is two contiguous 16 KB
 //     cp.async.bulk copies issued by one thread (adaptive blocks gather 16-byte pieces with cp.async, one slot per
